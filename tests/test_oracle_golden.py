@@ -1,0 +1,158 @@
+"""Pin the CPU oracle against the reference's golden vectors (no GPU needed).
+
+Bar: bit-exact for neighbour lists / LENS / coordination numbers; SOAP |d| <= 1e-9 * max|p|
+(the oracle is float64 throughout; the reference files were produced by DScribe, whose rounding
+differs); timeSOAP within 1e-7 absolute (the sqrt(2-2cos) noise floor).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+from golden_cases import fluid_case, random_csr_cases, random_soap_spectra
+
+from oracle import lens_oracle as lo
+from oracle import soap_oracle as so
+from oracle import timesoap_oracle as to
+
+# case id -> (r_cut, delay, centre indices, env indices); reference tests/lens/conftest.py:6-74
+LENS_CASES = {
+    "c0": (3, 1, None, None),
+    "c1": (4, 1, None, None),
+    "c2": (4, 1, [0], None),  # centers="id 1"
+    "c3": (4, 1, None, [0]),  # selection="id 1"
+    "c4": (4, 1, None, None),  # n_jobs=2
+    "c5": (4, 2, None, None),
+}
+NN_CASES = {k: v for k, v in LENS_CASES.items() if k != "c5"}  # tests/neighbors/conftest.py:6-59
+
+
+def test_trj_lens_and_nc_bit_exact(balls7, ref_lens):
+    pos, dims = balls7["positions"], balls7["dims"]
+    assert np.array_equal(lo.compute_lens_arrays(pos, dims, 15.0), ref_lens["trj_lens"])
+    assert np.array_equal(lo.coord_number_arrays(pos, dims, 15.0), ref_lens["trj_n_c"])
+
+
+@pytest.mark.parametrize("case", sorted(LENS_CASES))
+def test_lens_cases(balls7, ref_lens, case):
+    r_cut, delay, cent, env = LENS_CASES[case]
+    got = lo.compute_lens_arrays(
+        balls7["positions"], balls7["dims"], r_cut, delay=delay, cent_idx=cent, env_idx=env
+    )
+    assert np.array_equal(got, ref_lens["lens_" + case])
+
+
+@pytest.mark.parametrize("case", sorted(NN_CASES))
+def test_nn_cases(balls7, ref_lens, case):
+    r_cut, _, cent, env = NN_CASES[case]
+    got = lo.coord_number_arrays(
+        balls7["positions"], balls7["dims"], r_cut, cent_idx=cent, env_idx=env
+    )
+    assert np.array_equal(got, ref_lens["nn_" + case])
+
+
+def lens_2d_inputs():
+    """tests/lens/test_lens.py:17-34 -- positions pass through an XYZ file (float32) and every
+    frame ends up with the *last* frame's extent as box."""
+    rng = np.random.default_rng(42)
+    coords = rng.random((100, 100, 3))
+    coords[..., 2] = 0.0
+    pos = coords.astype(np.float32)
+    ext = pos[99].max(axis=0) - pos[99].min(axis=0)
+    ext[2] = 0.5
+    dims = np.tile(np.concatenate([ext, [90, 90, 90]]).astype(np.float32), (100, 1))
+    return pos, dims
+
+
+@pytest.mark.parametrize("pbc", [True, False])
+def test_lens_2d(ref_lens, pbc):
+    pos, dims = lens_2d_inputs()
+    got = lo.compute_lens_arrays(pos, dims, 0.1, respect_pbc=pbc)
+    assert np.array_equal(got, ref_lens["lens_2d_pbc" if pbc else "lens_2d_fbc"])
+
+
+def test_numba_random_csr(numba_cases):
+    for k, case in enumerate(random_csr_cases()):
+        indptr, indices = lo.neighbors(
+            case["pos_env"], case["pos_cent"], case["r_cut"], case["box"], case["pbc"]
+        )
+        assert np.array_equal(indptr, numba_cases[f"csr{k}_indptr"]), k
+        assert np.array_equal(indices, numba_cases[f"csr{k}_indices"]), k
+
+
+def test_numba_fluid(numba_cases):
+    pos, box, r_cut = fluid_case()
+    dims = np.tile(np.concatenate([box, [90, 90, 90]]).astype(np.float32), (pos.shape[0], 1))
+    assert np.array_equal(lo.compute_lens_arrays(pos, dims, r_cut), numba_cases["fluid_lens"])
+    assert np.array_equal(lo.coord_number_arrays(pos, dims, r_cut), numba_cases["fluid_counts"])
+
+
+# reference tests/soap/conftest.py:6-74 (true parameters; file names of c1/c2 are misleading)
+SOAP_CASES = {
+    "soap_c0": (8.0, 4, 4, True, list(range(7))),
+    "soap_c1": (4.0, 4, 4, True, list(range(7))),
+    "soap_c2": (8.0, 6, 6, True, list(range(7))),
+    "soap_c3": (8.0, 4, 4, True, [0, 1, 2, 3, 5, 6]),  # "not name C5"
+    "soap_c4": (8.0, 4, 4, True, [2, 5]),  # "name C3 or name C6"
+    "soap_c5": (8.0, 4, 4, False, list(range(7))),
+    "trj_soap": (10.0, 8, 8, True, list(range(7))),
+}
+
+
+@pytest.mark.parametrize("case", sorted(SOAP_CASES))
+def test_soap_oracle_vs_dscribe_golden(balls7, ref_soap, case):
+    r_cut, n_max, l_max, pbc, cent = SOAP_CASES[case]
+    frames = np.arange(0, 201, 10)[:: (4 if case == "trj_soap" else 2)]
+    gold = ref_soap[case][:, :: (4 if case == "trj_soap" else 2)]
+    pos = balls7["positions"][frames]
+    cells = balls7["dims"][frames, :3] if pbc else None
+    got = so.soap_trajectory(pos, np.full(7, 6), np.asarray(cent), cells, r_cut, n_max, l_max)
+    assert got.shape == gold.shape
+    assert np.abs(got - gold).max() <= 1e-9 * np.abs(gold).max()
+
+
+def test_soap_doctest_known_answers(xyz60):
+    """saponify.py:86-87,174 and timesoap.py:50-52,115-116,172-173 (all rtol=1e-3)."""
+    pos = xyz60["positions"]
+    soap = so.soap_trajectory(pos, np.zeros(60, int), np.arange(60), None, 2.0, 8, 8)
+    assert np.isclose(soap[0].sum(), float(xyz60["kat_soap0_sum"]), atol=1e-6, rtol=1e-3)
+    assert so.fill_soap_vector(soap).shape[2] == int(xyz60["kat_full_len"])
+    assert np.isclose(
+        to.normalize_soap(soap)[0].sum(), float(xyz60["kat_norm0_sum"]), atol=1e-6, rtol=1e-3
+    )
+    assert np.isclose(
+        to.soap_distance(soap[0][0], soap[0][1]), float(xyz60["kat_dist01"]), atol=1e-6, rtol=1e-3
+    )
+    assert np.isclose(to.timesoap(soap).sum(), float(xyz60["kat_tsoap_sum"]), atol=1e-6, rtol=1e-3)
+
+
+def test_timesoap_oracle_vs_reference_module(numba_cases):
+    s = random_soap_spectra()
+    for delay in (1, 3):
+        assert np.array_equal(to.timesoap(s, delay), numba_cases[f"tsoap_d{delay}"])
+    assert np.array_equal(to.normalize_soap(s), numba_cases["tsoap_norm"])
+    with pytest.raises(ValueError, match="delay value outside bounds"):
+        to.timesoap(s, 0)
+    with pytest.raises(ValueError, match="delay value outside bounds"):
+        to.timesoap(s, s.shape[1])
+
+
+def test_tsoap_goldens_from_golden_soap(ref_soap):
+    """tSOAP goldens follow from the SOAP goldens through the oracle's timeSOAP where both are
+    stored on the same frames: trj_tsoap was computed from trj_soap (test_trj.py:104-106)."""
+    # Only frames 0::10 of SOAP are stored, so check the delay-1 identity on the oracle SOAP instead
+    # (done on GPU-side tests at full length); here pin shapes and value ranges.
+    assert ref_soap["trj_tsoap"].shape == (7, 200)
+    assert ref_soap["tsoap_c0"].shape == (7, 200)
+    assert ref_soap["tsoap_c2"].shape == (7, 197)
+    assert np.all(ref_soap["tsoap_c1"] == 0.0)
+
+
+def test_tsoap_chain_c0_and_c2(balls7, ref_soap):
+    """tests/tsoap/conftest.py:6-35: SOAP(rc=8, n=l=4) on all 201 frames -> timeSOAP delay 1 / 4
+    (case c2's file name says rc4 but its parameters are r_c=8, delay=4)."""
+    soap = so.soap_trajectory(
+        balls7["positions"], np.full(7, 6), np.arange(7), balls7["dims"][:, :3], 8.0, 4, 4
+    )
+    assert np.allclose(to.timesoap(soap, 1), ref_soap["tsoap_c0"], atol=1e-6, rtol=0)
+    assert np.allclose(to.timesoap(soap, 4), ref_soap["tsoap_c2"], atol=1e-6, rtol=0)
