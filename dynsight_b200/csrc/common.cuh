@@ -1,0 +1,70 @@
+// common.cuh -- shared helpers of libdynsight_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/dynsight_b200.h"
+
+namespace dsg {
+
+// ---- error reporting (thread-local message, no exceptions across the C ABI) ----------------
+char* last_error_buffer();
+int set_error(int code, const char* fmt, ...);
+
+#define DSG_CUDA_CHECK(expr)                                                                  \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return ::dsg::set_error(DSG_ERR_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__,  \
+                                    __LINE__, cudaGetErrorString(_e));                        \
+    } while (0)
+
+void count_launch();
+
+#define DSG_LAUNCH_CHECK(name)                                                                \
+    do {                                                                                      \
+        ::dsg::count_launch();                                                                \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess)                                                                \
+            return ::dsg::set_error(DSG_ERR_CUDA, "launch of %s failed at %s:%d: %s", name,   \
+                                    __FILE__, __LINE__, cudaGetErrorString(_e));              \
+    } while (0)
+
+// ---- reference arithmetic shared by host and device ---------------------------------------
+
+// Python / numba float floor division a // b: exact floor of the true quotient (via fmod).
+// Used for ncell_k = max(3, int(box_k // r_cut)), lens.py:43-45.
+__host__ __device__ inline double py_floordiv(double a, double b) {
+    double mod = fmod(a, b);
+    double div = (a - mod) / b;
+    if (mod != 0.0 && ((b < 0.0) != (mod < 0.0))) div -= 1.0;
+    if (div == 0.0) return copysign(0.0, a / b);
+    double fl = floor(div);
+    if (div - fl > 0.5) fl += 1.0;
+    return fl;
+}
+
+// int(x / box * ncell) % ncell with truncation toward zero then Python modulo (lens.py:52-54).
+__host__ __device__ inline int cell_of(double x, double box, int ncell) {
+    double v = x / box * (double)ncell;
+    long long t = (long long)v;  // truncation toward zero, like numba's int()
+    long long r = t % ncell;
+    if (r < 0) r += ncell;
+    return (int)r;
+}
+
+__host__ __device__ inline int wrap_cell(int c, int n) {
+    c %= n;
+    return c < 0 ? c + n : c;
+}
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+constexpr int kNumSMs = 148;  // B200
+
+}  // namespace dsg

@@ -1,0 +1,157 @@
+// lens.cu -- LENS from sorted CSR rows + coordination numbers (sm_100a).
+//
+// Replaces lens/lens.py:150-189 (lens_from_two_csr: serial two-pointer merge per centre) and the
+// Python double loop of trajectory/trajectory.py:168-184.  One warp owns one (centre, frame-pair):
+// both sorted rows are loaded coalesced, one element per lane, and the intersection size comes from
+// lane-parallel equality tests against shuffled copies of the other row (a merge without a serial
+// pointer chase).  Integer work is exact; the single float64 division is IEEE (bit-exact).
+#include "common.cuh"
+
+namespace dsg {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr int kLensWarps = 8;
+
+// |A n B| for two ascending rows of distinct int32, cooperatively by one warp.
+__device__ __forceinline__ int warp_intersect(const int* __restrict__ ra, int na,
+                                              const int* __restrict__ rb, int nb, int lane) {
+    int inter = 0;
+    for (int a0 = 0; a0 < na; a0 += 32) {
+        const int ia = a0 + lane;
+        const int va = ia < na ? ra[ia] : -1;           // ids are >= 0: -1 never matches
+        const int a_lo = __shfl_sync(kFullMask, va, 0);
+        const int a_last = min(31, na - a0 - 1);
+        const int a_hi = __shfl_sync(kFullMask, va, a_last);
+        bool hit = false;
+        for (int b0 = 0; b0 < nb; b0 += 32) {
+            const int ib = b0 + lane;
+            const int vb = ib < nb ? rb[ib] : -2;
+            const int b_last = min(31, nb - b0 - 1);
+            const int b_lo = __shfl_sync(kFullMask, vb, 0);
+            const int b_hi = __shfl_sync(kFullMask, vb, b_last);
+            if (b_hi < a_lo) continue;  // chunk of B entirely below this chunk of A
+            if (b_lo > a_hi) break;     // sorted: nothing further can match
+            for (int j = 0; j <= b_last; ++j) hit |= (va == __shfl_sync(kFullMask, vb, j));
+        }
+        inter += __popc(__ballot_sync(kFullMask, hit));
+    }
+    return inter;
+}
+
+__device__ __forceinline__ double lens_value(int a, int b, int inter) {
+    const int denom = a + b;                 // lens.py:170
+    if (denom <= 0) return 0.0;              // lens.py:171-173
+    const int numer = denom - 2 * inter;     // lens.py:187
+    return (double)numer / (double)denom;    // lens.py:188 (IEEE float64 division)
+}
+
+// grid: (ceil(n_pairs / kLensWarps), n_cent); warp w of a block handles pair blockIdx.x*W + w of
+// centre blockIdx.y, so one block writes kLensWarps consecutive doubles of an output row and the
+// row shared by pairs k and k+delay is served from L1.
+__global__ void __launch_bounds__(kLensWarps * 32)
+lens_pairs_kernel(const int* __restrict__ indptr, const long long* __restrict__ frame_off,
+                  const int* __restrict__ indices, int n_pairs, int n_cent, int delay,
+                  double* __restrict__ out, long long ld_out, long long col0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = blockIdx.x * kLensWarps + warp;
+    const int i = blockIdx.y;
+    if (k >= n_pairs) return;
+    const size_t stride = (size_t)n_cent + 1;
+    const int* p1 = indptr + (size_t)k * stride + i;
+    const int* p2 = indptr + (size_t)(k + delay) * stride + i;
+    const int s1 = p1[0], e1 = p1[1], s2 = p2[0], e2 = p2[1];
+    const int na = e1 - s1, nb = e2 - s2;
+    int inter = 0;
+    if (na > 0 && nb > 0)
+        inter = warp_intersect(indices + frame_off[k] + s1, na, indices + frame_off[k + delay] + s2,
+                               nb, lane);
+    if (lane == 0) out[(long long)i * ld_out + col0 + k] = lens_value(na, nb, inter);
+}
+
+__global__ void __launch_bounds__(kLensWarps * 32)
+lens_two_csr_kernel(const int* __restrict__ indptr1, const int* __restrict__ indices1,
+                    const int* __restrict__ indptr2, const int* __restrict__ indices2, int n_cent,
+                    double* __restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long i = (long long)blockIdx.x * kLensWarps + warp;
+    if (i >= n_cent) return;
+    const int s1 = indptr1[i], e1 = indptr1[i + 1], s2 = indptr2[i], e2 = indptr2[i + 1];
+    const int na = e1 - s1, nb = e2 - s2;
+    int inter = 0;
+    if (na > 0 && nb > 0) inter = warp_intersect(indices1 + s1, na, indices2 + s2, nb, lane);
+    if (lane == 0) out[i] = lens_value(na, nb, inter);
+}
+
+// counts (F, M) int32 -> out[i*ld + col0 + f] float64 through a 32x32 shared-memory tile so that
+// both the read and the write are coalesced.
+__global__ void __launch_bounds__(256)
+counts_to_f64_kernel(const int* __restrict__ counts, int n_frames, int n_cent,
+                     double* __restrict__ out, long long ld_out, long long col0) {
+    __shared__ int tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const int i0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int f = f0 + r, i = i0 + tx;
+        tile[r][tx] = (f < n_frames && i < n_cent) ? counts[(size_t)f * n_cent + i] : 0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r, f = f0 + tx;
+        if (i < n_cent && f < n_frames) out[(long long)i * ld_out + col0 + f] = (double)tile[tx][r];
+    }
+}
+
+}  // namespace dsg
+
+using namespace dsg;
+
+extern "C" int dsg_lens_pairs(const int32_t* d_indptr, const int64_t* d_frame_off,
+                              const int32_t* d_indices, int n_frames, int n_cent, int delay,
+                              double* d_out, int64_t ld_out, int64_t col0, void* stream) {
+    if (!d_indptr || !d_frame_off || !d_out)
+        return set_error(DSG_ERR_INVALID_ARGUMENT, "NULL device pointer argument");
+    if (n_cent < 1 || n_cent > 65535 * 1024)
+        return set_error(DSG_ERR_INVALID_ARGUMENT, "n_cent=%d out of range", n_cent);
+    if (delay < 1 || delay >= n_frames)
+        return set_error(DSG_ERR_INVALID_ARGUMENT, "delay=%d must be in [1, n_frames=%d)", delay,
+                         n_frames);
+    const int n_pairs = n_frames - delay;
+    // grid.y is limited to 65535: fold centres into chunks
+    for (int i0 = 0; i0 < n_cent; i0 += 65535) {
+        const int ni = n_cent - i0 < 65535 ? n_cent - i0 : 65535;
+        dim3 grid((n_pairs + kLensWarps - 1) / kLensWarps, ni);
+        lens_pairs_kernel<<<grid, kLensWarps * 32, 0, (cudaStream_t)stream>>>(
+            d_indptr + i0, (const long long*)d_frame_off, d_indices, n_pairs, n_cent, delay,
+            d_out + (long long)i0 * ld_out, ld_out, col0);
+        DSG_LAUNCH_CHECK("lens_pairs_kernel");
+    }
+    return DSG_OK;
+}
+
+extern "C" int dsg_lens_from_two_csr(const int32_t* d_indptr1, const int32_t* d_indices1,
+                                     const int32_t* d_indptr2, const int32_t* d_indices2,
+                                     int n_cent, double* d_out, void* stream) {
+    if (!d_indptr1 || !d_indptr2 || !d_out)
+        return set_error(DSG_ERR_INVALID_ARGUMENT, "NULL device pointer argument");
+    if (n_cent < 1) return set_error(DSG_ERR_INVALID_ARGUMENT, "n_cent=%d must be >= 1", n_cent);
+    const int blocks = (n_cent + kLensWarps - 1) / kLensWarps;
+    lens_two_csr_kernel<<<blocks, kLensWarps * 32, 0, (cudaStream_t)stream>>>(
+        d_indptr1, d_indices1, d_indptr2, d_indices2, n_cent, d_out);
+    DSG_LAUNCH_CHECK("lens_two_csr_kernel");
+    return DSG_OK;
+}
+
+extern "C" int dsg_counts_to_f64(const int32_t* d_counts, int n_frames, int n_cent, double* d_out,
+                                 int64_t ld_out, int64_t col0, void* stream) {
+    if (!d_counts || !d_out) return set_error(DSG_ERR_INVALID_ARGUMENT, "NULL device pointer");
+    if (n_frames < 1 || n_cent < 1)
+        return set_error(DSG_ERR_INVALID_ARGUMENT, "n_frames=%d, n_cent=%d must be >= 1", n_frames,
+                         n_cent);
+    dim3 grid((n_cent + 31) / 32, (n_frames + 31) / 32);
+    counts_to_f64_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_counts, n_frames, n_cent, d_out,
+                                                                ld_out, col0);
+    DSG_LAUNCH_CHECK("counts_to_f64_kernel");
+    return DSG_OK;
+}

@@ -1,0 +1,705 @@
+// neighbors.cu -- batched periodic cell list -> sorted CSR neighbour lists (sm_100a).
+//
+// Replaces lens/lens.py:29-147 (build_cell_list + neighbor_list_celllist_centers) of the
+// reference.  The reference builds a linked-list cell list serially and walks the 27 cells twice
+// per centre on CPU threads; here every frame of a batch is processed by the same launches:
+//
+//   K1 cell_assign   thread / atom : reference cell index (same formula, float64), histogram
+//   K2 scan          exclusive scan of the cell histogram of the whole batch -> cell_start
+//   K3 cell_scatter  thread / atom : counting-sort scatter into cell order as float4 {x,y,z,id}
+//   K4 neigh<COUNT>  warp / centre cell : the 27 neighbour cells are staged through shared
+//                    memory once per cell, every centre of the cell tests the staged tile,
+//                    warp ballots give per-centre counts
+//   K5 scan          counts -> per-frame CSR row pointers (+ int64 frame offsets)
+//   K6 neigh<FILL>   same traversal, ballot compaction writes the rows, warp bitonic sort
+//
+// Bit-exactness: the distance test is decided in float32 only when the float32 value is outside
+// a rigorous guard band around (r_cut-1e-6)^2 (frame_finalize computes the band from the
+// coordinate magnitudes); inside the band the reference's float64 expression is evaluated.
+#include <climits>
+#include <vector>
+
+#include "common.cuh"
+
+namespace dsg {
+
+struct FrameParams {
+    double box[3];
+    int ncell[3];
+    int cell_base;           // first cell of this frame in the batch-wide cell arrays
+    unsigned amax_bits[3];   // max |x_k| over env atoms and centres (float bits, atomicMax)
+    float r2_lo, r2_hi;      // float32 guard band
+    float boxf[3];
+    float inv_boxf[3];
+};
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kStageCap = 128;  // float4 candidates staged per warp (2 KB)
+constexpr unsigned kFull = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------
+// scan primitives (int32 items, uniform segments)
+// ------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int t = __shfl_up_sync(kFull, v, off);
+        if (lane >= off) v += t;
+    }
+    return v;
+}
+
+// Exclusive scan of one value per thread across a 256-thread block; returns exclusive prefix,
+// *total receives the block total.
+__device__ __forceinline__ int block_excl_scan(int v, int* total) {
+    __shared__ int warp_sums[kScanThreads / 32];
+    __shared__ int block_total;
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = warp_incl_scan(v, lane);
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < kScanThreads / 32 ? warp_sums[lane] : 0;
+        int wi = warp_incl_scan(w, lane);
+        if (lane < kScanThreads / 32) warp_sums[lane] = wi - w;
+        if (lane == kScanThreads / 32 - 1) block_total = wi;
+    }
+    __syncthreads();
+    int res = incl - v + warp_sums[warp];
+    *total = block_total;
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_tile_sums_kernel(const int* __restrict__ in, long long seg_len, int tiles_per_seg,
+                      int* __restrict__ tile_sums) {
+    const long long seg = blockIdx.y;
+    const long long tile0 = (long long)blockIdx.x * kScanTile;
+    const int* src = in + seg * seg_len;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        long long idx = tile0 + threadIdx.x + (long long)k * kScanThreads;
+        if (idx < seg_len) s += src[idx];
+    }
+    int total;
+    block_excl_scan(s, &total);
+    if (threadIdx.x == 0) tile_sums[seg * tiles_per_seg + blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_tile_offsets_kernel(int* __restrict__ tile_sums, int tiles_per_seg,
+                         long long* __restrict__ seg_totals) {
+    const long long seg = blockIdx.x;
+    int* t = tile_sums + seg * tiles_per_seg;
+    long long running = 0;
+    for (int base = 0; base < tiles_per_seg; base += kScanThreads) {
+        int i = base + threadIdx.x;
+        int v = i < tiles_per_seg ? t[i] : 0;
+        int total;
+        int ex = block_excl_scan(v, &total);
+        if (i < tiles_per_seg) t[i] = (int)(running + ex);
+        running += total;
+    }
+    if (threadIdx.x == 0 && seg_totals) seg_totals[seg] = running;
+}
+
+// out has (seg_len + 1) entries per segment: exclusive prefix + total.
+__global__ void __launch_bounds__(kScanThreads)
+scan_apply_kernel(const int* __restrict__ in, long long seg_len, int tiles_per_seg,
+                  const int* __restrict__ tile_offsets, int* __restrict__ out) {
+    const long long seg = blockIdx.y;
+    const long long first = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanItems;
+    const int* src = in + seg * seg_len;
+    int* dst = out + seg * (seg_len + 1);
+    int v[kScanItems];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        long long idx = first + k;
+        v[k] = idx < seg_len ? src[idx] : 0;
+        s += v[k];
+    }
+    int total;
+    int ex = block_excl_scan(s, &total) + tile_offsets[seg * tiles_per_seg + blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        long long idx = first + k;
+        if (idx < seg_len) dst[idx] = ex;
+        ex += v[k];
+        if (idx == seg_len - 1) dst[seg_len] = ex;
+    }
+}
+
+// frame_off[0..n] = exclusive int64 scan of seg_totals[0..n)
+__global__ void frame_offsets_kernel(const long long* __restrict__ seg_totals, int n,
+                                     long long* __restrict__ frame_off) {
+    // one warp; chunks of 32
+    int lane = threadIdx.x;
+    long long running = 0;
+    for (int base = 0; base < n; base += 32) {
+        int i = base + lane;
+        long long v = i < n ? seg_totals[i] : 0;
+        long long incl = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            long long t = __shfl_up_sync(kFull, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (i < n) frame_off[i] = running + incl - v;
+        running += __shfl_sync(kFull, incl, 31);
+    }
+    if (lane == 0) frame_off[n] = running;
+}
+
+static int run_scan(const int* in, long long seg_len, int n_seg, int* out, int* tile_tmp,
+                    long long* seg_totals, cudaStream_t st) {
+    int tiles = (int)((seg_len + kScanTile - 1) / kScanTile);
+    dim3 grid(tiles, n_seg);
+    scan_tile_sums_kernel<<<grid, kScanThreads, 0, st>>>(in, seg_len, tiles, tile_tmp);
+    DSG_LAUNCH_CHECK("scan_tile_sums_kernel");
+    scan_tile_offsets_kernel<<<n_seg, kScanThreads, 0, st>>>(tile_tmp, tiles, seg_totals);
+    DSG_LAUNCH_CHECK("scan_tile_offsets_kernel");
+    scan_apply_kernel<<<grid, kScanThreads, 0, st>>>(in, seg_len, tiles, tile_tmp, out);
+    DSG_LAUNCH_CHECK("scan_apply_kernel");
+    return DSG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 / K3 : cell assignment and counting-sort scatter
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+cell_assign_kernel(const T* __restrict__ pos, int n_atoms, FrameParams* __restrict__ fp,
+                   unsigned* __restrict__ cell_id, int* __restrict__ cell_cnt) {
+    const int f = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const FrameParams* p = fp + f;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    if (i < n_atoms) {
+        const size_t g = ((size_t)f * n_atoms + i) * 3;
+        const double x = (double)pos[g], y = (double)pos[g + 1], z = (double)pos[g + 2];
+        const int ny = p->ncell[1], nz = p->ncell[2];
+        const int cx = cell_of(x, p->box[0], p->ncell[0]);
+        const int cy = cell_of(y, p->box[1], ny);
+        const int cz = cell_of(z, p->box[2], nz);
+        const int c = (cx * ny + cy) * nz + cz;
+        cell_id[(size_t)f * n_atoms + i] = (unsigned)c;
+        atomicAdd(&cell_cnt[p->cell_base + c], 1);
+        ax = __double2float_ru(fabs(x));
+        ay = __double2float_ru(fabs(y));
+        az = __double2float_ru(fabs(z));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        ax = fmaxf(ax, __shfl_xor_sync(kFull, ax, off));
+        ay = fmaxf(ay, __shfl_xor_sync(kFull, ay, off));
+        az = fmaxf(az, __shfl_xor_sync(kFull, az, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        // non-negative floats order like their bit patterns
+        atomicMax(&fp[f].amax_bits[0], __float_as_uint(ax));
+        atomicMax(&fp[f].amax_bits[1], __float_as_uint(ay));
+        atomicMax(&fp[f].amax_bits[2], __float_as_uint(az));
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+cell_scatter_kernel(const T* __restrict__ pos, int n_atoms, const FrameParams* __restrict__ fp,
+                    const unsigned* __restrict__ cell_id, int* __restrict__ cell_cnt,
+                    const int* __restrict__ cell_start, float4* __restrict__ sorted) {
+    const int f = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_atoms) return;
+    const size_t a = (size_t)f * n_atoms + i;
+    const int gc = fp[f].cell_base + (int)cell_id[a];
+    // cell_cnt is consumed back to zero: slot = start + (remaining - 1)
+    const int slot = cell_start[gc] + atomicSub(&cell_cnt[gc], 1) - 1;
+    const size_t g = a * 3;
+    sorted[slot] = make_float4((float)pos[g], (float)pos[g + 1], (float)pos[g + 2],
+                               __int_as_float(i));
+}
+
+// Guard band of the float32 distance test (see DESIGN.md "bit-exact membership"):
+// |dr2_f32 - dr2_ref| <= tol whenever every |d_k| <= 1.5 r_cut, so
+//   dr2_f32 < r2 - tol  => reference accepts,   dr2_f32 > r2 + tol => reference rejects.
+__global__ void frame_finalize_kernel(FrameParams* __restrict__ fp, int n_frames, double r_cut,
+                                      double r2) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    FrameParams* p = fp + f;
+    const double u = 5.9604644775390625e-08;  // 2^-24
+    double tol = 8.0 * u * r2;
+    bool exact_only = false;
+    for (int k = 0; k < 3; ++k) {
+        const double a = (double)__uint_as_float(p->amax_bits[k]);
+        const double b = p->box[k] > 0.0 ? p->box[k] : 0.0;
+        const double e = 8.0 * u * (a + b);
+        const double delta = 4.0 * e;
+        tol += delta * (3.0 * r_cut + delta);
+        if (b > 0.0) {
+            const double dq = 4.0 * u * (2.0 * a / b + 1.0);  // error of the f32 image quotient
+            if (!(dq < 0.25)) exact_only = true;
+        }
+        p->boxf[k] = (float)p->box[k];
+        p->inv_boxf[k] = p->box[k] > 0.0 ? (float)(1.0 / p->box[k]) : 0.f;
+    }
+    if (!(tol < 0.5 * r2) || exact_only) {
+        p->r2_lo = -INFINITY;
+        p->r2_hi = INFINITY;
+    } else {
+        p->r2_lo = __double2float_rd(r2 - tol);
+        p->r2_hi = __double2float_ru(r2 + tol);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4 / K6 : neighbour traversal
+// ------------------------------------------------------------------------------------------
+struct NeighArgs {
+    const void* pos_env;    // original positions (exact test)
+    const void* pos_cent;
+    int n_env, n_cent;
+    const FrameParams* fp;
+    const int* env_start;   // batch-wide cell starts of env atoms
+    const int* cent_start;  // same grid, centres
+    const float4* env_sorted;
+    const float4* cent_sorted;
+    int respect_pbc;
+    double r2;
+    int* counts;                  // COUNT: (F, M)
+    const int* indptr;            // FILL: (F, M+1)
+    const long long* frame_off;   // FILL: (F+1)
+    int* indices;                 // FILL
+};
+
+template <typename T>
+__device__ __noinline__ bool exact_test(const T* __restrict__ pe, const T* __restrict__ pc,
+                                        const double* __restrict__ box, bool pbc, double r2) {
+    // lens.py:100-104 in float64, from the caller's original coordinates
+    double dr2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double d = (double)pe[k] - (double)pc[k];
+        if (pbc && box[k] > 0.0) d -= rint(d / box[k]) * box[k];
+        dr2 += d * d;
+    }
+    return dr2 < r2;
+}
+
+__device__ __forceinline__ void warp_sort_row(int* row, int n, int* smem_i, int lane) {
+    if (n <= 1) return;
+    if (n <= 32) {
+        int v = lane < n ? row[lane] : INT_MAX;
+#pragma unroll
+        for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const int o = __shfl_xor_sync(kFull, v, j);
+                const bool asc = (lane & k) == 0;
+                const bool lower = (lane & j) == 0;
+                v = (lower == asc) ? min(v, o) : max(v, o);
+            }
+        }
+        if (lane < n) row[lane] = v;
+        return;
+    }
+    if (n <= kStageCap * 4) {
+        int p2 = 64;
+        while (p2 < n) p2 <<= 1;
+        for (int t = lane; t < p2; t += 32) smem_i[t] = t < n ? row[t] : INT_MAX;
+        __syncwarp();
+        for (int k = 2; k <= p2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = lane; t < (p2 >> 1); t += 32) {
+                    const int i0 = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int i1 = i0 | j;
+                    const bool asc = (i0 & k) == 0;
+                    const int x = smem_i[i0], y = smem_i[i1];
+                    if ((x > y) == asc) {
+                        smem_i[i0] = y;
+                        smem_i[i1] = x;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        for (int t = lane; t < n; t += 32) row[t] = smem_i[t];
+        __syncwarp();
+        return;
+    }
+    // very long rows (rare): in-place odd-even transposition in global memory
+    for (int phase = 0; phase < n; ++phase) {
+        for (int t = (phase & 1) + 2 * lane; t + 1 < n; t += 64) {
+            const int x = row[t], y = row[t + 1];
+            if (x > y) {
+                row[t] = y;
+                row[t + 1] = x;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <typename T, bool FILL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+neigh_kernel(const NeighArgs a) {
+    __shared__ float4 stage_all[kWarpsPerBlock][kStageCap];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.y;
+    const FrameParams* __restrict__ p = a.fp + f;
+    const int nx = p->ncell[0], ny = p->ncell[1], nz = p->ncell[2];
+    const int c = blockIdx.x * kWarpsPerBlock + warp;  // cell inside the frame
+    if (c >= nx * ny * nz) return;
+    const int base_cell = p->cell_base;
+    const int cbeg = a.cent_start[base_cell + c];
+    const int cend = a.cent_start[base_cell + c + 1];
+    if (cbeg == cend) return;
+
+    float4* stage = stage_all[warp];
+    const int cz = c % nz, cy = (c / nz) % ny, cx = c / (nz * ny);
+
+    // the 27 cells of the reference's traversal (lens.py:92-97); lanes 27..31 idle
+    int run_start = 0, run_len = 0;
+    if (lane < 27) {
+        const int ddx = lane / 9 - 1, ddy = (lane / 3) % 3 - 1, ddz = lane % 3 - 1;
+        const int cc = (wrap_cell(cx + ddx, nx) * ny + wrap_cell(cy + ddy, ny)) * nz +
+                       wrap_cell(cz + ddz, nz);
+        run_start = a.env_start[base_cell + cc];
+        run_len = a.env_start[base_cell + cc + 1] - run_start;
+    }
+    const int run_incl = warp_incl_scan(run_len, lane);
+    const int run_excl = run_incl - run_len;
+    const int n_cand = __shfl_sync(kFull, run_incl, 31);
+
+    const bool pbc = a.respect_pbc != 0;
+    const float bx = p->boxf[0], by = p->boxf[1], bz = p->boxf[2];
+    const float ibx = p->inv_boxf[0], iby = p->inv_boxf[1], ibz = p->inv_boxf[2];
+    const bool px = pbc && p->box[0] > 0.0, py = pbc && p->box[1] > 0.0, pz = pbc && p->box[2] > 0.0;
+    const float r2_lo = p->r2_lo, r2_hi = p->r2_hi;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const T* __restrict__ pos_env_f = (const T*)a.pos_env + (size_t)f * a.n_env * 3;
+    const T* __restrict__ pos_cent_f = (const T*)a.pos_cent + (size_t)f * a.n_cent * 3;
+    const double r2 = a.r2;
+
+    for (int cb = cbeg; cb < cend; cb += 32) {
+        const int nb = min(32, cend - cb);
+        float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < nb) me = a.cent_sorted[cb + lane];
+        const int my_id = __float_as_int(me.w);
+        int my_cnt = 0;
+        long long my_row = 0;
+        if (FILL && lane < nb)
+            my_row = a.frame_off[f] + (long long)a.indptr[(size_t)f * (a.n_cent + 1) + my_id];
+
+        for (int base = 0; base < n_cand; base += kStageCap) {
+            const int clen = min(kStageCap, n_cand - base);
+            __syncwarp();
+            // stage candidates [base, base+clen): flat index -> (run, offset) by a shuffle
+            // binary search over the inclusive run prefix
+            for (int q0 = 0; q0 < clen; q0 += 32) {
+                const int q = base + q0 + lane;
+                const bool valid = q0 + lane < clen;
+                int r = 0;
+#pragma unroll
+                for (int s = 16; s >= 1; s >>= 1) {
+                    const int v = __shfl_sync(kFull, run_incl, (r + s - 1) & 31);
+                    if (v <= q) r += s;
+                }
+                r = valid ? r : 0;
+                const int src = __shfl_sync(kFull, run_start, r) + (q - __shfl_sync(kFull, run_excl, r));
+                if (valid) stage[q0 + lane] = a.env_sorted[src];
+            }
+            __syncwarp();
+
+            for (int ci = 0; ci < nb; ++ci) {
+                const float ccx = __shfl_sync(kFull, me.x, ci);
+                const float ccy = __shfl_sync(kFull, me.y, ci);
+                const float ccz = __shfl_sync(kFull, me.z, ci);
+                const int cid = __shfl_sync(kFull, my_id, ci);
+                const long long row = FILL ? __shfl_sync(kFull, my_row, ci) : 0;
+                const int cur = __shfl_sync(kFull, my_cnt, ci);
+                int add = 0;
+                for (int q0 = 0; q0 < clen; q0 += 32) {
+                    const bool valid = q0 + lane < clen;
+                    const float4 cd = stage[valid ? q0 + lane : 0];
+                    const int j = __float_as_int(cd.w);
+                    float dx = cd.x - ccx, dy = cd.y - ccy, dz = cd.z - ccz;
+                    if (px) dx = fmaf(-rintf(dx * ibx), bx, dx);
+                    if (py) dy = fmaf(-rintf(dy * iby), by, dy);
+                    if (pz) dz = fmaf(-rintf(dz * ibz), bz, dz);
+                    const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                    bool hit = d2 < r2_lo;
+                    if (valid && !hit && !(d2 > r2_hi))
+                        hit = exact_test<T>(pos_env_f + (size_t)j * 3, pos_cent_f + (size_t)cid * 3,
+                                            p->box, pbc, r2);
+                    hit = hit && valid && (j != cid);  // lens.py:104 "j != i"
+                    const unsigned m = __ballot_sync(kFull, hit);
+                    if (FILL && hit) a.indices[row + cur + add + __popc(m & lt_mask)] = j;
+                    add += __popc(m);
+                }
+                if (lane == ci) my_cnt += add;
+            }
+        }
+        if (!FILL) {
+            if (lane < nb) a.counts[(size_t)f * a.n_cent + my_id] = my_cnt;
+        } else {
+            __syncwarp();
+            for (int ci = 0; ci < nb; ++ci) {
+                const long long row = __shfl_sync(kFull, my_row, ci);
+                const int n = __shfl_sync(kFull, my_cnt, ci);
+                warp_sort_row(a.indices + row, n, reinterpret_cast<int*>(stage), lane);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct NeighLayout {
+    long long total_cells = 0;
+    int max_cells = 0;
+    size_t off_fp = 0, off_cell_id_e = 0, off_cnt_e = 0, off_start_e = 0, off_sorted_e = 0;
+    size_t off_cell_id_c = 0, off_cnt_c = 0, off_start_c = 0, off_sorted_c = 0;
+    size_t off_tile_tmp = 0, off_seg_totals = 0;
+    size_t bytes = 0;
+    size_t tile_tmp_ints = 0;
+};
+
+static int make_layout(int n_frames, int n_env, int n_cent, bool same, const double* h_box,
+                       double r_cut, NeighLayout* L, std::vector<FrameParams>* fps) {
+    if (n_frames < 1 || n_frames > 65535)
+        return set_error(DSG_ERR_INVALID_ARGUMENT, "n_frames=%d must be in [1, 65535] per batch",
+                         n_frames);
+    if (n_env < 1 || n_cent < 1)
+        return set_error(DSG_ERR_INVALID_ARGUMENT, "n_env=%d and n_cent=%d must be >= 1", n_env,
+                         n_cent);
+    if (!(r_cut > 0.0)) return set_error(DSG_ERR_INVALID_ARGUMENT, "r_cut=%g must be > 0", r_cut);
+    if (!h_box) return set_error(DSG_ERR_INVALID_ARGUMENT, "h_box is NULL");
+    if ((long long)n_frames * n_env >= INT_MAX || (long long)n_frames * n_cent >= INT_MAX)
+        return set_error(DSG_ERR_OVERFLOW, "n_frames*n_atoms must stay below 2^31 per batch");
+    long long total = 0;
+    int max_cells = 0;
+    if (fps) fps->resize(n_frames);
+    for (int f = 0; f < n_frames; ++f) {
+        long long nc[3];
+        for (int k = 0; k < 3; ++k) {
+            const double b = h_box[3 * f + k];
+            if (!(b > 0.0) || !std::isfinite(b))
+                return set_error(DSG_ERR_INVALID_ARGUMENT,
+                                 "box[%d][%d]=%g: the cell list needs a positive box", f, k, b);
+            double q = py_floordiv(b, r_cut);  // lens.py:43-45
+            long long n = (long long)q;
+            if (n < 3) n = 3;
+            nc[k] = n;
+        }
+        const long long cells = nc[0] * nc[1] * nc[2];
+        if (cells >= INT_MAX || total + cells >= INT_MAX)
+            return set_error(DSG_ERR_OVERFLOW,
+                             "cell grid too large (frame %d: %lld cells); use fewer frames per batch",
+                             f, cells);
+        if (fps) {
+            FrameParams& p = (*fps)[f];
+            for (int k = 0; k < 3; ++k) {
+                p.box[k] = h_box[3 * f + k];
+                p.ncell[k] = (int)nc[k];
+                p.amax_bits[k] = 0u;
+                p.boxf[k] = 0.f;
+                p.inv_boxf[k] = 0.f;
+            }
+            p.cell_base = (int)total;
+            p.r2_lo = p.r2_hi = 0.f;
+        }
+        total += cells;
+        if (cells > max_cells) max_cells = (int)cells;
+    }
+    L->total_cells = total;
+    L->max_cells = max_cells;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t r = o;
+        o += align_up(bytes);
+        return r;
+    };
+    const size_t fe = (size_t)n_frames * n_env, fc = (size_t)n_frames * n_cent;
+    L->off_fp = take(sizeof(FrameParams) * n_frames);
+    L->off_cell_id_e = take(4 * fe);
+    L->off_cnt_e = take(4 * (size_t)total);
+    L->off_start_e = take(4 * ((size_t)total + 1));
+    L->off_sorted_e = take(16 * fe);
+    if (!same) {
+        L->off_cell_id_c = take(4 * fc);
+        L->off_cnt_c = take(4 * (size_t)total);
+        L->off_start_c = take(4 * ((size_t)total + 1));
+        L->off_sorted_c = take(16 * fc);
+    } else {
+        L->off_cell_id_c = L->off_cell_id_e;
+        L->off_cnt_c = L->off_cnt_e;
+        L->off_start_c = L->off_start_e;
+        L->off_sorted_c = L->off_sorted_e;
+    }
+    const size_t tiles_cells = ((size_t)total + kScanTile - 1) / kScanTile;
+    const size_t tiles_cnt = (size_t)n_frames * (((size_t)n_cent + kScanTile - 1) / kScanTile);
+    L->tile_tmp_ints = tiles_cells > tiles_cnt ? tiles_cells : tiles_cnt;
+    L->off_tile_tmp = take(4 * L->tile_tmp_ints);
+    L->off_seg_totals = take(8 * (size_t)n_frames);
+    L->bytes = o;
+    return DSG_OK;
+}
+
+template <typename T>
+static int build_cells(const T* d_pos, int n_frames, int n_atoms, FrameParams* d_fp,
+                       unsigned* d_cell_id, int* d_cnt, int* d_start, float4* d_sorted,
+                       long long total_cells, int* d_tile_tmp, cudaStream_t st, bool scatter_only) {
+    dim3 grid((n_atoms + 255) / 256, n_frames);
+    if (!scatter_only) {
+        DSG_CUDA_CHECK(cudaMemsetAsync(d_cnt, 0, 4 * (size_t)total_cells, st));
+        cell_assign_kernel<T><<<grid, 256, 0, st>>>(d_pos, n_atoms, d_fp, d_cell_id, d_cnt);
+        DSG_LAUNCH_CHECK("cell_assign_kernel");
+        int rc = run_scan(d_cnt, total_cells, 1, d_start, d_tile_tmp, nullptr, st);
+        if (rc) return rc;
+    }
+    cell_scatter_kernel<T><<<grid, 256, 0, st>>>(d_pos, n_atoms, d_fp, d_cell_id, d_cnt, d_start,
+                                                 d_sorted);
+    DSG_LAUNCH_CHECK("cell_scatter_kernel");
+    return DSG_OK;
+}
+
+template <typename T>
+static int neigh_impl(bool fill, const void* d_pos_env, const void* d_pos_cent, int n_frames,
+                      int n_env, int n_cent, const double* h_box, double r_cut, int respect_pbc,
+                      void* d_ws, size_t ws_bytes, int32_t* d_counts, int32_t* d_indptr,
+                      int64_t* d_frame_off, int32_t* d_indices, cudaStream_t st) {
+    const bool same = d_pos_cent == nullptr;
+    if (same && n_cent != n_env)
+        return set_error(DSG_ERR_INVALID_ARGUMENT,
+                         "d_pos_cent is NULL (centres == env) but n_cent=%d != n_env=%d", n_cent,
+                         n_env);
+    NeighLayout L;
+    std::vector<FrameParams> fps;
+    int rc = make_layout(n_frames, n_env, n_cent, same, h_box, r_cut, &L, fill ? nullptr : &fps);
+    if (rc) return rc;
+    if (!d_ws || ws_bytes < L.bytes)
+        return set_error(DSG_ERR_WORKSPACE_TOO_SMALL, "workspace has %zu bytes, %zu needed",
+                         ws_bytes, L.bytes);
+    if (!d_pos_env || !d_indptr || !d_frame_off || (!fill && !d_counts) || (fill && !d_indices))
+        return set_error(DSG_ERR_INVALID_ARGUMENT, "NULL device pointer argument");
+    char* ws = (char*)d_ws;
+    FrameParams* d_fp = (FrameParams*)(ws + L.off_fp);
+    unsigned* cid_e = (unsigned*)(ws + L.off_cell_id_e);
+    int* cnt_e = (int*)(ws + L.off_cnt_e);
+    int* start_e = (int*)(ws + L.off_start_e);
+    float4* sorted_e = (float4*)(ws + L.off_sorted_e);
+    unsigned* cid_c = (unsigned*)(ws + L.off_cell_id_c);
+    int* cnt_c = (int*)(ws + L.off_cnt_c);
+    int* start_c = (int*)(ws + L.off_start_c);
+    float4* sorted_c = (float4*)(ws + L.off_sorted_c);
+    int* tile_tmp = (int*)(ws + L.off_tile_tmp);
+    long long* seg_totals = (long long*)(ws + L.off_seg_totals);
+    const double rc_eff = r_cut - 1e-6;      // lens.py:78
+    const double r2 = rc_eff * rc_eff;
+
+    if (!fill) {
+        DSG_CUDA_CHECK(cudaMemcpyAsync(d_fp, fps.data(), sizeof(FrameParams) * n_frames,
+                                       cudaMemcpyHostToDevice, st));
+        rc = build_cells<T>((const T*)d_pos_env, n_frames, n_env, d_fp, cid_e, cnt_e, start_e,
+                            sorted_e, L.total_cells, tile_tmp, st, false);
+        if (rc) return rc;
+        if (!same) {
+            rc = build_cells<T>((const T*)d_pos_cent, n_frames, n_cent, d_fp, cid_c, cnt_c,
+                                start_c, sorted_c, L.total_cells, tile_tmp, st, false);
+            if (rc) return rc;
+        }
+        frame_finalize_kernel<<<(n_frames + 127) / 128, 128, 0, st>>>(d_fp, n_frames, r_cut, r2);
+        DSG_LAUNCH_CHECK("frame_finalize_kernel");
+    }
+
+    NeighArgs a;
+    a.pos_env = d_pos_env;
+    a.pos_cent = same ? d_pos_env : d_pos_cent;
+    a.n_env = n_env;
+    a.n_cent = n_cent;
+    a.fp = d_fp;
+    a.env_start = start_e;
+    a.cent_start = start_c;
+    a.env_sorted = sorted_e;
+    a.cent_sorted = sorted_c;
+    a.respect_pbc = respect_pbc;
+    a.r2 = r2;
+    a.counts = d_counts;
+    a.indptr = d_indptr;
+    a.frame_off = (const long long*)d_frame_off;
+    a.indices = d_indices;
+    dim3 grid((L.max_cells + kWarpsPerBlock - 1) / kWarpsPerBlock, n_frames);
+    if (!fill) {
+        neigh_kernel<T, false><<<grid, kWarpsPerBlock * 32, 0, st>>>(a);
+        DSG_LAUNCH_CHECK("neigh_kernel<count>");
+        rc = run_scan(d_counts, n_cent, n_frames, d_indptr, tile_tmp, seg_totals, st);
+        if (rc) return rc;
+        frame_offsets_kernel<<<1, 32, 0, st>>>(seg_totals, n_frames, (long long*)d_frame_off);
+        DSG_LAUNCH_CHECK("frame_offsets_kernel");
+    } else {
+        neigh_kernel<T, true><<<grid, kWarpsPerBlock * 32, 0, st>>>(a);
+        DSG_LAUNCH_CHECK("neigh_kernel<fill>");
+    }
+    return DSG_OK;
+}
+
+}  // namespace dsg
+
+using namespace dsg;
+
+extern "C" int dsg_neigh_workspace_bytes(int n_frames, int n_env, int n_cent, int same_centres,
+                                         const double* h_box, double r_cut, size_t* bytes_out) {
+    if (!bytes_out) return set_error(DSG_ERR_INVALID_ARGUMENT, "bytes_out is NULL");
+    NeighLayout L;
+    int rc = make_layout(n_frames, n_env, n_cent, same_centres != 0, h_box, r_cut, &L, nullptr);
+    if (rc) return rc;
+    *bytes_out = L.bytes;
+    return DSG_OK;
+}
+
+extern "C" int dsg_neigh_count(const void* d_pos_env, const void* d_pos_cent, int pos_dtype,
+                               int n_frames, int n_env, int n_cent, const double* h_box,
+                               double r_cut, int respect_pbc, void* d_workspace,
+                               size_t workspace_bytes, int32_t* d_counts, int32_t* d_indptr,
+                               int64_t* d_frame_off, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pos_dtype == DSG_F32)
+        return neigh_impl<float>(false, d_pos_env, d_pos_cent, n_frames, n_env, n_cent, h_box,
+                                 r_cut, respect_pbc, d_workspace, workspace_bytes, d_counts,
+                                 d_indptr, d_frame_off, nullptr, st);
+    if (pos_dtype == DSG_F64)
+        return neigh_impl<double>(false, d_pos_env, d_pos_cent, n_frames, n_env, n_cent, h_box,
+                                  r_cut, respect_pbc, d_workspace, workspace_bytes, d_counts,
+                                  d_indptr, d_frame_off, nullptr, st);
+    return set_error(DSG_ERR_INVALID_ARGUMENT, "pos_dtype=%d is neither DSG_F32 nor DSG_F64",
+                     pos_dtype);
+}
+
+extern "C" int dsg_neigh_fill(const void* d_pos_env, const void* d_pos_cent, int pos_dtype,
+                              int n_frames, int n_env, int n_cent, const double* h_box,
+                              double r_cut, int respect_pbc, void* d_workspace,
+                              size_t workspace_bytes, const int32_t* d_indptr,
+                              const int64_t* d_frame_off, int32_t* d_indices, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pos_dtype == DSG_F32)
+        return neigh_impl<float>(true, d_pos_env, d_pos_cent, n_frames, n_env, n_cent, h_box,
+                                 r_cut, respect_pbc, d_workspace, workspace_bytes, nullptr,
+                                 const_cast<int32_t*>(d_indptr),
+                                 const_cast<int64_t*>(d_frame_off), d_indices, st);
+    if (pos_dtype == DSG_F64)
+        return neigh_impl<double>(true, d_pos_env, d_pos_cent, n_frames, n_env, n_cent, h_box,
+                                  r_cut, respect_pbc, d_workspace, workspace_bytes, nullptr,
+                                  const_cast<int32_t*>(d_indptr),
+                                  const_cast<int64_t*>(d_frame_off), d_indices, st);
+    return set_error(DSG_ERR_INVALID_ARGUMENT, "pos_dtype=%d is neither DSG_F32 nor DSG_F64",
+                     pos_dtype);
+}

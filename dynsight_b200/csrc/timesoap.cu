@@ -1,0 +1,165 @@
+// timesoap.cu -- fused streaming timeSOAP (sm_100a).
+//
+// Replaces timesoap/timesoap.py:13-179 (normalize_soap + soap_distance + timesoap: >= 4 full-size
+// numpy temporaries) with one pass: a warp owns one particle and a run of frames, streams the
+// SOAP vectors once (coalesced 256-byte warp loads), keeps the previous vector and its squared
+// norm in registers (delay == 1) and emits sqrt(max(0, 2 - 2 clip(cos))) per frame pair.
+// HBM-bound: 8*C bytes read + 8 bytes written per particle-frame.
+#include "common.cuh"
+
+namespace dsg {
+
+constexpr unsigned kFullTs = 0xffffffffu;
+constexpr int kTsWarps = 4;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFullTs, v, off);
+    return v;
+}
+
+// timesoap.py:54-58 + :118-127.  A zero-norm vector normalises to the zero vector => cos = 0.
+__device__ __forceinline__ double soap_dist_from_sums(double n1sq, double n2sq, double dot) {
+    double c = 0.0;
+    if (n1sq > 0.0 && n2sq > 0.0) c = dot / (sqrt(n1sq) * sqrt(n2sq));
+    c = fmin(1.0, fmax(-1.0, c));
+    return sqrt(fmax(0.0, 2.0 - 2.0 * c));
+}
+
+struct TsArgs {
+    const double* soap;
+    int n_particles, n_frames, n_comp;
+    long long stride_i, stride_f;
+    int delay;
+    double* out;
+    long long ld_out, col0;
+    int seg_len, n_seg;
+};
+
+// delay == 1, n_comp <= 32*KV: previous vector lives in registers.
+template <int KV>
+__global__ void __launch_bounds__(kTsWarps * 32)
+timesoap_stream_kernel(const TsArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * kTsWarps + warp;
+    if (w >= (long long)a.n_particles * a.n_seg) return;
+    const int i = (int)(w / a.n_seg), seg = (int)(w % a.n_seg);
+    const int n_out = a.n_frames - 1;
+    const int f_begin = seg * a.seg_len;
+    const int f_end = min(n_out, f_begin + a.seg_len);
+    const double* __restrict__ base = a.soap + (long long)i * a.stride_i;
+    double prev[KV];
+    double psq = 0.0;
+    {
+        const double* __restrict__ v = base + (long long)f_begin * a.stride_f;
+#pragma unroll
+        for (int k = 0; k < KV; ++k) {
+            const int c = lane + 32 * k;
+            prev[k] = c < a.n_comp ? v[c] : 0.0;
+            psq = fma(prev[k], prev[k], psq);
+        }
+        psq = warp_sum(psq);
+    }
+    for (int f = f_begin; f < f_end; ++f) {
+        const double* __restrict__ v = base + (long long)(f + 1) * a.stride_f;
+        double cur[KV];
+#pragma unroll
+        for (int k = 0; k < KV; ++k) {
+            const int c = lane + 32 * k;
+            cur[k] = c < a.n_comp ? v[c] : 0.0;
+        }
+        double csq = 0.0, dot = 0.0;
+#pragma unroll
+        for (int k = 0; k < KV; ++k) {
+            csq = fma(cur[k], cur[k], csq);
+            dot = fma(cur[k], prev[k], dot);
+            prev[k] = cur[k];
+        }
+        csq = warp_sum(csq);
+        dot = warp_sum(dot);
+        if (lane == 0) a.out[(long long)i * a.ld_out + a.col0 + f] = soap_dist_from_sums(psq, csq, dot);
+        psq = csq;
+    }
+}
+
+// general delay / long vectors: both vectors are read per output (the second read of a vector
+// happens `delay` steps later from the same SM and is served by L1/L2).
+__global__ void __launch_bounds__(kTsWarps * 32)
+timesoap_general_kernel(const TsArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * kTsWarps + warp;
+    if (w >= (long long)a.n_particles * a.n_seg) return;
+    const int i = (int)(w / a.n_seg), seg = (int)(w % a.n_seg);
+    const int n_out = a.n_frames - a.delay;
+    const int f_begin = seg * a.seg_len;
+    const int f_end = min(n_out, f_begin + a.seg_len);
+    const double* __restrict__ base = a.soap + (long long)i * a.stride_i;
+    for (int f = f_begin; f < f_end; ++f) {
+        const double* __restrict__ v1 = base + (long long)f * a.stride_f;
+        const double* __restrict__ v2 = base + (long long)(f + a.delay) * a.stride_f;
+        double s1 = 0.0, s2 = 0.0, dot = 0.0;
+        for (int c = lane; c < a.n_comp; c += 32) {
+            const double x = v1[c], y = v2[c];
+            s1 = fma(x, x, s1);
+            s2 = fma(y, y, s2);
+            dot = fma(x, y, dot);
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        dot = warp_sum(dot);
+        if (lane == 0) a.out[(long long)i * a.ld_out + a.col0 + f] = soap_dist_from_sums(s1, s2, dot);
+    }
+}
+
+}  // namespace dsg
+
+using namespace dsg;
+
+extern "C" int dsg_timesoap(const double* d_soap, int n_particles, int n_frames, int n_comp,
+                            int64_t stride_i, int64_t stride_f, int delay, double* d_out,
+                            int64_t ld_out, int64_t col0, void* stream) {
+    if (!d_soap || !d_out) return set_error(DSG_ERR_INVALID_ARGUMENT, "NULL device pointer");
+    if (n_particles < 1 || n_comp < 1)
+        return set_error(DSG_ERR_INVALID_ARGUMENT, "n_particles=%d, n_comp=%d must be >= 1",
+                         n_particles, n_comp);
+    if (delay < 1 || delay >= n_frames)  // timesoap.py:175-177
+        return set_error(DSG_ERR_INVALID_ARGUMENT, "delay value outside bounds");
+    TsArgs a;
+    a.soap = d_soap;
+    a.n_particles = n_particles;
+    a.n_frames = n_frames;
+    a.n_comp = n_comp;
+    a.stride_i = stride_i;
+    a.stride_f = stride_f;
+    a.delay = delay;
+    a.out = d_out;
+    a.ld_out = ld_out;
+    a.col0 = col0;
+    const int n_out = n_frames - delay;
+    // enough warps to fill 148 SMs several times over, segments not shorter than 8 outputs
+    const long long target_warps = 8LL * kNumSMs * 32;
+    long long n_seg = (target_warps + n_particles - 1) / n_particles;
+    if (n_seg < 1) n_seg = 1;
+    int seg_len = (int)((n_out + n_seg - 1) / n_seg);
+    if (seg_len < 8) seg_len = 8;
+    if (seg_len > n_out) seg_len = n_out;
+    a.seg_len = seg_len;
+    a.n_seg = (n_out + seg_len - 1) / seg_len;
+    const long long warps = (long long)n_particles * a.n_seg;
+    const long long blocks = (warps + kTsWarps - 1) / kTsWarps;
+    if (blocks > 0x7fffffffLL) return set_error(DSG_ERR_OVERFLOW, "grid too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int kv = (n_comp + 31) / 32;
+    if (delay == 1 && kv <= 16) {
+        if (kv <= 2) timesoap_stream_kernel<2><<<(unsigned)blocks, kTsWarps * 32, 0, st>>>(a);
+        else if (kv <= 4) timesoap_stream_kernel<4><<<(unsigned)blocks, kTsWarps * 32, 0, st>>>(a);
+        else if (kv <= 8) timesoap_stream_kernel<8><<<(unsigned)blocks, kTsWarps * 32, 0, st>>>(a);
+        else if (kv <= 12) timesoap_stream_kernel<12><<<(unsigned)blocks, kTsWarps * 32, 0, st>>>(a);
+        else timesoap_stream_kernel<16><<<(unsigned)blocks, kTsWarps * 32, 0, st>>>(a);
+        DSG_LAUNCH_CHECK("timesoap_stream_kernel");
+    } else {
+        timesoap_general_kernel<<<(unsigned)blocks, kTsWarps * 32, 0, st>>>(a);
+        DSG_LAUNCH_CHECK("timesoap_general_kernel");
+    }
+    return DSG_OK;
+}

@@ -1,0 +1,241 @@
+"""Device-level operators: torch CUDA tensors in, torch CUDA tensors out, through the C ABI.
+
+These mirror the reference's L2 kernels (SURVEY.md section 8b "lower-level kernel boundary"),
+batched over frames:
+
+* :func:`neighbor_lists`      <- ``neighbor_list_celllist_centers``  (lens/lens.py:69-147)
+* :func:`lens_pairs` / :func:`lens_from_two_csr` <- ``lens_from_two_csr`` (lens/lens.py:150-189)
+* :func:`coordination_numbers` <- ``Trj.get_coord_number`` counting loop (trajectory.py:168-184)
+* :func:`timesoap_device`     <- ``timesoap`` (timesoap/timesoap.py:130-179)
+* :func:`soap_power_spectrum` <- DScribe ``SOAP.create`` as called at soapify/saponify.py:98-122
+
+PyTorch is plumbing only (device memory, streams).  Every operator calls hand-written sm_100a
+kernels; there is no CPU or eager-torch fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from dynsight_b200 import _lib
+
+
+def launch_count() -> int:
+    """Kernel launches issued by libdynsight_b200 in this process (counted inside the library)."""
+    return int(_lib.load().dsg_launch_count())
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return _lib.DSG_F32
+    if t.dtype == torch.float64:
+        return _lib.DSG_F64
+    msg = f"positions must be float32 or float64, got {t.dtype}"
+    raise TypeError(msg)
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        msg = f"{name} must be a CUDA tensor (dynsight_b200 has no CPU path)"
+        raise RuntimeError(msg)
+    if not t.is_contiguous():
+        msg = f"{name} must be contiguous"
+        raise ValueError(msg)
+
+
+def _host_box(box: np.ndarray | torch.Tensor, n_frames: int) -> np.ndarray:
+    if isinstance(box, torch.Tensor):
+        box = box.detach().cpu().numpy()
+    b = np.ascontiguousarray(np.asarray(box, dtype=np.float64))
+    if b.ndim == 1:
+        b = np.ascontiguousarray(np.broadcast_to(b[None, :3], (n_frames, 3)))
+    b = np.ascontiguousarray(b[:, :3])
+    if b.shape != (n_frames, 3):
+        msg = f"box must have shape ({n_frames}, 3), got {b.shape}"
+        raise ValueError(msg)
+    return b
+
+
+@dataclass
+class NeighborBatch:
+    """Sorted CSR neighbour lists of a batch of frames (device resident).
+
+    Row ``i`` of frame ``f`` is ``indices[frame_off[f] + indptr[f, i] : frame_off[f] + indptr[f, i+1]]``.
+    """
+
+    counts: torch.Tensor  # (F, M) int32
+    indptr: torch.Tensor  # (F, M+1) int32, frame-local
+    frame_off: torch.Tensor  # (F+1,) int64
+    indices: torch.Tensor  # (nnz,) int32
+    n_frames: int
+    n_cent: int
+
+    def frame_csr(self, f: int) -> tuple[torch.Tensor, torch.Tensor]:
+        """(indptr int32 (M+1,), indices int32 (nnz_f,)) of one frame -- the numba return value."""
+        off = self.frame_off[f : f + 2].tolist()
+        return self.indptr[f], self.indices[off[0] : off[1]]
+
+
+def neighbor_lists(
+    pos_env: torch.Tensor,
+    box: np.ndarray | torch.Tensor,
+    r_cut: float,
+    pos_cent: torch.Tensor | None = None,
+    respect_pbc: bool = True,
+    counts_only: bool = False,
+) -> NeighborBatch:
+    """Sorted CSR neighbour lists for every frame of a batch.
+
+    ``pos_env`` (F, N, 3) and optional ``pos_cent`` (F, M, 3): CUDA float32/float64.
+    ``box`` (F, 3) or (3,) box lengths (host).  ``pos_cent=None`` means centres == env atoms.
+    """
+    lib = _lib.load()
+    _require_cuda(pos_env, "pos_env")
+    if pos_env.ndim != 3 or pos_env.shape[2] != 3:  # noqa: PLR2004
+        msg = f"pos_env must have shape (F, N, 3), got {tuple(pos_env.shape)}"
+        raise ValueError(msg)
+    n_frames, n_env, _ = pos_env.shape
+    code = _dtype_code(pos_env)
+    if pos_cent is not None:
+        _require_cuda(pos_cent, "pos_cent")
+        if pos_cent.dtype != pos_env.dtype or pos_cent.shape[0] != n_frames:
+            msg = "pos_cent must match pos_env in dtype and frame count"
+            raise ValueError(msg)
+        n_cent = pos_cent.shape[1]
+    else:
+        n_cent = n_env
+    h_box = _host_box(box, n_frames)
+    dev = pos_env.device
+    ws_bytes = ctypes.c_size_t(0)
+    _lib.check(
+        lib.dsg_neigh_workspace_bytes(
+            n_frames, n_env, n_cent, int(pos_cent is None), h_box.ctypes.data, float(r_cut),
+            ctypes.byref(ws_bytes),
+        )
+    )  # fmt: skip
+    workspace = torch.empty(ws_bytes.value, dtype=torch.uint8, device=dev)
+    counts = torch.empty((n_frames, n_cent), dtype=torch.int32, device=dev)
+    indptr = torch.empty((n_frames, n_cent + 1), dtype=torch.int32, device=dev)
+    frame_off = torch.empty(n_frames + 1, dtype=torch.int64, device=dev)
+    cent_ptr = pos_cent.data_ptr() if pos_cent is not None else None
+    common = (
+        pos_env.data_ptr(), cent_ptr, code, n_frames, n_env, n_cent, h_box.ctypes.data,
+        float(r_cut), int(bool(respect_pbc)), workspace.data_ptr(), ws_bytes.value,
+    )  # fmt: skip
+    _lib.check(
+        lib.dsg_neigh_count(
+            *common, counts.data_ptr(), indptr.data_ptr(), frame_off.data_ptr(), _stream_ptr()
+        )
+    )
+    if counts_only:
+        indices = torch.empty(0, dtype=torch.int32, device=dev)
+        return NeighborBatch(counts, indptr, frame_off, indices, n_frames, n_cent)
+    nnz = int(frame_off[-1].item())  # the one host sync of the two-phase protocol
+    indices = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    _lib.check(
+        lib.dsg_neigh_fill(
+            *common, indptr.data_ptr(), frame_off.data_ptr(), indices.data_ptr(), _stream_ptr()
+        )
+    )
+    return NeighborBatch(counts, indptr, frame_off, indices[:nnz], n_frames, n_cent)
+
+
+def lens_pairs(
+    batch: NeighborBatch, delay: int = 1, out: torch.Tensor | None = None, col0: int = 0
+) -> torch.Tensor:
+    """LENS of frames (a, a+delay) for all a inside one batch -> (M, n_pairs) float64."""
+    lib = _lib.load()
+    n_pairs = batch.n_frames - delay
+    if n_pairs < 1:
+        msg = "No valid pairs found."
+        raise RuntimeError(msg)
+    if out is None:
+        out = torch.empty((batch.n_cent, n_pairs), dtype=torch.float64, device=batch.indptr.device)
+        col0 = 0
+    _lib.check(
+        lib.dsg_lens_pairs(
+            batch.indptr.data_ptr(), batch.frame_off.data_ptr(), batch.indices.data_ptr(),
+            batch.n_frames, batch.n_cent, int(delay), out.data_ptr(), out.stride(0), int(col0),
+            _stream_ptr(),
+        )
+    )  # fmt: skip
+    return out
+
+
+def lens_from_two_csr(
+    indptr1: torch.Tensor, indices1: torch.Tensor, indptr2: torch.Tensor, indices2: torch.Tensor
+) -> torch.Tensor:
+    """Same signature as the reference's ``lens_from_two_csr`` (lens.py:150-189), on device."""
+    lib = _lib.load()
+    for name, t in (("indptr1", indptr1), ("indices1", indices1), ("indptr2", indptr2),
+                    ("indices2", indices2)):  # fmt: skip
+        _require_cuda(t, name)
+        if t.dtype != torch.int32:
+            msg = f"{name} must be int32"
+            raise TypeError(msg)
+    n_cent = indptr1.numel() - 1
+    out = torch.empty(n_cent, dtype=torch.float64, device=indptr1.device)
+    _lib.check(
+        lib.dsg_lens_from_two_csr(
+            indptr1.data_ptr(), indices1.data_ptr(), indptr2.data_ptr(), indices2.data_ptr(),
+            n_cent, out.data_ptr(), _stream_ptr(),
+        )
+    )  # fmt: skip
+    return out
+
+
+def coordination_numbers(
+    counts: torch.Tensor, out: torch.Tensor | None = None, col0: int = 0
+) -> torch.Tensor:
+    """counts (F, M) int32 -> (M, F) float64, the layout of the coord_number Insight."""
+    lib = _lib.load()
+    _require_cuda(counts, "counts")
+    n_frames, n_cent = counts.shape
+    if out is None:
+        out = torch.empty((n_cent, n_frames), dtype=torch.float64, device=counts.device)
+        col0 = 0
+    _lib.check(
+        lib.dsg_counts_to_f64(
+            counts.data_ptr(), n_frames, n_cent, out.data_ptr(), out.stride(0), int(col0),
+            _stream_ptr(),
+        )
+    )  # fmt: skip
+    return out
+
+
+def timesoap_device(
+    soap: torch.Tensor, delay: int = 1, out: torch.Tensor | None = None, col0: int = 0
+) -> torch.Tensor:
+    """timeSOAP of a (n_particles, n_frames, n_comp) float64 CUDA tensor (any frame/particle strides,
+    unit stride along components) -> (n_particles, n_frames - delay) float64."""
+    lib = _lib.load()
+    if not soap.is_cuda:
+        msg = "soap must be a CUDA tensor (dynsight_b200 has no CPU path)"
+        raise RuntimeError(msg)
+    if soap.dtype != torch.float64 or soap.ndim != 3:  # noqa: PLR2004
+        msg = "soap must be float64 with shape (n_particles, n_frames, n_comp)"
+        raise ValueError(msg)
+    n_p, n_f, n_c = soap.shape
+    if delay < 1 or delay >= n_f:
+        msg = "delay value outside bounds"
+        raise ValueError(msg)
+    if soap.stride(2) != 1:
+        soap = soap.contiguous()
+    if out is None:
+        out = torch.empty((n_p, n_f - delay), dtype=torch.float64, device=soap.device)
+        col0 = 0
+    _lib.check(
+        lib.dsg_timesoap(
+            soap.data_ptr(), n_p, n_f, n_c, soap.stride(0), soap.stride(1), int(delay),
+            out.data_ptr(), out.stride(0), int(col0), _stream_ptr(),
+        )
+    )  # fmt: skip
+    return out

@@ -1,0 +1,151 @@
+/*
+ * dynsight_b200.h -- C ABI of the B200-native descriptor engine (libdynsight_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of GMPavanLab/dynsight: per-frame periodic neighbour search
+ * -> LENS / coordination number, SOAP power spectrum -> timeSOAP.  The reference is pure Python
+ * (numba + DScribe); this header is what its FFI for the path would bind (ctypes stubs are shown
+ * in INTEGRATION.md).  Each entry point cites the reference interface it replaces
+ * (paths relative to /root/reference/src/dynsight/_internal/).
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer (owned by the caller, e.g. a torch tensor);
+ *     h_* is a HOST pointer.  No allocation happens inside the library except tiny pinned staging.
+ *   - all arrays are dense, C-contiguous; frames are the slowest axis of every batched array.
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued asynchronously on it.
+ *   - return value: 0 = ok, negative = error (DSG_ERR_*); dsg_last_error() gives the message of
+ *     the calling thread's last failure.  Nothing is thrown across the boundary.
+ *   - thread safety: no global mutable state; calls on distinct streams may run concurrently.
+ *   - pos_dtype: DSG_F32 (what MDAnalysis hands out) or DSG_F64 (what the numba kernels take).
+ */
+#ifndef DYNSIGHT_B200_H
+#define DYNSIGHT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSG_OK 0
+#define DSG_ERR_INVALID_ARGUMENT (-1)
+#define DSG_ERR_CUDA (-2)
+#define DSG_ERR_WORKSPACE_TOO_SMALL (-3)
+#define DSG_ERR_UNSUPPORTED (-4)
+#define DSG_ERR_OVERFLOW (-5)
+
+#define DSG_F32 0
+#define DSG_F64 1
+
+/* Library / build identification. */
+const char* dsg_version(void);
+/* Message of the last error raised on the calling thread ("" if none). */
+const char* dsg_last_error(void);
+/* Compute capability of the current device as major*10+minor (100 on B200); <0 on error. */
+int dsg_device_arch(void);
+/* Number of kernel launches this library has issued in the process (monotonic counter;
+ * bench.py differences it around the timed region to report "gpu_launches"). */
+long long dsg_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Neighbour lists (replaces lens/lens.py:29-147: build_cell_list +
+ * neighbor_list_celllist_centers, batched over frames).
+ *
+ * Membership rule reproduced bit-exactly (lens.py:98-104): env atom j is a neighbour of centre i
+ * iff  j != i  (env-local vs centre-local index)  and  |dr|^2 < (r_cut - 1e-6)^2  with
+ * dr = pos_env[j] - pos_cent[i] evaluated in float64, minimum-imaged per axis iff respect_pbc and
+ * box[k] > 0; candidates come from the 27 cells around the centre's cell of the reference's own
+ * grid: ncell_k = max(3, int(box_k // r_cut)), cell = int(x / box * ncell) % ncell.
+ * Rows are sorted ascending (lens.py:142-145).
+ *
+ * Two-phase protocol (the caller owns every buffer):
+ *   1. dsg_neigh_workspace_bytes(...)                      -> size of the scratch buffer
+ *   2. dsg_neigh_count(..., d_workspace, d_counts, d_indptr, d_frame_off)
+ *      builds the cell lists of all frames in the workspace, writes per-centre counts,
+ *      per-frame-local CSR row pointers and the exclusive int64 frame offsets
+ *   3. caller reads d_frame_off[n_frames] (= total nnz), allocates d_indices
+ *   4. dsg_neigh_fill(..., d_workspace, d_indptr, d_frame_off, d_indices)
+ *      (same arguments as step 2; the workspace must be untouched in between)
+ * Row i of frame f is d_indices[d_frame_off[f] + d_indptr[f*(n_cent+1)+i] ...+i+1]).
+ *
+ * d_pos_cent == NULL means "centres are the env atoms" (centers == selection).
+ * h_box: (n_frames, 3) float64 box lengths on the HOST (ts.dimensions[:3], lens.py:268-274).
+ * ------------------------------------------------------------------------------------------ */
+int dsg_neigh_workspace_bytes(int n_frames, int n_env, int n_cent, int same_centres,
+                              const double* h_box, double r_cut, size_t* bytes_out);
+
+int dsg_neigh_count(const void* d_pos_env, const void* d_pos_cent, int pos_dtype, int n_frames,
+                    int n_env, int n_cent, const double* h_box, double r_cut, int respect_pbc,
+                    void* d_workspace, size_t workspace_bytes, int32_t* d_counts,
+                    int32_t* d_indptr, int64_t* d_frame_off, void* stream);
+
+int dsg_neigh_fill(const void* d_pos_env, const void* d_pos_cent, int pos_dtype, int n_frames,
+                   int n_env, int n_cent, const double* h_box, double r_cut, int respect_pbc,
+                   void* d_workspace, size_t workspace_bytes, const int32_t* d_indptr,
+                   const int64_t* d_frame_off, int32_t* d_indices, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LENS (replaces lens/lens.py:150-189 lens_from_two_csr, batched over frame pairs).
+ *
+ * Frames a = 0..n_pairs-1 are paired with b = a + delay inside one CSR batch as produced above
+ * (n_frames = n_pairs + delay).  out[i*ld_out + col0 + a] = ((|A|+|B|) - 2|A n B|) / (|A|+|B|)
+ * in IEEE float64, 0.0 when |A|+|B| == 0 -- the (n_centers, n_pairs) layout of compute_lens
+ * (lens.py:262,303).
+ * ------------------------------------------------------------------------------------------ */
+int dsg_lens_pairs(const int32_t* d_indptr, const int64_t* d_frame_off, const int32_t* d_indices,
+                   int n_frames, int n_cent, int delay, double* d_out, int64_t ld_out,
+                   int64_t col0, void* stream);
+
+/* Single pair of independent CSR lists: exactly the signature of lens_from_two_csr. */
+int dsg_lens_from_two_csr(const int32_t* d_indptr1, const int32_t* d_indices1,
+                          const int32_t* d_indptr2, const int32_t* d_indices2, int n_cent,
+                          double* d_out, void* stream);
+
+/* Coordination numbers (replaces trajectory/trajectory.py:168-184): counts (n_frames, n_cent)
+ * int32 -> out[i*ld_out + col0 + f] float64, the (n_centers, n_frames) layout of the Insight. */
+int dsg_counts_to_f64(const int32_t* d_counts, int n_frames, int n_cent, double* d_out,
+                      int64_t ld_out, int64_t col0, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * timeSOAP (replaces timesoap/timesoap.py:13-179: normalize_soap + soap_distance + timesoap).
+ *
+ * soap is addressed as soap[i*stride_i + f*stride_f + c] (element strides, float64), which covers
+ * both the contiguous (n_particles, n_frames, n_comp) array and the transposed view
+ * saponify_trajectory returns (saponify.py:124).  out[i*ld_out + col0 + f] for f in
+ * [0, n_frames-delay):  sqrt(max(0, 2 - 2*clip(v1.v2/(|v1||v2|), -1, 1))), with the reference's
+ * convention that a zero-norm vector normalises to the zero vector (result sqrt(2)).
+ * Returns DSG_ERR_INVALID_ARGUMENT if delay < 1 or delay >= n_frames (timesoap.py:175-177).
+ * ------------------------------------------------------------------------------------------ */
+int dsg_timesoap(const double* d_soap, int n_particles, int n_frames, int n_comp,
+                 int64_t stride_i, int64_t stride_f, int delay, double* d_out, int64_t ld_out,
+                 int64_t col0, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SOAP power spectrum (replaces soapify/saponify.py:98-122, i.e. DScribe
+ * SOAP(species, r_cut, n_max, l_max, periodic, sigma=1, rbf="gto").create, batched over frames).
+ *
+ * h_alphas (l_max+1, n_max), h_betas (l_max+1, n_max, n_max): GTO exponents and Loewdin
+ * orthonormalisation matrices of DScribe's get_basis_gto, computed by the host in float64.
+ * d_species (n_atoms) int32 in [0, n_species): index into the ascending-atomic-number species list.
+ * d_centres (n_cent) int32: selection-local indices of the centre atoms.
+ * h_box (n_frames,3) float64 or NULL (non-periodic / pbc off): orthorhombic cell lengths.
+ * Every periodic image within r_cut + sqrt(-2 ln 1e-3) contributes (centre included).
+ * out[i*stride_i + f*stride_f + c], c in [0, n_feat) with
+ * n_feat = (S*n_max)*(S*n_max+1)/2*(l_max+1); order: species pairs Z<=Z', then l, n, n'
+ * (n'>=n when Z==Z').  float64 output, float64 arithmetic.
+ * ------------------------------------------------------------------------------------------ */
+int dsg_soap_n_features(int n_species, int n_max, int l_max);
+
+int dsg_soap_workspace_bytes(int n_frames, int n_atoms, int n_cent, int n_species, int n_max,
+                             int l_max, const double* h_box, double r_cut, size_t* bytes_out);
+
+int dsg_soap(const void* d_pos, int pos_dtype, const int32_t* d_species, const int32_t* d_centres,
+             int n_frames, int n_atoms, int n_cent, int n_species, const double* h_box,
+             double r_cut, int n_max, int l_max, const double* h_alphas, const double* h_betas,
+             void* d_workspace, size_t workspace_bytes, double* d_out, int64_t stride_i,
+             int64_t stride_f, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYNSIGHT_B200_H */

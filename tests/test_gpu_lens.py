@@ -1,0 +1,247 @@
+"""GPU parity: neighbour CSR / LENS / coordination number through the C ABI vs the CPU oracle.
+
+Bar: bit-exact (integer index work + one IEEE float64 division).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+from golden_cases import fluid_case, random_csr_cases
+from test_oracle_golden import LENS_CASES, NN_CASES, lens_2d_inputs
+
+from oracle import lens_oracle as lo
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(x, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda().contiguous()
+
+
+def _check_batch_vs_oracle(batch, pos_env, pos_cent, box, r_cut, pbc):
+    """Compare every frame of a NeighborBatch with the oracle CSR."""
+    counts = batch.counts.cpu().numpy()
+    indptr = batch.indptr.cpu().numpy()
+    frame_off = batch.frame_off.cpu().numpy()
+    indices = batch.indices.cpu().numpy()
+    for f in range(pos_env.shape[0]):
+        bx = box[f] if np.ndim(box) == 2 else box  # noqa: PLR2004
+        ip, ix = lo.neighbors(pos_env[f], pos_env[f] if pos_cent is None else pos_cent[f], r_cut, bx,
+                              pbc)  # fmt: skip
+        assert np.array_equal(indptr[f], ip), f"indptr differs in frame {f}"
+        assert np.array_equal(counts[f], np.diff(ip)), f"counts differ in frame {f}"
+        got = indices[frame_off[f] : frame_off[f + 1]]
+        assert np.array_equal(got, ix), f"indices differ in frame {f}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_random_csr_cases_vs_numba_golden(numba_cases, dtype):
+    from dynsight_b200 import engine
+
+    for k, case in enumerate(random_csr_cases()):
+        pe = _dev(case["pos_env"][None], dtype)
+        same = case["pos_cent"] is case["pos_env"]
+        pc = None if same else _dev(case["pos_cent"][None], dtype)
+        batch = engine.neighbor_lists(pe, case["box"], case["r_cut"], pc, case["pbc"])
+        ip, ix = batch.frame_csr(0)
+        assert np.array_equal(ip.cpu().numpy(), numba_cases[f"csr{k}_indptr"]), k
+        assert np.array_equal(ix.cpu().numpy(), numba_cases[f"csr{k}_indices"]), k
+
+
+def test_random_cases_batched_with_explicit_centres():
+    """Several frames per launch, centres passed explicitly even when equal to env."""
+    from dynsight_b200 import engine
+
+    rng = np.random.default_rng(5)
+    n_frames, n, m = 7, 211, 97
+    box = (rng.random((n_frames, 3)) * 6 + 4).astype(np.float32)  # per-frame box (NPT-like)
+    pe = ((rng.random((n_frames, n, 3)) * 1.2 - 0.1) * box[:, None, :]).astype(np.float32)
+    pc = ((rng.random((n_frames, m, 3)) * 1.2 - 0.1) * box[:, None, :]).astype(np.float32)
+    for pbc in (True, False):
+        batch = engine.neighbor_lists(_dev(pe), box, 1.6, _dev(pc), pbc)
+        _check_batch_vs_oracle(batch, pe, pc, box, 1.6, pbc)
+
+
+def test_float64_positions_not_representable_in_float32():
+    from dynsight_b200 import engine
+
+    rng = np.random.default_rng(11)
+    box = np.array([7.3, 6.1, 8.9])
+    pe = rng.random((3, 500, 3)) * box
+    batch = engine.neighbor_lists(_dev(pe), box, 1.45, None, True)
+    _check_batch_vs_oracle(batch, pe, None, box, 1.45, True)
+
+
+def test_guard_band_pairs_exactly_at_cutoff():
+    """Pairs at |d| == r_cut - 1e-6 +- ulps must follow the float64 rule (strict <)."""
+    from dynsight_b200 import engine
+
+    r_cut = 1.5
+    box = np.array([12.0, 12.0, 12.0])
+    base = np.array([3.0, 3.0, 3.0])
+    rc = r_cut - 1e-6
+    offs = [rc, np.nextafter(rc, 0), np.nextafter(rc, 9), rc * (1 - 1e-7), rc * (1 + 1e-7), r_cut]
+    pts = [base]
+    for k, o in enumerate(offs):
+        v = np.zeros(3)
+        v[k % 3] = o
+        pts.append(base + v)
+        pts.append(base - v * 0.999999)
+    pe = np.asarray(pts)[None]
+    for arr in (pe, pe.astype(np.float32)):
+        batch = engine.neighbor_lists(_dev(arr), box, r_cut, None, True)
+        _check_batch_vs_oracle(batch, arr, None, box, r_cut, True)
+
+
+def test_fluid_lens_and_counts_vs_numba_golden(numba_cases):
+    from dynsight_b200 import engine
+
+    pos, box, r_cut = fluid_case()
+    batch = engine.neighbor_lists(_dev(pos), box, r_cut, None, True)
+    lens = engine.lens_pairs(batch, 1).cpu().numpy()
+    assert np.array_equal(lens, numba_cases["fluid_lens"])
+    nc = engine.coordination_numbers(batch.counts).cpu().numpy()
+    assert np.array_equal(nc, numba_cases["fluid_counts"])
+    ip, ix = batch.frame_csr(pos.shape[0] - 1)
+    assert np.array_equal(ip.cpu().numpy(), numba_cases["fluid_last_indptr"])
+    assert np.array_equal(ix.cpu().numpy(), numba_cases["fluid_last_indices"])
+    # delay 2 against the oracle
+    lens2 = engine.lens_pairs(batch, 2).cpu().numpy()
+    dims = np.tile(np.concatenate([box, [90, 90, 90]]).astype(np.float32), (pos.shape[0], 1))
+    assert np.array_equal(lens2, lo.compute_lens_arrays(pos, dims, r_cut, delay=2))
+
+
+def test_lens_from_two_csr_signature():
+    from dynsight_b200 import engine
+
+    pos, box, r_cut = fluid_case(n_side=8, n_frames=2)
+    a = lo.neighbors(pos[0], pos[0], r_cut, box, True)
+    b = lo.neighbors(pos[1], pos[1], r_cut, box, True)
+    got = engine.lens_from_two_csr(_dev(a[0]), _dev(a[1]), _dev(b[0]), _dev(b[1])).cpu().numpy()
+    assert np.array_equal(got, lo.lens_from_two_csr(a[0], a[1], b[0], b[1]))
+
+
+def test_long_rows_sorted_paths():
+    """Rows longer than 32 (shared-memory bitonic) and longer than 512 (global fallback)."""
+    from dynsight_b200 import engine
+
+    rng = np.random.default_rng(3)
+    box = np.array([6.0, 6.0, 6.0], dtype=np.float32)
+    for n, r_cut in ((300, 1.9), (4000, 1.99)):
+        pe = (rng.random((2, n, 3)) * box).astype(np.float32)
+        batch = engine.neighbor_lists(_dev(pe), box, r_cut, None, True)
+        assert int(batch.counts.max()) > (32 if n == 300 else 512)  # noqa: PLR2004
+        _check_batch_vs_oracle(batch, pe, None, box, r_cut, True)
+        lens = engine.lens_pairs(batch, 1).cpu().numpy()
+        dims = np.tile(np.concatenate([box, [90, 90, 90]]).astype(np.float32), (2, 1))
+        assert np.array_equal(lens, lo.compute_lens_arrays(pe, dims, r_cut))
+
+
+def test_balls7_reference_goldens(balls7, ref_lens):
+    """tests/trajectory/test_trj.py:79-94 numbers (r_cut=15) straight through the engine."""
+    from dynsight_b200 import engine
+
+    pos, dims = balls7["positions"], balls7["dims"]
+    batch = engine.neighbor_lists(_dev(pos), dims[:, :3], 15.0, None, True)
+    assert np.array_equal(engine.lens_pairs(batch, 1).cpu().numpy(), ref_lens["trj_lens"])
+    assert np.array_equal(
+        engine.coordination_numbers(batch.counts).cpu().numpy(), ref_lens["trj_n_c"]
+    )
+
+
+@pytest.mark.parametrize("pbc", [True, False])
+def test_lens_2d_goldens(ref_lens, pbc):
+    from dynsight_b200 import engine
+
+    pos, dims = lens_2d_inputs()
+    batch = engine.neighbor_lists(_dev(pos), dims[:, :3], 0.1, None, pbc)
+    got = engine.lens_pairs(batch, 1).cpu().numpy()
+    assert np.array_equal(got, ref_lens["lens_2d_pbc" if pbc else "lens_2d_fbc"])
+
+
+@pytest.mark.parametrize("case", sorted(LENS_CASES))
+def test_lens_cases_goldens(balls7, ref_lens, case):
+    from dynsight_b200 import engine
+
+    r_cut, delay, cent, env = LENS_CASES[case]
+    pos, dims = balls7["positions"], balls7["dims"]
+    pe = pos if env is None else pos[:, env]
+    pc = None if cent is None and env is None else (pos if cent is None else pos[:, cent])
+    batch = engine.neighbor_lists(
+        _dev(pe), dims[:, :3], r_cut, None if pc is None else _dev(pc), True
+    )
+    assert np.array_equal(
+        engine.lens_pairs(batch, delay).cpu().numpy(), ref_lens["lens_" + case]
+    )
+    if case in NN_CASES:
+        assert np.array_equal(
+            engine.coordination_numbers(batch.counts).cpu().numpy(), ref_lens["nn_" + case]
+        )
+
+
+def test_error_paths():
+    from dynsight_b200 import _lib, engine
+
+    pos = torch.zeros((1, 4, 3), dtype=torch.float32, device="cuda")
+    with pytest.raises(_lib.DsgError):
+        engine.neighbor_lists(pos, np.array([0.0, 1.0, 1.0]), 1.0)  # non-positive box
+    with pytest.raises(_lib.DsgError):
+        engine.neighbor_lists(pos, np.array([1.0, 1.0, 1.0]), -1.0)
+    with pytest.raises(RuntimeError):
+        engine.neighbor_lists(pos.cpu(), np.array([1.0, 1.0, 1.0]), 1.0)
+    batch = engine.neighbor_lists(pos, np.array([5.0, 5.0, 5.0]), 1.0)
+    with pytest.raises(RuntimeError, match="No valid pairs found."):
+        engine.lens_pairs(batch, 1)
+
+
+def test_large_fluid_properties():
+    """cfg3-sized frame (1e6 particles): properties that need no oracle at this size --
+    rows strictly ascending, neighbour relation symmetric (sum of ids trick), counts == row
+    lengths, LENS of a frame with itself == 0 -- plus an oracle spot check on a sub-block."""
+    from dynsight_b200 import engine
+
+    n_side = 100
+    n = n_side**3
+    box_l = (n / 0.8) ** (1 / 3)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    grid = (torch.arange(n_side, device="cuda", dtype=torch.float32) + 0.5) * (box_l / n_side)
+    lat = torch.stack(torch.meshgrid(grid, grid, grid, indexing="ij"), dim=-1).reshape(-1, 3)
+    pos0 = torch.remainder(lat + 0.25 * torch.randn(lat.shape, device="cuda", generator=g), box_l)
+    pos0 = pos0.clamp_(max=float(np.nextafter(np.float32(box_l), np.float32(0))))
+    pos = torch.stack([pos0, pos0]).contiguous()
+    box = np.full(3, np.float32(box_l), dtype=np.float32)
+    batch = engine.neighbor_lists(pos, box, 1.5, None, True)
+    indptr = batch.indptr[0].long()
+    ix = batch.indices[: int(batch.frame_off[1])].long()
+    assert torch.equal(batch.counts[0].long(), indptr[1:] - indptr[:-1])
+    # strictly ascending inside rows: positions where the next entry is not larger must be row ends
+    row_of = torch.repeat_interleave(torch.arange(n, device="cuda"), batch.counts[0].long())
+    same_row = row_of[1:] == row_of[:-1]
+    assert bool(torch.all(ix[1:][same_row] > ix[:-1][same_row]))
+    # symmetry: j in N(i) <=> i in N(j)  => multiset of (i,j) equals multiset of (j,i)
+    key_fwd = row_of * n + ix
+    key_bwd = ix * n + row_of
+    assert torch.equal(torch.sort(key_fwd).values, torch.sort(key_bwd).values)
+    lens = engine.lens_pairs(batch, 1)
+    assert float(lens.abs().max()) == 0.0
+    mean_nc = float(batch.counts[0].float().mean())
+    assert 9.0 < mean_nc < 14.0  # rho*=0.8, r_cut=1.5 -> ~11.3
+    # oracle spot check of 2000 centres against the full frame
+    sel = torch.arange(0, n, n // 2000, device="cuda")[:2000]
+    p_host = pos0.cpu().numpy()
+    ip, ixo = lo.neighbors(p_host, p_host[sel.cpu().numpy()], 1.5, box, True)
+    # the oracle's "j != i" compares env index with *centre-local* index, so emulate by checking
+    # rows through set equality after removing/adding the self / local-index quirk
+    indptr_h = indptr.cpu().numpy()
+    ix_h = ix.cpu().numpy()
+    for k, c in enumerate(sel.cpu().numpy()):
+        want = set(ixo[ip[k] : ip[k + 1]].tolist())
+        want.discard(int(c))  # self is a neighbour in the oracle call (centre-local index k != c)
+        got = set(ix_h[indptr_h[c] : indptr_h[c + 1]].tolist())
+        # env atom with index == k is skipped by the oracle call; tolerate exactly that one id
+        assert got - {k} == want - {k}, (k, c)
