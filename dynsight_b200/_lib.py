@@ -50,6 +50,7 @@ SIGNATURES: dict[str, tuple] = {
         _c_int,
         [_c_ptr, _c_int, _c_int, _c_int, _c_i64, _c_i64, _c_int, _c_ptr, _c_i64, _c_i64, _c_ptr],
     ),
+    "dsg_normalize_soap": (_c_int, [_c_ptr, _c_ptr, _c_i64, _c_int, _c_ptr]),
     "dsg_soap_n_features": (_c_int, [_c_int, _c_int, _c_int]),
     "dsg_soap_workspace_bytes": (
         _c_int,

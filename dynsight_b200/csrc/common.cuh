@@ -63,6 +63,13 @@ __host__ __device__ inline int wrap_cell(int c, int n) {
     return c < 0 ? c + n : c;
 }
 
+// Exclusive scan of n_seg uniform segments of int32 (neighbors.cu).  out has seg_len+1 entries per
+// segment (prefix + total); tile_tmp needs n_seg*ceil(seg_len/4096) ints; seg_totals (int64, one
+// per segment) may be NULL.
+int run_scan(const int* in, long long seg_len, int n_seg, int* out, int* tile_tmp,
+             long long* seg_totals, cudaStream_t st);
+constexpr int kScanTileItems = 4096;
+
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 constexpr int kNumSMs = 148;  // B200

@@ -157,8 +157,8 @@ __global__ void frame_offsets_kernel(const long long* __restrict__ seg_totals, i
     if (lane == 0) frame_off[n] = running;
 }
 
-static int run_scan(const int* in, long long seg_len, int n_seg, int* out, int* tile_tmp,
-                    long long* seg_totals, cudaStream_t st) {
+int run_scan(const int* in, long long seg_len, int n_seg, int* out, int* tile_tmp,
+             long long* seg_totals, cudaStream_t st) {
     int tiles = (int)((seg_len + kScanTile - 1) / kScanTile);
     dim3 grid(tiles, n_seg);
     scan_tile_sums_kernel<<<grid, kScanThreads, 0, st>>>(in, seg_len, tiles, tile_tmp);

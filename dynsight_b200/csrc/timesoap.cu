@@ -111,9 +111,40 @@ timesoap_general_kernel(const TsArgs a) {
     }
 }
 
+// normalize_soap (timesoap.py:54-58): v / |v| where |v| > 0, else the zero vector.
+__global__ void __launch_bounds__(kTsWarps * 32)
+normalize_kernel(const double* __restrict__ in, double* __restrict__ out, long long n_vec,
+                 int n_comp) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long v = (long long)blockIdx.x * kTsWarps + warp;
+    if (v >= n_vec) return;
+    const double* __restrict__ src = in + v * n_comp;
+    double* __restrict__ dst = out + v * n_comp;
+    double s = 0.0;
+    for (int c = lane; c < n_comp; c += 32) s = fma(src[c], src[c], s);
+    s = warp_sum(s);
+    const double norm = sqrt(s);
+    for (int c = lane; c < n_comp; c += 32) dst[c] = norm > 0.0 ? src[c] / norm : 0.0;
+}
+
 }  // namespace dsg
 
 using namespace dsg;
+
+extern "C" int dsg_normalize_soap(const double* d_in, double* d_out, int64_t n_vectors,
+                                  int n_comp, void* stream) {
+    if (!d_in || !d_out) return set_error(DSG_ERR_INVALID_ARGUMENT, "NULL device pointer");
+    if (n_vectors < 0 || n_comp < 1)
+        return set_error(DSG_ERR_INVALID_ARGUMENT, "n_vectors=%lld, n_comp=%d out of range",
+                         (long long)n_vectors, n_comp);
+    if (n_vectors == 0) return DSG_OK;
+    const long long blocks = (n_vectors + kTsWarps - 1) / kTsWarps;
+    if (blocks > 0x7fffffffLL) return set_error(DSG_ERR_OVERFLOW, "grid too large");
+    normalize_kernel<<<(unsigned)blocks, kTsWarps * 32, 0, (cudaStream_t)stream>>>(
+        d_in, d_out, n_vectors, n_comp);
+    DSG_LAUNCH_CHECK("normalize_kernel");
+    return DSG_OK;
+}
 
 extern "C" int dsg_timesoap(const double* d_soap, int n_particles, int n_frames, int n_comp,
                             int64_t stride_i, int64_t stride_f, int delay, double* d_out,

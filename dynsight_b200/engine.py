@@ -239,3 +239,82 @@ def timesoap_device(
         )
     )  # fmt: skip
     return out
+
+
+def normalize_soap_device(soap: torch.Tensor) -> torch.Tensor:
+    """Unit-normalise the last axis of a float64 CUDA tensor (zero vectors stay zero)."""
+    lib = _lib.load()
+    if not soap.is_cuda or soap.dtype != torch.float64:
+        msg = "soap must be a float64 CUDA tensor"
+        raise RuntimeError(msg)
+    src = soap.contiguous()
+    out = torch.empty_like(src)
+    n_comp = src.shape[-1]
+    _lib.check(
+        lib.dsg_normalize_soap(
+            src.data_ptr(), out.data_ptr(), src.numel() // max(n_comp, 1), n_comp, _stream_ptr()
+        )
+    )
+    return out
+
+
+def soap_power_spectrum(
+    pos: torch.Tensor,
+    species: torch.Tensor,
+    centres: torch.Tensor,
+    box: np.ndarray | torch.Tensor | None,
+    r_cut: float,
+    n_max: int,
+    l_max: int,
+    n_species: int | None = None,
+    out: torch.Tensor | None = None,
+    frame0: int = 0,
+) -> torch.Tensor:
+    """SOAP power spectrum of a batch of frames -> (n_centres, n_frames, n_feat) float64.
+
+    ``pos`` (F, N, 3) CUDA float32/float64; ``species`` (N,) int32 in [0, n_species) (index into the
+    ascending-atomic-number species list); ``centres`` (M,) int32 selection-local indices;
+    ``box`` (F, 3) / (3,) orthorhombic lengths, or ``None`` for a non-periodic calculation.
+    If ``out`` (M, F_total, C) is given, frames are written at ``out[:, frame0:frame0+F]``.
+    """
+    from dynsight_b200 import soap_basis
+
+    lib = _lib.load()
+    _require_cuda(pos, "pos")
+    _require_cuda(species, "species")
+    _require_cuda(centres, "centres")
+    if species.dtype != torch.int32 or centres.dtype != torch.int32:
+        msg = "species and centres must be int32"
+        raise TypeError(msg)
+    n_frames, n_atoms, _ = pos.shape
+    n_cent = centres.numel()
+    if n_species is None:
+        n_species = int(species.max().item()) + 1
+    alphas, betas = soap_basis.gto_basis(float(r_cut), int(n_max), int(l_max))
+    n_feat = soap_basis.n_features(n_species, n_max, l_max)
+    h_box = None if box is None else _host_box(box, n_frames)
+    box_ptr = None if h_box is None else h_box.ctypes.data
+    ws_bytes = ctypes.c_size_t(0)
+    _lib.check(
+        lib.dsg_soap_workspace_bytes(
+            n_frames, n_atoms, n_cent, n_species, n_max, l_max, box_ptr, float(r_cut),
+            ctypes.byref(ws_bytes),
+        )
+    )  # fmt: skip
+    workspace = torch.empty(ws_bytes.value, dtype=torch.uint8, device=pos.device)
+    if out is None:
+        out = torch.empty((n_cent, n_frames, n_feat), dtype=torch.float64, device=pos.device)
+        frame0 = 0
+    view = out[:, frame0 : frame0 + n_frames]
+    if view.shape != (n_cent, n_frames, n_feat) or view.stride(2) != 1:
+        msg = f"out has shape {tuple(out.shape)}; expected (n_centres, >= frame0+F, {n_feat})"
+        raise ValueError(msg)
+    _lib.check(
+        lib.dsg_soap(
+            pos.data_ptr(), _dtype_code(pos), species.data_ptr(), centres.data_ptr(), n_frames,
+            n_atoms, n_cent, n_species, box_ptr, float(r_cut), int(n_max), int(l_max),
+            alphas.ctypes.data, betas.ctypes.data, workspace.data_ptr(), ws_bytes.value,
+            view.data_ptr(), view.stride(0), view.stride(1), _stream_ptr(),
+        )
+    )  # fmt: skip
+    return out

@@ -1,0 +1,195 @@
+"""LENS package -- drop-in for ``dynsight.lens`` (reference ``src/dynsight/lens.py:3-11``).
+
+Same names, arguments, defaults, return shapes and error messages as
+``dynsight._internal.lens.lens.compute_lens`` (lens.py:192-310) and
+``list_neighbours_along_trajectory`` (lens.py:313-390); the work runs on the GPU through
+:mod:`dynsight_b200.engine` (batched cell list -> sorted CSR -> warp merge).  ``n_jobs`` is
+accepted and ignored (the reference uses it for ``numba.set_num_threads``).
+"""
+
+from __future__ import annotations
+
+from typing import TYPE_CHECKING, Any, Iterator, Sequence
+
+import numpy as np
+import torch
+
+from dynsight_b200 import engine, frames
+
+if TYPE_CHECKING:
+    from numpy.typing import NDArray
+
+__all__ = ["compute_lens", "compute_lens_device", "list_neighbours_along_trajectory"]
+
+
+def _mean_neighbours_estimate(n_env: int, box: np.ndarray, r_cut: float) -> float:
+    vol = float(np.prod(np.maximum(box[0], 1e-12)))
+    return min(float(n_env), n_env / vol * 4.18879 * float(r_cut) ** 3)
+
+
+def compute_lens_device(
+    universe: Any,
+    r_cut: float,
+    delay: int = 1,
+    centers: str = "all",
+    selection: str = "all",
+    trajslice: slice | None = None,
+    respect_pbc: bool = True,
+    batch_frames: int | None = None,
+) -> torch.Tensor:
+    """:func:`compute_lens` that leaves the (n_centers, n_pairs) float64 result on the device."""
+    ag_env = universe.select_atoms(selection)
+    ag_cent = universe.select_atoms(centers)
+    fr_idx = frames.frame_sequence(universe.trajectory.n_frames, trajslice)
+    n_pairs = len(fr_idx) - delay
+    if delay < 1 or n_pairs < 1:  # "pairs" would be empty (lens.py:255-260)
+        msg = "No valid pairs found."
+        raise RuntimeError(msg)
+    n_all = len(universe.atoms)
+    ix_env = np.asarray(ag_env.indices)
+    ix_cent = np.asarray(ag_cent.indices)
+    same = ix_env.shape == ix_cent.shape and bool(np.array_equal(ix_env, ix_cent))
+    dev = frames.device()
+    out = torch.empty((ix_cent.size, n_pairs), dtype=torch.float64, device=dev)
+    if batch_frames is None:
+        batch_frames = frames.pick_batch_frames(max(ix_env.size, ix_cent.size), 160.0, delay + 1)
+    batch_frames = max(batch_frames, delay + 1)
+    for fb in frames.iter_batches(universe, fr_idx, batch_frames, overlap=delay):
+        box = frames.lens_boxes(fb, 1.01)
+        pos_env = fb.select(ix_env, n_all)
+        pos_cent = None if same else fb.select(ix_cent, n_all)
+        nb = engine.neighbor_lists(pos_env, box, r_cut, pos_cent, respect_pbc)
+        engine.lens_pairs(nb, delay, out=out, col0=fb.seq0)
+    return out
+
+
+def compute_lens(
+    universe: Any,
+    r_cut: float,
+    delay: int = 1,
+    centers: str = "all",
+    selection: str = "all",
+    trajslice: slice | None = None,
+    respect_pbc: bool = True,
+    n_jobs: int = 1,  # noqa: ARG001  (numba thread count in the reference)
+) -> NDArray[np.float64]:
+    """Compute the LENS descriptor for all frames along a trajectory.
+
+    Returns LENS values for each centre and each pair of frames, shape (n_centers, n_pairs),
+    float64 -- identical (bit for bit) to the reference's result.
+
+    Raises:
+        RuntimeError: "No valid pairs found." when the frame selection is shorter than ``delay``.
+    """
+    return (
+        compute_lens_device(universe, r_cut, delay, centers, selection, trajslice, respect_pbc)
+        .cpu()
+        .numpy()
+    )
+
+
+class FrameNeighbours(Sequence):
+    """Neighbours of every centre in one frame; item ``i`` is ``ag_env[indices[s:e]]``."""
+
+    def __init__(self, ag_env: Any, indptr: np.ndarray, indices: np.ndarray) -> None:
+        self._ag_env = ag_env
+        self.indptr = indptr
+        self.indices = indices
+
+    def __len__(self) -> int:
+        return len(self.indptr) - 1
+
+    def __getitem__(self, i: int) -> Any:  # type: ignore[override]
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        return self._ag_env[self.indices[self.indptr[i] : self.indptr[i + 1]]]
+
+    def __iter__(self) -> Iterator[Any]:
+        for i in range(len(self)):
+            yield self[i]
+
+
+class NeighbourList(Sequence):
+    """``list[list[AtomGroup]]`` of the reference, materialised lazily.
+
+    The reference builds one AtomGroup per centre and frame in a Python loop (lens.py:383-388),
+    which dominates its run time; here the CSR arrays are kept and an AtomGroup is only created
+    when an element is accessed.  ``counts`` (n_frames, n_centers) gives the coordination numbers
+    without touching any AtomGroup.
+    """
+
+    def __init__(self, ag_env: Any, counts: torch.Tensor, indptr: np.ndarray,
+                 frame_off: np.ndarray, indices: np.ndarray) -> None:  # fmt: skip
+        self._ag_env = ag_env
+        self.counts_device = counts  # (F, M) int32 CUDA
+        self.indptr = indptr  # (F, M+1) int32 host
+        self.frame_off = frame_off
+        self.indices = indices
+
+    def __len__(self) -> int:
+        return self.indptr.shape[0]
+
+    def __getitem__(self, f: int) -> FrameNeighbours:  # type: ignore[override]
+        if isinstance(f, slice):
+            return [self[k] for k in range(*f.indices(len(self)))]  # type: ignore[return-value]
+        if f < 0:
+            f += len(self)
+        if not 0 <= f < len(self):
+            raise IndexError(f)
+        return FrameNeighbours(
+            self._ag_env, self.indptr[f], self.indices[self.frame_off[f] : self.frame_off[f + 1]]
+        )
+
+    def __iter__(self) -> Iterator[FrameNeighbours]:
+        for f in range(len(self)):
+            yield self[f]
+
+
+def list_neighbours_along_trajectory(
+    universe: Any,
+    r_cut: float,
+    centers: str = "all",
+    selection: str = "all",
+    trajslice: slice | None = None,
+    respect_pbc: bool = True,
+    n_jobs: int = 1,  # noqa: ARG001
+) -> NeighbourList:
+    """Produce a per-frame list of neighbours: ``result[frame][centre]`` is an AtomGroup of the
+    environment atoms within ``r_cut`` (same membership and ascending order as the reference)."""
+    if trajslice is None:
+        trajslice = slice(None)
+    ag_centers = universe.select_atoms(centers)
+    ag_env = universe.select_atoms(selection)
+    fr_idx = list(range(*trajslice.indices(universe.trajectory.n_frames)))
+    n_all = len(universe.atoms)
+    ix_env = np.asarray(ag_env.indices)
+    ix_cent = np.asarray(ag_centers.indices)
+    same = ix_env.shape == ix_cent.shape and bool(np.array_equal(ix_env, ix_cent))
+    counts, indptrs, offs, idxs = [], [], [0], []
+    if fr_idx:
+        batch_frames = frames.pick_batch_frames(max(ix_env.size, ix_cent.size), 160.0, 1)
+        for fb in frames.iter_batches(universe, fr_idx, batch_frames):
+            box = frames.lens_boxes(fb, None)  # no 1.01 factor here (lens.py:368-371)
+            pos_env = fb.select(ix_env, n_all)
+            pos_cent = None if same else fb.select(ix_cent, n_all)
+            nb = engine.neighbor_lists(pos_env, box, r_cut, pos_cent, respect_pbc)
+            counts.append(nb.counts)
+            indptrs.append(nb.indptr.cpu().numpy())
+            fo = nb.frame_off.cpu().numpy()
+            offs.extend((fo[1:] + offs[-1]).tolist())
+            idxs.append(nb.indices.cpu().numpy())
+    if not counts:
+        dev_counts = torch.empty((0, ix_cent.size), dtype=torch.int32, device=frames.device())
+        return NeighbourList(ag_env, dev_counts, np.zeros((0, ix_cent.size + 1), np.int32),
+                             np.zeros(1, np.int64), np.zeros(0, np.int32))  # fmt: skip
+    return NeighbourList(
+        ag_env,
+        torch.cat(counts, dim=0),
+        np.concatenate(indptrs, axis=0),
+        np.asarray(offs, dtype=np.int64),
+        np.concatenate(idxs),
+    )

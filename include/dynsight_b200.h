@@ -120,6 +120,11 @@ int dsg_timesoap(const double* d_soap, int n_particles, int n_frames, int n_comp
                  int64_t stride_i, int64_t stride_f, int delay, double* d_out, int64_t ld_out,
                  int64_t col0, void* stream);
 
+/* normalize_soap (timesoap/timesoap.py:13-58): n_vectors contiguous vectors of n_comp float64,
+ * out = v/|v| where |v| > 0 else 0. */
+int dsg_normalize_soap(const double* d_in, double* d_out, int64_t n_vectors, int n_comp,
+                       void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * SOAP power spectrum (replaces soapify/saponify.py:98-122, i.e. DScribe
  * SOAP(species, r_cut, n_max, l_max, periodic, sigma=1, rbf="gto").create, batched over frames).

@@ -1,0 +1,206 @@
+"""GPU tests through the drop-in Python API, written like the reference's own tests
+(tests/lens/test_lens.py, tests/neighbors/test_nn.py, tests/soap/test_soap.py,
+tests/tsoap/test_tsoap.py, tests/trajectory/test_trj.py) against the reference's golden files.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+from test_oracle_golden import SOAP_CASES
+
+pytestmark = pytest.mark.gpu
+
+# (r_cut, delay, centers, selection, n_jobs) -- tests/lens/conftest.py:6-74
+LENS_API_CASES = {
+    "c0": (3, 1, "all", "all", 1),
+    "c1": (4, 1, "all", "all", 1),
+    "c2": (4, 1, "id 1", "all", 1),
+    "c3": (4, 1, "all", "id 1", 1),
+    "c4": (4, 1, "all", "all", 2),
+    "c5": (4, 2, "all", "all", 1),
+}
+SOAP_API_CENTERS = {
+    "soap_c0": "all", "soap_c1": "all", "soap_c2": "all", "soap_c3": "not name C5",
+    "soap_c4": "name C3 or name C6", "soap_c5": "all", "trj_soap": "all",
+}  # fmt: skip
+
+
+@pytest.fixture(scope="module")
+def trj(balls7):
+    from dynsight_b200.trajectory import Trj
+    from dynsight_b200.universe import ArrayUniverse
+
+    return Trj(
+        ArrayUniverse(
+            balls7["positions"], balls7["dims"], balls7["names"], balls7["types"], balls7["ids"]
+        )
+    )
+
+
+@pytest.mark.parametrize("case", sorted(LENS_API_CASES))
+def test_lens(trj, ref_lens, case):
+    r_cut, delay, centers, selection, n_jobs = LENS_API_CASES[case]
+    got = trj.get_lens(r_cut=r_cut, delay=delay, centers=centers, selection=selection,
+                       n_jobs=n_jobs)  # fmt: skip
+    assert got.meta == {"name": "lens", "r_cut": r_cut, "delay": delay, "centers": centers,
+                        "selection": selection}  # fmt: skip
+    assert got.dataset.dtype == np.float64
+    assert np.allclose(ref_lens["lens_" + case], got.dataset, atol=1e-6)
+    assert np.array_equal(ref_lens["lens_" + case], got.dataset)
+
+
+@pytest.mark.parametrize("case", ["c0", "c1", "c2", "c3", "c4"])
+def test_nn(trj, ref_lens, case):
+    r_cut, _, centers, selection, n_jobs = LENS_API_CASES[case]
+    neigh, got = trj.get_coord_number(r_cut=r_cut, centers=centers, selection=selection,
+                                      n_jobs=n_jobs)  # fmt: skip
+    assert np.array_equal(ref_lens["nn_" + case], got.dataset)
+    assert len(neigh) == 201 and len(neigh[0]) == got.dataset.shape[0]
+
+
+def test_lens_2d(ref_lens, tmp_path):
+    """tests/lens/test_lens.py:66-92, including the box assignment loop over an XYZ universe."""
+    from dynsight_b200.trajectory import Trj
+
+    rng = np.random.default_rng(42)
+    coords = rng.random((100, 100, 3))
+    coords[..., 2] = 0.0
+    path = tmp_path / "random_2d.xyz"
+    with path.open("w") as fh:
+        for frame in coords:
+            print(coords.shape[1], file=fh)
+            print("# comment line", file=fh)
+            for atom in frame:
+                print("C", atom[0], atom[1], atom[2], file=fh)
+    trj_2d = Trj.init_from_xyz(path, dt=1.0)
+    for ts in trj_2d.universe.trajectory:
+        pos = trj_2d.universe.atoms.positions
+        lengths = pos.max(axis=0) - pos.min(axis=0)
+        lengths[2] = 0.5
+        ts.dimensions = np.concatenate([lengths, np.array([90, 90, 90])])
+    lens_pbc = trj_2d.get_lens(r_cut=0.1, respect_pbc=True)
+    _ = trj_2d.get_coord_number(r_cut=0.1, respect_pbc=True)
+    assert np.array_equal(ref_lens["lens_2d_pbc"], lens_pbc.dataset)
+    lens_fbc = trj_2d.get_lens(r_cut=0.1, respect_pbc=False)
+    _ = trj_2d.get_coord_number(r_cut=0.1, respect_pbc=False)
+    assert np.array_equal(ref_lens["lens_2d_fbc"], lens_fbc.dataset)
+
+
+@pytest.mark.parametrize("case", sorted(SOAP_CASES))
+def test_soap(trj, ref_soap, case):
+    r_cut, n_max, l_max, pbc, _ = SOAP_CASES[case]
+    got = trj.get_soap(r_cut=r_cut, n_max=n_max, l_max=l_max, respect_pbc=pbc,
+                       centers=SOAP_API_CENTERS[case])  # fmt: skip
+    assert got.meta["name"] == "soap" and got.meta["centers"] == SOAP_API_CENTERS[case]
+    assert np.allclose(ref_soap[case], got.dataset[:, ::10])  # test_soap.py:37 (rtol 1e-5)
+
+
+def test_tsoap(trj, ref_soap):
+    soap = trj.get_soap(r_cut=8, n_max=4, l_max=4)
+    for delay, key in ((1, "tsoap_c0"), (4, "tsoap_c2")):
+        _, ts = trj.get_timesoap(soap_insight=soap, delay=delay)
+        assert ts.meta["name"] == "timesoap" and ts.meta["delay"] == delay
+        assert np.allclose(ref_soap[key], ts.dataset, atol=1e-6)
+    soap4 = trj.get_soap(r_cut=4, n_max=4, l_max=4)
+    _, ts = trj.get_timesoap(soap_insight=soap4, delay=1)
+    assert np.allclose(ref_soap["tsoap_c1"], ts.dataset, atol=1e-6)
+
+
+def test_get_descriptors_like_test_trj(trj, ref_lens, ref_soap):
+    """tests/trajectory/test_trj.py:75-106 (hot-path descriptors only)."""
+    r_cut = 15.0
+    neigcounts, n_c = trj.get_coord_number(r_cut=r_cut)
+    lens = trj.get_lens(r_cut=r_cut)
+    soap, tsoap = trj.get_timesoap(r_cut=10.0, n_max=8, l_max=8)
+    np.testing.assert_allclose(ref_lens["trj_n_c"], n_c.dataset, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(ref_lens["trj_lens"], lens.dataset, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(ref_soap["trj_soap"], soap.dataset[:, ::10], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(ref_soap["trj_tsoap"], tsoap.dataset, rtol=1e-3, atol=1e-6)
+    # neighbour AtomGroups: same members as the CSR rows
+    first = neigcounts[0][0]
+    assert len(first) == int(n_c.dataset[0, 0])
+    # second call re-using the neighbour list
+    _, n_c2 = trj.get_coord_number(r_cut=r_cut, neigcounts=neigcounts)
+    assert np.array_equal(n_c2.dataset, n_c.dataset)
+    _, n_c3 = trj.get_coord_number(r_cut=r_cut, neigcounts=[list(fr) for fr in neigcounts[:3]])
+    assert np.array_equal(n_c3.dataset, n_c.dataset[:, :3])
+
+
+def test_trajslice_and_batching_match_oracle(balls7):
+    """Sliced trajectories and small frame batches (halo of `delay` frames between batches)."""
+    from dynsight_b200 import lens as dlens
+    from dynsight_b200 import soap as dsoap
+    from dynsight_b200.universe import ArrayUniverse
+    from golden_cases import fluid_case
+
+    from oracle import lens_oracle as lo
+    from oracle import soap_oracle as so
+    from oracle import timesoap_oracle as to
+
+    pos, box, r_cut = fluid_case(n_side=9, n_frames=12)
+    dims = np.tile(np.concatenate([box, [90, 90, 90]]).astype(np.float32), (12, 1))
+    u = ArrayUniverse(pos, dims, names=["O"] * pos.shape[1])
+    sl = slice(1, 12, 2)
+    frames = list(range(12))[sl]
+    for delay in (1, 2):
+        want = lo.compute_lens_arrays(pos, dims, r_cut, delay=delay, frames=frames)
+        for bf in (None, 3, 4):
+            got = dlens.compute_lens_device(u, r_cut, delay, trajslice=sl, batch_frames=bf)
+            assert np.array_equal(got.cpu().numpy(), want), (delay, bf)
+    with pytest.raises(RuntimeError, match="No valid pairs found."):
+        dlens.compute_lens(u, r_cut, delay=6, trajslice=sl)
+    # SOAP -> timeSOAP without materialising SOAP, in overlapping batches
+    cent = "index 0:40"
+    soap = so.soap_trajectory(pos[frames] * 3.0, np.full(pos.shape[1], 8), np.arange(41),
+                              dims[frames, :3] * 3.0, 4.0, 4, 3)  # fmt: skip
+    u3 = ArrayUniverse(pos * 3.0, dims * np.array([3, 3, 3, 1, 1, 1], dtype=np.float32),
+                       names=["O"] * pos.shape[1])  # fmt: skip
+    for bf in (None, 3):
+        got = dsoap.timesoap_from_trajectory(u3, 4.0, 4, 3, delay=2, centers=cent, trajslice=sl,
+                                             batch_frames=bf).cpu().numpy()  # fmt: skip
+        want = to.timesoap(soap, 2)
+        assert np.all(np.abs(got - want) <= 1e-5 * np.abs(want) + 1e-7)
+
+
+def test_soap_small_api_functions():
+    from dynsight_b200 import soap as dsoap
+    from golden_cases import random_soap_spectra
+
+    from oracle import timesoap_oracle as to
+
+    s = random_soap_spectra()
+    assert np.allclose(dsoap.normalize_soap(s), to.normalize_soap(s), rtol=1e-12, atol=0)
+    d = dsoap.soap_distance(s[:, 0], s[:, 1])
+    assert np.allclose(d, to.soap_distance(s[:, 0], s[:, 1]), atol=1e-7)
+    assert np.isclose(dsoap.soap_distance(s[7, 0], s[7, 1]), to.soap_distance(s[7, 0], s[7, 1]))
+    assert np.allclose(dsoap.timesoap(s, 2), to.timesoap(s, 2), atol=1e-7)
+    with pytest.raises(ValueError, match="delay value outside bounds"):
+        dsoap.timesoap(s, 9)
+
+
+def test_multi_species_via_types():
+    """Species come from atom types; order = ascending atomic number (DScribe), unpinned by the
+    reference, checked against the oracle's convention."""
+    from dynsight_b200 import soap as dsoap
+    from dynsight_b200.universe import ArrayUniverse
+
+    from oracle import soap_oracle as so
+
+    rng = np.random.default_rng(8)
+    n = 120
+    box = np.array([26.5, 27.0, 28.0], dtype=np.float32)
+    pos = (rng.random((2, n, 3)) * box).astype(np.float32)
+    types = np.array(["O", "H", "Cu"])[rng.integers(0, 3, n)]
+    types[:3] = ["Cu", "H", "O"]
+    dims = np.tile(np.concatenate([box, [90, 90, 90]]).astype(np.float32), (2, 1))
+    u = ArrayUniverse(pos, dims, names=types, types=types)
+    got = dsoap.saponify_trajectory(u, 4.5, 4, 4, centers="type O or type Cu")
+    z = np.array([{"H": 1, "O": 8, "Cu": 29}[t] for t in types])
+    cent = np.nonzero((types == "O") | (types == "Cu"))[0]
+    want = so.soap_trajectory(pos, z, cent, dims[:, :3].astype(float), 4.5, 4, 4)
+    assert got.shape == want.shape == (len(cent), 2, 3 * 4 * (3 * 4 + 1) // 2 * 5)
+    scale = np.abs(want).max(axis=-1, keepdims=True)
+    assert (np.abs(got - want) / scale).max() < 1e-8
+    with pytest.raises(KeyError, match="not a chemical symbol"):
+        dsoap.saponify_trajectory(ArrayUniverse(pos, dims, names=["Qq"] * n, types=["Qq"] * n), 4.5)

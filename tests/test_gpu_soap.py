@@ -1,0 +1,162 @@
+"""GPU parity: SOAP power spectrum through the C ABI vs the reference's DScribe goldens and the
+CPU oracle.
+
+Tolerance (BASELINE.json north_star: 1e-5 relative): |d| <= 1e-5 * max|p| per vector; the kernel
+is float64 so the observed error is ~1e-10, and the tests assert a 1e-8 bar to catch regressions.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+from test_oracle_golden import SOAP_CASES
+
+from oracle import soap_oracle as so
+from oracle import timesoap_oracle as to
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-8
+
+
+def _rel_err(got: np.ndarray, want: np.ndarray) -> float:
+    scale = np.abs(want).max(axis=-1, keepdims=True)
+    return float((np.abs(got - want) / scale).max())
+
+
+def _soap_gpu(pos, species_idx, centres, box, r_cut, n_max, l_max, dtype=torch.float32):
+    from dynsight_b200 import engine
+
+    return (
+        engine.soap_power_spectrum(
+            torch.as_tensor(np.ascontiguousarray(pos)).to(dtype).cuda(),
+            torch.as_tensor(np.asarray(species_idx, dtype=np.int32)).cuda(),
+            torch.as_tensor(np.asarray(centres, dtype=np.int32)).cuda(),
+            box, r_cut, n_max, l_max,
+        )
+        .cpu()
+        .numpy()
+    )  # fmt: skip
+
+
+@pytest.mark.parametrize("case", sorted(SOAP_CASES))
+def test_dscribe_goldens(balls7, ref_soap, case):
+    """tests/soap/conftest.py:6-74 + tests/trajectory/test_trj.py:82 (golden frames 0::10)."""
+    r_cut, n_max, l_max, pbc, cent = SOAP_CASES[case]
+    pos = balls7["positions"]
+    box = balls7["dims"][:, :3] if pbc else None
+    got = _soap_gpu(pos, np.zeros(7), cent, box, r_cut, n_max, l_max)
+    gold = ref_soap[case]
+    assert got.shape == (len(cent), 201, gold.shape[2])
+    assert _rel_err(got[:, ::10], gold) < REL
+
+
+def test_tsoap_goldens_end_to_end(balls7, ref_soap):
+    """tests/tsoap/conftest.py:6-35 and test_trj.py:104-106: SOAP kernel -> timeSOAP kernel."""
+    from dynsight_b200 import engine
+
+    pos = torch.as_tensor(balls7["positions"]).cuda()
+    sp = torch.zeros(7, dtype=torch.int32, device="cuda")
+    cen = torch.arange(7, dtype=torch.int32, device="cuda")
+    box = balls7["dims"][:, :3]
+    soap44 = engine.soap_power_spectrum(pos, sp, cen, box, 8.0, 4, 4)
+    t1 = engine.timesoap_device(soap44, 1).cpu().numpy()
+    t4 = engine.timesoap_device(soap44, 4).cpu().numpy()
+    assert np.allclose(t1, ref_soap["tsoap_c0"], atol=1e-6, rtol=0)
+    assert np.allclose(t4, ref_soap["tsoap_c2"], atol=1e-6, rtol=0)
+    soap88 = engine.soap_power_spectrum(pos, sp, cen, box, 10.0, 8, 8)
+    t = engine.timesoap_device(soap88, 1).cpu().numpy()
+    assert np.allclose(t, ref_soap["trj_tsoap"], atol=1e-6, rtol=1e-3)
+    # rc=4: no neighbours inside the cutoff region -> identical spectra -> timeSOAP ~ 0 (golden c1)
+    soap_rc4 = engine.soap_power_spectrum(pos, sp, cen, box, 4.0, 4, 4)
+    t = engine.timesoap_device(soap_rc4, 1).cpu().numpy()
+    assert np.allclose(t, ref_soap["tsoap_c1"], atol=1e-6, rtol=0)
+
+
+def test_doctest_known_answers(xyz60):
+    """saponify.py:86-87 / :174 and timesoap.py:50-52, :115-116, :172-173 (rtol 1e-3), no box."""
+    from dynsight_b200 import engine
+
+    soap_t = engine.soap_power_spectrum(
+        torch.as_tensor(xyz60["positions"]).cuda(),
+        torch.zeros(60, dtype=torch.int32, device="cuda"),
+        torch.arange(60, dtype=torch.int32, device="cuda"),
+        None, 2.0, 8, 8,
+    )  # fmt: skip
+    soap = soap_t.cpu().numpy()
+    assert soap.shape == (60, 20, 324)
+    assert np.isclose(soap[0].sum(), float(xyz60["kat_soap0_sum"]), atol=1e-6, rtol=1e-3)
+    tsoap = engine.timesoap_device(soap_t, 1).cpu().numpy()
+    assert np.isclose(tsoap.sum(), float(xyz60["kat_tsoap_sum"]), atol=1e-6, rtol=1e-3)
+    assert np.isclose(tsoap[0, 0], float(xyz60["kat_dist01"]), atol=1e-6, rtol=1e-3)
+    want = so.soap_trajectory(xyz60["positions"][:2], np.zeros(60, int), np.arange(60), None, 2.0, 8, 8)
+    assert _rel_err(soap[:, :2], want) < REL
+
+
+@pytest.mark.parametrize(
+    ("n_atoms", "box_l", "r_cut", "n_max", "l_max", "n_species", "dtype"),
+    [
+        (400, 31.0, 5.0, 8, 8, 1, torch.float32),   # wide cells on all axes (31 > 3 * 8.72)
+        (300, 19.0, 5.0, 8, 8, 1, torch.float64),   # narrow: explicit image loop, float64 input
+        (60, 7.5, 4.0, 4, 5, 1, torch.float32),     # box < search radius: several images per atom
+        (250, 27.0, 5.0, 8, 10, 3, torch.float32),  # 3 species, l_max = 10 (cfg4 parameters)
+        (200, 28.0, 4.5, 6, 3, 2, torch.float32),   # 2 species, odd l_max
+        (150, 30.0, 5.5, 12, 2, 1, torch.float32),  # n_max > 8: two radial blocks
+        (220, 33.0, 6.0, 3, 12, 2, torch.float32),  # l_max = 12
+    ],
+)
+def test_random_boxes_vs_oracle(n_atoms, box_l, r_cut, n_max, l_max, n_species, dtype):
+    rng = np.random.default_rng(n_atoms + n_max * 100 + l_max)
+    box = np.array([box_l, box_l * 1.1, box_l * 0.93])
+    pos = (rng.random((2, n_atoms, 3)) * 1.3 - 0.15) * box  # some atoms outside the box
+    if dtype == torch.float32:
+        pos = pos.astype(np.float32)
+    sp_idx = rng.integers(0, n_species, n_atoms)
+    sp_idx[:n_species] = np.arange(n_species)
+    zs = np.array([1, 8, 29])[:n_species]
+    centres = np.sort(rng.choice(n_atoms, size=min(n_atoms, 23), replace=False))
+    got = _soap_gpu(pos, sp_idx, centres, box, r_cut, n_max, l_max, dtype)
+    want = so.soap_trajectory(
+        pos, zs[sp_idx], centres, np.tile(box, (2, 1)), r_cut, n_max, l_max
+    )
+    assert got.shape == want.shape
+    assert _rel_err(got, want) < REL
+
+
+def test_non_periodic_cluster_vs_oracle():
+    rng = np.random.default_rng(4)
+    pos = (rng.normal(size=(3, 500, 3)) * 9.0).astype(np.float32)
+    centres = np.arange(0, 500, 17)
+    got = _soap_gpu(pos, np.zeros(500), centres, None, 5.0, 8, 8)
+    want = so.soap_trajectory(pos, np.zeros(500, int), centres, None, 5.0, 8, 8)
+    assert _rel_err(got, want) < REL
+
+
+def test_invariances_at_bench_scale():
+    """cfg2-like frame (10k atoms): rotation + translation + permutation invariance of the power
+    spectrum, and agreement with the oracle on a few centres."""
+    from dynsight_b200 import engine
+
+    rng = np.random.default_rng(0)
+    n = 10_000
+    box_l = (n / 0.0334) ** (1 / 3)
+    pos = (rng.random((1, n, 3)) * box_l).astype(np.float64)
+    box = np.full(3, box_l)
+    sp = torch.zeros(n, dtype=torch.int32, device="cuda")
+    cen = torch.arange(n, dtype=torch.int32, device="cuda")
+    base = engine.soap_power_spectrum(torch.as_tensor(pos).cuda(), sp, cen, box, 5.0, 8, 8)
+    # cubic-group rotation (x,y,z)->(y,z,x) keeps the box, plus a translation and a permutation
+    perm = rng.permutation(n)
+    pos2 = (pos[:, :, [1, 2, 0]] + np.array([3.3, -7.1, 11.9]))[:, perm]
+    other = engine.soap_power_spectrum(torch.as_tensor(pos2).cuda(), sp, cen, box, 5.0, 8, 8)
+    a = base.cpu().numpy()[perm, 0]
+    b = other.cpu().numpy()[:, 0]
+    assert _rel_err(b, a) < 1e-9
+    pick = np.arange(0, n, n // 12)[:12]
+    want = so.soap_trajectory(pos, np.zeros(n, int), pick, np.tile(box, (1, 1)), 5.0, 8, 8)
+    assert _rel_err(base.cpu().numpy()[pick], want) < REL
+    # timeSOAP of identical frames is (numerically) zero
+    two = torch.cat([base, base], dim=1)
+    assert float(engine.timesoap_device(two, 1).abs().max()) <= 1e-7
+    _ = to

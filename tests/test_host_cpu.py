@@ -1,0 +1,223 @@
+"""CPU-only tests of the host logic: Universe shim, selections, readers, frame batching plans,
+the C-ABI surface (symbols vs header) and the "no oracle / no fallback in the product" rule."""
+
+from __future__ import annotations
+
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _universe(balls7):
+    from dynsight_b200.universe import ArrayUniverse
+
+    return ArrayUniverse(
+        balls7["positions"], balls7["dims"], balls7["names"], balls7["types"], balls7["ids"]
+    )
+
+
+def test_selection_language(balls7):
+    u = _universe(balls7)
+    assert u.select_atoms("all").n_atoms == 7
+    assert u.select_atoms("id 1").indices.tolist() == [0]
+    assert u.select_atoms("name C3 or name C6").indices.tolist() == [2, 5]
+    assert u.select_atoms("not name C5").indices.tolist() == [0, 1, 2, 3, 5, 6]
+    assert u.select_atoms("type C").n_atoms == 7
+    assert u.select_atoms("type O").n_atoms == 0
+    assert u.select_atoms("id 2:4 and not name C3").indices.tolist() == [1, 3]
+    assert u.select_atoms("(name C1 C2) or index 6").indices.tolist() == [0, 1, 6]
+    sub = u.select_atoms("not name C5")
+    assert sub.select_atoms("name C6 C5").indices.tolist() == [5]
+    with pytest.raises(ValueError):
+        u.select_atoms("frobnicate 3")
+    with pytest.raises(ValueError):
+        u.select_atoms("name")
+
+
+def test_universe_surface(balls7):
+    u = _universe(balls7)
+    assert u.trajectory.n_frames == 201 and len(u.trajectory) == 201
+    ag = u.select_atoms("name C3 or name C6")
+    u.trajectory[5]
+    assert np.array_equal(ag.positions, balls7["positions"][5][[2, 5]])
+    assert np.array_equal(u.trajectory.ts.dimensions, balls7["dims"][5])
+    assert np.array_equal(u.atoms.positions, balls7["positions"][5])
+    seen = [ts.frame for ts in u.trajectory[10:20:3]]
+    assert seen == [10, 13, 16, 19]
+    assert ag[np.array([1])].indices.tolist() == [5]
+    assert len(ag) == 2 and ag.atoms.types.tolist() == ["C", "C"]
+
+
+def test_xyz_box_assignment_broadcasts_like_mdanalysis():
+    """with a box-less reader the last assigned box wins."""
+    from dynsight_b200.universe import ArrayUniverse
+
+    u = ArrayUniverse(np.zeros((4, 3, 3), dtype=np.float32))
+    assert u.trajectory.ts.dimensions is None
+    for k, ts in enumerate(u.trajectory):
+        ts.dimensions = np.array([1.0 + k, 2, 3, 90, 90, 90])
+    u.trajectory[0]
+    assert u.trajectory.ts.dimensions[0] == 4.0
+
+
+def test_readers_roundtrip(tmp_path, balls7):
+    from dynsight_b200 import io as dio
+
+    # xyz
+    p = tmp_path / "t.xyz"
+    pos = balls7["positions"][:3]
+    with p.open("w") as fh:
+        for fr in pos:
+            fh.write(f"{fr.shape[0]}\ncomment\n")
+            for a in fr:
+                fh.write(f"C {a[0]!r} {a[1]!r} {a[2]!r}\n".replace("np.float32(", "").replace(")", ""))
+    topo, got = dio.read_xyz(p)
+    assert np.array_equal(got, pos) and topo.types.tolist() == ["C"] * 7
+    # uncompressed xtc written by hand
+    import struct
+
+    raw = b""
+    for k, fr in enumerate(pos):
+        raw += struct.pack(">iiif", 1995, 7, k, float(k))
+        raw += struct.pack(">9f", 3, 0, 0, 0, 3, 0, 0, 0, 3)
+        raw += struct.pack(">i", 7)
+        raw += struct.pack(">21f", *(fr / np.float32(10)).ravel().tolist())
+    q = tmp_path / "t.xtc"
+    q.write_bytes(raw)
+    got, dims = dio.read_xtc_uncompressed(q)
+    assert got.shape == (3, 7, 3) and np.allclose(got, pos, atol=1e-4)
+    assert np.array_equal(dims[0], np.array([30, 30, 30, 90, 90, 90], dtype=np.float32))
+    (tmp_path / "bad.xtc").write_bytes(struct.pack(">ii", 1995, 100) + b"\0" * 100)
+    with pytest.raises(NotImplementedError):
+        dio.read_xtc_uncompressed(tmp_path / "bad.xtc")
+
+
+def test_frame_sequence_and_batch_plan():
+    from dynsight_b200 import frames
+
+    assert frames.frame_sequence(10, None) == list(range(10))
+    assert frames.frame_sequence(10, slice(2, 9, 3)) == [2, 5, 8]
+    assert frames.pick_batch_frames(1000, 100.0, 3, budget_bytes=1e6) == 10
+    assert frames.pick_batch_frames(10**6, 100.0, 3, budget_bytes=1e6) == 3
+    assert frames.pick_batch_frames(10, 1.0, 1) <= 4096
+
+
+def test_basis_matches_dscribe_recipe():
+    from dynsight_b200 import soap_basis
+
+    alphas, betas = soap_basis.gto_basis(8.0, 4, 4)
+    assert alphas.shape == (5, 4) and betas.shape == (5, 4, 4)
+    # alpha_{l,0} = ln(1000) for every l because a_0 = 1
+    assert np.allclose(alphas[:, 0], np.log(1000.0))
+    # betas orthonormalise the overlap: beta S beta^T = 1
+    from math import gamma
+
+    for l in range(5):
+        m = alphas[l][:, None] + alphas[l][None, :]
+        s = 0.5 * gamma(l + 1.5) * m ** (-(l + 1.5))
+        assert np.allclose(betas[l] @ s @ betas[l].T, np.eye(4), atol=1e-8)
+    assert soap_basis.n_features(1, 8, 8) == 324
+    assert soap_basis.n_features(3, 8, 10) == 3300
+    with pytest.raises(ValueError):
+        soap_basis.gto_basis(0.5, 4, 4)
+
+
+def test_fill_soap_vector_shapes():
+    from dynsight_b200 import soap
+
+    x = np.arange(2 * 3 * 324, dtype=np.float64).reshape(2, 3, 324)
+    full = soap.fill_soap_vector_from_dscribe(x)
+    assert full.shape == (2, 3, 576)  # doctest saponify.py:174
+    blk = full[0, 0].reshape(9, 8, 8)
+    assert np.array_equal(blk, np.transpose(blk, (0, 2, 1)))
+    assert soap.fill_soap_vector_from_dscribe(x[0]).shape == (3, 576)
+    assert soap.fill_soap_vector_from_dscribe(x[0, 0]).shape == (576,)
+    from oracle import soap_oracle
+
+    assert np.array_equal(full, soap_oracle.fill_soap_vector(x))
+
+
+def test_api_errors_without_gpu(balls7):
+    """Errors the reference raises before any compute must not need a GPU either."""
+    from dynsight_b200.trajectory import Insight, Trj
+
+    trj = Trj(_universe(balls7))
+    assert (trj.n_atoms, trj.n_frames) == (7, 201)
+    assert trj.with_slice(slice(0, 50, 5)).n_frames == 10
+    with pytest.raises(ValueError, match="r_cut, n_max e l_max cannot be None"):
+        trj.get_timesoap()
+    bad = Insight(np.zeros((2, 3, 4)), {"name": "lens"})
+    with pytest.raises(ValueError, match="must be 'soap'"):
+        trj.get_timesoap(soap_insight=bad)
+    with pytest.raises(ValueError, match="dataset.ndim != 3."):
+        Insight(np.zeros((2, 3)), {}).get_angular_velocity()
+    with pytest.raises(ValueError, match="delay value outside bounds"):
+        Insight(np.zeros((2, 3, 4)), {"name": "soap"}).get_angular_velocity(delay=3)
+    coords = trj.with_slice(slice(0, 4)).get_coordinates("name C1")
+    assert coords.shape == (4, 1, 3)
+
+
+def test_insight_json_roundtrip(tmp_path):
+    from dynsight_b200.trajectory import Insight
+
+    ins = Insight(np.arange(6, dtype=np.float64).reshape(2, 3), {"name": "lens", "r_cut": 3.0})
+    ins.dump_to_json(tmp_path / "a.json")
+    back = Insight.load_from_json(tmp_path / "a.json")
+    assert np.array_equal(back.dataset, ins.dataset) and back.meta == ins.meta
+    (tmp_path / "e.json").write_text("{}")
+    with pytest.raises(ValueError, match="'dataset_file' key not found"):
+        Insight.load_from_json(tmp_path / "e.json")
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library loads and exports every function include/dynsight_b200.h declares
+    (no compute calls here: there is no GPU in the CPU test environment)."""
+    from dynsight_b200 import _lib
+    from dynsight_b200.build import build_library
+
+    build_library()
+    header = (ROOT / "include" / "dynsight_b200.h").read_text()
+    declared = set(re.findall(r"\b(dsg_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), "ctypes table and header disagree"
+    loaded = _lib.load()
+    assert b"sm_100a" in loaded.dsg_version()
+    assert loaded.dsg_soap_n_features(1, 8, 8) == 324
+    # argument validation happens before any CUDA call
+    n = ctypes.c_size_t(0)
+    box = np.array([10.0, 10.0, 10.0])
+    assert loaded.dsg_neigh_workspace_bytes(1, 10, 10, 1, box.ctypes.data, 2.0, ctypes.byref(n)) == 0
+    assert n.value > 0
+    assert loaded.dsg_neigh_workspace_bytes(1, 10, 10, 1, box.ctypes.data, -1.0, ctypes.byref(n)) < 0
+    assert b"r_cut" in loaded.dsg_last_error()
+
+
+def test_product_never_touches_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may use oracle/."""
+    for path in (ROOT / "dynsight_b200").rglob("*"):
+        if path.suffix in {".py", ".cu", ".cuh", ".h"}:
+            text = path.read_text()
+            assert "oracle" not in text.lower(), f"{path} mentions the oracle"
+            assert "/root/reference" not in text, f"{path} reads the reference tree"
+
+
+def test_no_cuda_means_loud_failure(balls7):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from dynsight_b200.trajectory import Trj
+
+    trj = Trj(_universe(balls7))
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        trj.get_lens(r_cut=15.0)
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        trj.get_soap(r_cut=8.0, n_max=4, l_max=4)
