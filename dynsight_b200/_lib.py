@@ -28,6 +28,7 @@ SIGNATURES: dict[str, tuple] = {
     "dsg_last_error": (ctypes.c_char_p, []),
     "dsg_device_arch": (_c_int, []),
     "dsg_launch_count": (ctypes.c_longlong, []),
+    "dsg_fp64_fma_probe": (_c_int, [_c_ptr, _c_int, _c_int, _c_ptr, ctypes.POINTER(_c_dbl)]),
     "dsg_neigh_workspace_bytes": (
         _c_int, [_c_int, _c_int, _c_int, _c_int, _c_ptr, _c_dbl, ctypes.POINTER(_c_size)],
     ),

@@ -23,7 +23,33 @@ int set_error(int code, const char* fmt, ...) {
     return code;
 }
 
+// fp64 FMA throughput probe: 16 independent chains per thread, `iters` rounds.
+__global__ void __launch_bounds__(256) fp64_fma_probe_kernel(double* out, int iters, double seed) {
+    double a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = seed + (double)(threadIdx.x + k);
+    const double m = 1.0000001, c = 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a[k] = fma(a[k], m, c);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += a[k];
+    if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;  // keep the work alive
+}
+
 }  // namespace dsg
+
+extern "C" int dsg_fp64_fma_probe(double* d_scratch, int blocks, int iters, void* stream,
+                                  double* flops_out) {
+    if (!d_scratch || blocks < 1 || iters < 1)
+        return dsg::set_error(DSG_ERR_INVALID_ARGUMENT, "bad probe arguments");
+    dsg::fp64_fma_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_scratch, iters, 1.0);
+    DSG_LAUNCH_CHECK("fp64_fma_probe_kernel");
+    if (flops_out) *flops_out = 2.0 * 16.0 * 256.0 * (double)blocks * (double)iters;
+    return DSG_OK;
+}
 
 extern "C" const char* dsg_version(void) { return "dynsight_b200 0.1.0 (sm_100a)"; }
 

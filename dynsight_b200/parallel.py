@@ -1,0 +1,110 @@
+"""Frame-block sharding of a trajectory across the GPUs of one box (one process per GPU).
+
+Neighbour lists, coordination numbers and SOAP are independent per frame; LENS and timeSOAP
+couple frame ``t`` with ``t + delay`` only.  So the trajectory is cut into
+contiguous frame blocks, rank ``r`` owning ``[F*r/W, F*(r+1)/W)``, and the only data that crosses
+ranks is a halo of ``delay`` frames of positions that each rank receives from its successor
+(``torch.distributed`` send/recv: NCCL over NVLink on GPUs, gloo on CPU tensors in the tests).
+Outputs stay on the rank that produced them (rank ``r`` holds the pairs that start in its block);
+``gather_columns`` concatenates them on demand.  There is no reduction and no all-to-all.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass(frozen=True)
+class FrameShard:
+    rank: int
+    world: int
+    n_frames: int  # frames of the whole (sliced) trajectory
+    delay: int
+    start: int  # first owned frame (position in the frame sequence)
+    stop: int  # one past the last owned frame
+
+    @property
+    def n_owned(self) -> int:
+        return self.stop - self.start
+
+    @property
+    def halo(self) -> int:
+        """Frames needed from the following ranks so that every owned frame ``t`` with
+        ``t + delay < n_frames`` finds its partner."""
+        return max(0, min(self.n_frames, self.stop + self.delay) - self.stop)
+
+    @property
+    def n_pairs_owned(self) -> int:
+        """Pairs (t, t+delay) whose first frame is owned by this rank."""
+        return max(0, min(self.stop, self.n_frames - self.delay) - self.start)
+
+
+def shard_frames(n_frames: int, world: int, rank: int, delay: int = 1) -> FrameShard:
+    """Contiguous block ``[F*r/W, F*(r+1)/W)`` of rank ``r``."""
+    if world < 1 or not 0 <= rank < world:
+        msg = f"bad rank {rank} / world {world}"
+        raise ValueError(msg)
+    start = n_frames * rank // world
+    stop = n_frames * (rank + 1) // world
+    return FrameShard(rank, world, n_frames, delay, start, stop)
+
+
+def exchange_halo(
+    owned: torch.Tensor, shard: FrameShard, group: dist.ProcessGroup | None = None
+) -> torch.Tensor:
+    """Return ``owned`` (n_owned, ...) extended by the halo frames received from the next rank.
+
+    Rank ``r > 0`` sends its first ``halo(r-1)`` frames to rank ``r-1``; rank ``r < W-1`` receives
+    ``halo(r)`` frames from rank ``r+1``.  Both sides derive the counts from :func:`shard_frames`,
+    so one message per neighbour pair suffices.  Blocks must be at least ``delay`` frames long
+    (except the last one).  Works on CUDA tensors (NCCL) and CPU tensors (gloo).
+    """
+    if shard.world == 1:
+        return owned
+    if owned.shape[0] != shard.n_owned:
+        msg = f"rank {shard.rank}: got {owned.shape[0]} frames, owns {shard.n_owned}"
+        raise ValueError(msg)
+    ops = []
+    recv_buf = None
+    if shard.rank > 0:
+        prev = shard_frames(shard.n_frames, shard.world, shard.rank - 1, shard.delay)
+        if prev.halo > shard.n_owned:
+            msg = (
+                f"frame block of rank {shard.rank} ({shard.n_owned} frames) is shorter than the "
+                f"halo of {prev.halo} frames: use fewer ranks or a smaller delay"
+            )
+            raise ValueError(msg)
+        if prev.halo > 0:
+            ops.append(dist.P2POp(dist.isend, owned[: prev.halo].contiguous(), shard.rank - 1,
+                                  group))  # fmt: skip
+    if shard.rank < shard.world - 1 and shard.halo > 0:
+        recv_buf = torch.empty((shard.halo, *owned.shape[1:]), dtype=owned.dtype,
+                               device=owned.device)  # fmt: skip
+        ops.append(dist.P2POp(dist.irecv, recv_buf, shard.rank + 1, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return owned if recv_buf is None else torch.cat([owned, recv_buf], dim=0)
+
+
+def gather_columns(
+    local: torch.Tensor, group: dist.ProcessGroup | None = None
+) -> torch.Tensor | None:
+    """Concatenate per-rank result slabs (n_centers, n_local_pairs) along the frame axis on
+    rank 0 (other ranks return ``None``).  Slab widths may differ between ranks."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    width = torch.tensor([local.shape[1]], dtype=torch.int64, device=local.device)
+    widths = [torch.zeros_like(width) for _ in range(world)]
+    dist.all_gather(widths, width, group=group)
+    max_w = int(max(int(w.item()) for w in widths))
+    padded = torch.zeros((local.shape[0], max_w), dtype=local.dtype, device=local.device)
+    padded[:, : local.shape[1]] = local
+    out = [torch.zeros_like(padded) for _ in range(world)]
+    dist.all_gather(out, padded, group=group)
+    if rank != 0:
+        return None
+    return torch.cat([o[:, : int(w.item())] for o, w in zip(out, widths)], dim=1)

@@ -46,6 +46,10 @@ int dsg_device_arch(void);
 /* Number of kernel launches this library has issued in the process (monotonic counter;
  * bench.py differences it around the timed region to report "gpu_launches"). */
 long long dsg_launch_count(void);
+/* Measurement aid (bench.py): launches `blocks` x 256 threads doing `iters` rounds of 16 independent
+ * float64 FMAs each; *flops_out = floating-point operations issued.  d_scratch needs blocks*256
+ * doubles.  Timed by the caller with CUDA events to obtain the fp64 FMA peak of the device. */
+int dsg_fp64_fma_probe(double* d_scratch, int blocks, int iters, void* stream, double* flops_out);
 
 /* ------------------------------------------------------------------------------------------
  * Neighbour lists (replaces lens/lens.py:29-147: build_cell_list +

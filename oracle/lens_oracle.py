@@ -26,7 +26,7 @@ def build(force: bool = False) -> Path:
     src = _HERE / "lens_oracle.c"
     if force or not so.exists() or so.stat().st_mtime < src.stat().st_mtime:
         subprocess.run(
-            ["gcc", "-O2", "-fPIC", "-fopenmp", "-std=c11", "-shared", "-o", str(so), str(src),
+            ["/usr/bin/gcc" if __import__("os").path.exists("/usr/bin/gcc") else "gcc", "-O2", "-fPIC", "-fopenmp", "-std=c11", "-shared", "-o", str(so), str(src),
              "-lm"],
             check=True,
         )  # fmt: skip

@@ -233,3 +233,72 @@ def fill_soap_vector(soap: np.ndarray, lmax: int = 8, nmax: int = 8) -> np.ndarr
     if len(shape) == 2:  # noqa: PLR2004
         return out.squeeze(1)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# C / OpenMP version (oracle/soap_oracle.c): same algorithm, used as the timed CPU baseline
+# ---------------------------------------------------------------------------------------------
+_CLIB = None
+
+
+def _clib():
+    global _CLIB  # noqa: PLW0603
+    if _CLIB is None:
+        import ctypes
+        import subprocess
+        from pathlib import Path
+
+        here = Path(__file__).resolve().parent
+        so_path, src = here / "libsoap_oracle.so", here / "soap_oracle.c"
+        if not so_path.exists() or so_path.stat().st_mtime < src.stat().st_mtime:
+            subprocess.run(
+                ["/usr/bin/gcc" if __import__("os").path.exists("/usr/bin/gcc") else "gcc", "-O2", "-fPIC", "-fopenmp", "-std=c11", "-shared", "-o", str(so_path),
+                 str(src), "-lm"],
+                check=True,
+            )  # fmt: skip
+        _CLIB = ctypes.CDLL(str(so_path))
+        _CLIB.dsgo_soap_frame.restype = ctypes.c_int
+        _CLIB.dsgo_soap_frame.argtypes = [
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+            ctypes.c_int, ctypes.c_void_p, ctypes.c_double, ctypes.c_int, ctypes.c_int,
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+        ]  # fmt: skip
+        _CLIB.dsgo_soap_set_num_threads.argtypes = [ctypes.c_int]
+    return _CLIB
+
+
+def soap_frame_c(
+    pos: np.ndarray,
+    species_z: np.ndarray,
+    centre_idx: np.ndarray,
+    cell: np.ndarray | None,
+    r_cut: float,
+    n_max: int,
+    l_max: int,
+    basis: tuple[np.ndarray, np.ndarray] | None = None,
+    n_threads: int | None = None,
+) -> np.ndarray:
+    """Same contract as :func:`soap_frame`, evaluated by the C/OpenMP restatement."""
+    lib = _clib()
+    if n_threads is not None:
+        lib.dsgo_soap_set_num_threads(int(n_threads))
+    alphas, betas = basis if basis is not None else gto_basis(r_cut, n_max, l_max)
+    alphas = np.ascontiguousarray(alphas)
+    betas = np.ascontiguousarray(betas)
+    p = np.ascontiguousarray(pos, dtype=np.float64)
+    zs, sp = np.unique(species_z, return_inverse=True)
+    sp = np.ascontiguousarray(sp, dtype=np.int32)
+    cen = np.ascontiguousarray(centre_idx, dtype=np.int32)
+    n_sp = len(zs)
+    n_feat = (n_sp * n_max) * (n_sp * n_max + 1) // 2 * (l_max + 1)
+    out = np.zeros((len(cen), n_feat))
+    cell_arr = None if cell is None else np.ascontiguousarray(cell, dtype=np.float64)
+    rc = lib.dsgo_soap_frame(
+        p.ctypes.data, sp.ctypes.data, p.shape[0], cen.ctypes.data, len(cen), n_sp,
+        None if cell_arr is None else cell_arr.ctypes.data, float(r_cut), n_max, l_max,
+        alphas.ctypes.data, betas.ctypes.data, out.ctypes.data,
+    )  # fmt: skip
+    if rc != 0:
+        msg = "dsgo_soap_frame: unsupported arguments"
+        raise ValueError(msg)
+    return out

@@ -156,3 +156,23 @@ def test_tsoap_chain_c0_and_c2(balls7, ref_soap):
     )
     assert np.allclose(to.timesoap(soap, 1), ref_soap["tsoap_c0"], atol=1e-6, rtol=0)
     assert np.allclose(to.timesoap(soap, 4), ref_soap["tsoap_c2"], atol=1e-6, rtol=0)
+
+
+def test_soap_c_oracle_matches_numpy_oracle(balls7):
+    """The C/OpenMP restatement (CPU baseline) against the numpy restatement: cell-list path,
+    image-enumeration path, open boundary, several species."""
+    rng = np.random.default_rng(2)
+    # periodic, wide box -> cell list
+    box = np.array([27.0, 28.5, 30.0])
+    pos = rng.random((150, 3)) * box * 1.2 - 0.1 * box
+    z = np.array([1, 8])[rng.integers(0, 2, 150)]
+    cen = np.arange(0, 150, 7)
+    a = so.soap_frame(pos, z, cen, box, 5.0, 6, 5)
+    b = so.soap_frame_c(pos, z, cen, box, 5.0, 6, 5)
+    assert np.abs(a - b).max() <= 1e-11 * np.abs(a).max()
+    # balls_7: small box -> image enumeration; and non-periodic
+    p7 = balls7["positions"][3].astype(np.float64)
+    for cell in (balls7["dims"][3, :3].astype(np.float64), None):
+        a = so.soap_frame(p7, np.full(7, 6), np.arange(7), cell, 8.0, 4, 4)
+        b = so.soap_frame_c(p7, np.full(7, 6), np.arange(7), cell, 8.0, 4, 4)
+        assert np.abs(a - b).max() <= 1e-11 * np.abs(a).max()
