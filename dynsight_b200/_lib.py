@@ -10,8 +10,11 @@ from __future__ import annotations
 import ctypes
 from pathlib import Path
 
+import os
+
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libdynsight_b200.so"
+# DSG_LIB_PATH selects an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = Path(os.environ.get("DSG_LIB_PATH", _PKG / "libdynsight_b200.so"))
 
 DSG_F32 = 0
 DSG_F64 = 1

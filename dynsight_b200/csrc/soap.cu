@@ -1,19 +1,22 @@
 // soap.cu -- SOAP power spectrum (GTO radial basis, sigma = 1) batched over frames (sm_100a).
 //
-// Replaces the DScribe call of soapify/saponify.py:98-122.  One warp owns one centre:
+// Replaces the DScribe call of soapify/saponify.py:98-122.  One warp owns one centre; centres are
+// visited in cell order so that the warps resident on an SM read the same candidate cells:
 //
 //   gather   every periodic image within R = r_cut + sqrt(-2 ln 1e-3) is found through a cell list
 //            (cell edge >= R; axes shorter than 3R fall back to an explicit image loop; a
 //            non-periodic frame uses an open bounding-box grid); hits are ballot-compacted into a
-//            32-entry displacement list in shared memory
-//   phase B  two lanes per neighbour evaluate the un-normalised regular solid harmonics
-//            r^l Y_lm (polynomial recursions: no sqrt, no division, exact at r = 0)
+//            32-entry displacement list in shared memory (next batch prefetched)
+//   phase B  one lane per neighbour evaluates the un-normalised regular solid harmonics r^l Y_lm
+//            with fully unrolled polynomial recursions (no sqrt, no division, exact at r = 0)
 //   phase C  lane (g, k) owns radial index k and a load-balanced group g of angular momenta; it
-//            evaluates its Gaussians exp(-gamma_lk r^2) and accumulates G_lkm in registers
-//   epilogue Loewdin mixing c = (beta * prefactor) G in shared memory, then one lane per output
-//            contracts over m, scales and writes the spectrum coalesced.
+//            evaluates its Gaussians exp(-gamma_lk r^2) (each needed exponential exactly once per
+//            neighbour, branch-free float64 exp) and accumulates G_lkm in registers, reading the
+//            harmonics as 128-bit shared-memory broadcasts
+//   epilogue Loewdin mixing c = (beta * prefactor) G (scaled by sqrt of the m-weights) in shared
+//            memory, then one lane per output contracts over m and writes the spectrum coalesced.
 //
-// float64 throughout: the Loewdin matrices have entries of order 1e3 and cancel, so primitive
+// float64 throughout: the Loewdin matrices have entries of order 1e3..1e6 and cancel, so primitive
 // sums need double precision to meet 1e-5 relative (SURVEY.md section 7 "hard parts").
 #include <algorithm>
 #include <cmath>
@@ -30,8 +33,16 @@ constexpr int kMaxSpecies = 16;
 constexpr int kKBlock = 8;       // radial indices handled per pass (lanes: 4 groups x 8)
 constexpr int kGroups = 4;
 constexpr int kMaxItems = 4;
-constexpr int kHalfChunk = 16;   // neighbours per phase-B/C pass
+#ifndef DSG_SOAP_CHUNK
+#define DSG_SOAP_CHUNK 16
+#endif
+constexpr int kChunk = DSG_SOAP_CHUNK;  // neighbours per phase-B/C pass (one lane each in phase B)
 constexpr int kOpenCellsPerAxis = 32;
+#ifndef DSG_SOAP_MIN_BLOCKS
+#define DSG_SOAP_MIN_BLOCKS 6
+#endif
+constexpr int kListCap = 32;     // displacement list entries per warp
+constexpr int kCellTab = 32;     // (cell range, shift) entries resolved per pass
 
 enum AxisMode : int { kWide = 0, kNarrow = 1, kOpen = 2 };
 
@@ -50,25 +61,29 @@ struct SoapFrame {
 struct SoapPlan {
     int n_max, l_max, n_species, n_feat;
     int n_lm;          // (l_max+1)^2
-    int row_stride;    // P: doubles per neighbour in the harmonics buffer (odd)
+    int row_stride;    // P: doubles per neighbour in the harmonics buffer
+    int rbuf_doubles;  // per-warp harmonics buffer (also holds the mixed coefficients)
     int kblocks;
     int item_l[kGroups][kMaxItems];  // -1 = unused
 };
 
 struct SoapArgs {
-    const double* wpos;     // (F, N, 3) wrapped / shifted coordinates
-    const double* sx;       // cell-sorted SoA
+    const double* sx;       // cell-sorted SoA (wrapped / shifted coordinates)
     const double* sy;
     const double* sz;
     const int* sspec;
+    const int* sid;         // original atom index of a sorted slot
     const int* cell_start;
     const SoapFrame* frames;
-    const int* centres;
+    const int* centre_of_atom;  // (N) output row of an atom, -1 if it is not a centre
     int n_atoms, n_cent;
+    int slots_per_warp;
     double r2max;
     const double* gamma;    // (L+1, n)
     const double* bmat;     // (L+1, n, n)  beta * prefactor
-    const double* wlm;      // (n_lm)
+    const double* exp_tab;  // (64) 2^(j/64)
+    int bmat_smem_doubles;  // size of bmat if it is staged in shared memory, else 0
+    const double* swlm;     // (n_lm)  sqrt of the m-contraction weights
     const int* lm_l;        // (n_lm) -> l
     const int* decode;      // (n_feat)
     double* out;
@@ -186,7 +201,7 @@ soap_scatter_kernel(const double* __restrict__ wpos, const int* __restrict__ spe
                     const SoapFrame* __restrict__ fr, const unsigned* __restrict__ cell_id,
                     int* __restrict__ cell_cnt, const int* __restrict__ cell_start,
                     double* __restrict__ sx, double* __restrict__ sy, double* __restrict__ sz,
-                    int* __restrict__ sspec) {
+                    int* __restrict__ sspec, int* __restrict__ sid) {
     const int f = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_atoms) return;
@@ -197,83 +212,181 @@ soap_scatter_kernel(const double* __restrict__ wpos, const int* __restrict__ spe
     sy[slot] = wpos[a * 3 + 1];
     sz[slot] = wpos[a * 3 + 2];
     sspec[slot] = species[i];
+    sid[slot] = i;
+}
+
+__global__ void __launch_bounds__(256)
+soap_centre_map_kernel(const int* __restrict__ centres, int n_cent, int* __restrict__ map) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_cent) map[centres[i]] = i;
 }
 
 // ------------------------------------------------------------------------------------------
 // main kernel
 // ------------------------------------------------------------------------------------------
-__constant__ double c_inv_int[2 * kMaxL + 2];  // 1/i
-
 template <int N>
 struct Acc {
     double v[N > 0 ? N : 1];
 };
 
-// Phase B: un-normalised regular solid harmonics of one displacement, m of one parity.
-//   Rt[l*l + l + m] = S_l^m(z, r2) * A_m(x, y),   Rt[l*l + l - m] = S_l^m * B_m   (m > 0)
+// exp(x) for x in [-690, 0]: 2^n * 2^(j/16) * e^u; 2^(j/16) from a shared-memory table, e^u by a
+// short Taylor polynomial.  Relative error < 1e-15 + the rounding of x*16*log2(e) (<= 1e-14 for
+// |x| < 100).  Branch-free: 13 fp64 ops.
+constexpr int kExpTab = 16;
+#ifndef DSG_SOAP_EXP_TABLE
+#define DSG_SOAP_EXP_TABLE 1
+#endif
+#if DSG_SOAP_EXP_TABLE
+// 16 entries * 8 bytes = one 128-byte row of shared memory: every entry has its own bank pair, so
+// the divergent table reads of a warp are conflict-free.  |u| <= ln2/32, degree-6 Taylor
+// polynomial (truncation 4.5e-16).
+__device__ __forceinline__ double exp_neg(double x, const double* __restrict__ tab) {
+    const double t = fmax(x, -690.0) * 23.083120654223414;       // 16 * log2(e); keeps 2^n normal
+    const double magic = 6755399441055744.0;                     // 1.5 * 2^52
+    const double tn = t + magic;
+    const int kq = __double2loint(tn);                           // 16 n + j
+    const double u = (t - (tn - magic)) * 0.04332169878499658;   // ln2 / 16
+    double p = 1.38888888888888888889e-03;                       // 1/6!
+    p = fma(p, u, 8.33333333333333333333e-03);
+    p = fma(p, u, 4.16666666666666666667e-02);
+    p = fma(p, u, 1.66666666666666666667e-01);
+    p = fma(p, u, 0.5);
+    p = fma(p, u, 1.0);
+    p = fma(p, u, 1.0);
+    const double r = tab[kq & (kExpTab - 1)] * p;
+    return __hiloint2double(__double2hiint(r) + ((kq >> 4) << 20), __double2loint(r));
+}
+#else
+// table-free variant: 2^n * 2^f, f in [-1/2, 1/2], degree-12 Taylor polynomial of exp(f ln 2)
+// split into even and odd halves (two independent FMA chains).
+__device__ __forceinline__ double exp_neg(double x, const double* __restrict__) {
+    const double t = fmax(x, -690.0) * 1.4426950408889634074;
+    const double magic = 6755399441055744.0;
+    const double tn = t + magic;
+    const int n = __double2loint(tn);
+    const double f = t - (tn - magic);
+    const double u = f * 0.69314718055994530942;
+    const double u2 = u * u;
+    double pe = 2.08767569878680989792e-09;
+    pe = fma(pe, u2, 2.75573192239858906526e-07);
+    pe = fma(pe, u2, 2.48015873015873015873e-05);
+    pe = fma(pe, u2, 1.38888888888888888889e-03);
+    pe = fma(pe, u2, 4.16666666666666666667e-02);
+    pe = fma(pe, u2, 0.5);
+    pe = fma(pe, u2, 1.0);
+    double po = 2.50521083854417187751e-08;
+    po = fma(po, u2, 2.75573192239858906526e-06);
+    po = fma(po, u2, 1.98412698412698412698e-04);
+    po = fma(po, u2, 8.33333333333333333333e-03);
+    po = fma(po, u2, 1.66666666666666666667e-01);
+    po = fma(po, u2, 1.0);
+    const double p = fma(po, u, pe);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+#endif
+
+// Phase B: un-normalised regular solid harmonics of one displacement, rows padded to even length:
+//   rt[l(l+1) + l + m] = S_l^m(z, r2) * A_m(x, y),   rt[l(l+1) + l - m] = S_l^m * B_m   (m > 0)
 //   A_m + i B_m = (x + i y)^m ;  S_m^m = (2m-1)!!, S_{m+1}^m = (2m+1) z S_m^m,
 //   S_l^m = ((2l-1) z S_{l-1}^m - (l+m-1) r2 S_{l-2}^m) / (l-m)
-__device__ __forceinline__ void solid_harmonics(double x, double y, double z, double r2, int l_max,
-                                                int parity, double* __restrict__ rt) {
+template <int LT>
+__device__ __forceinline__ void solid_harmonics(double x, double y, double z, double r2,
+                                                double* __restrict__ rt) {
     double am = 1.0, bm = 0.0, dfact = 1.0;
-    for (int m = 0; m <= l_max; ++m) {
+#pragma unroll
+    for (int m = 0; m <= LT; ++m) {
         if (m > 0) {
             const double an = am * x - bm * y;
-            bm = am * y + bm * x;
+            bm = fma(am, y, bm * x);
             am = an;
             dfact *= (double)(2 * m - 1);
         }
-        if ((m & 1) != parity) continue;
         double s0 = dfact;  // S_m^m
-        rt[m * m + 2 * m] = s0 * am;
-        if (m > 0) rt[m * m] = s0 * bm;
-        if (m + 1 > l_max) continue;
-        double s1 = (double)(2 * m + 1) * z * s0;  // S_{m+1}^m
-        {
-            const int l = m + 1, o = l * l + l;
-            rt[o + m] = s1 * am;
-            if (m > 0) rt[o - m] = s1 * bm;
-        }
-        for (int l = m + 2; l <= l_max; ++l) {
-            const double s2 =
-                ((double)(2 * l - 1) * z * s1 - (double)(l + m - 1) * r2 * s0) * c_inv_int[l - m];
-            const int o = l * l + l;
-            rt[o + m] = s2 * am;
-            if (m > 0) rt[o - m] = s2 * bm;
-            s0 = s1;
-            s1 = s2;
+        rt[m * (m + 1) + 2 * m] = s0 * am;
+        if (m > 0) rt[m * (m + 1)] = s0 * bm;
+        if (m + 1 <= LT) {
+            double s1 = (double)(2 * m + 1) * z * s0;  // S_{m+1}^m
+            {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int l = m + 1, o = l * (l + 1) + l;
+                rt[o + m] = s1 * am;
+                if (m > 0) rt[o - m] = s1 * bm;
+            }
+#pragma unroll
+            for (int l = m + 2; l <= LT; ++l) {
+                const double inv = 1.0 / (double)(l - m);  // compile-time constant after unrolling
+                const double s2 =
+                    ((double)(2 * l - 1) * z * s1 - (double)(l + m - 1) * r2 * s0) * inv;
+                const int o = l * (l + 1) + l;
+                rt[o + m] = s2 * am;
+                if (m > 0) rt[o - m] = s2 * bm;
+                s0 = s1;
+                s1 = s2;
+            }
         }
     }
 }
 
-template <int S0, int S1, int S2, int S3>
-__global__ void __launch_bounds__(128)
+// acc[0..S) += e * r[0..S), r 16-byte aligned, read as 128-bit shared loads
+template <int S>
+__device__ __forceinline__ void accumulate(Acc<S>& a, double e, const double* __restrict__ r) {
+    if (S <= 0) return;
+    const double2* __restrict__ r2p = reinterpret_cast<const double2*>(r);
+#pragma unroll
+    for (int s = 0; s + 1 < S; s += 2) {
+        const double2 v = r2p[s >> 1];
+        a.v[s] = fma(e, v.x, a.v[s]);
+        a.v[s + 1] = fma(e, v.y, a.v[s + 1]);
+    }
+    if (S & 1) a.v[S - 1] = fma(e, r[S - 1], a.v[S - 1]);
+}
+
+template <int S>
+__device__ __forceinline__ void store_item(const Acc<S>& a, int l, int k, int n,
+                                           double* __restrict__ cz) {
+    if (S <= 0 || l < 0) return;
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+        if (s < 2 * l + 1) cz[(l * l + s) * n + k] = a.v[s];
+}
+
+template <int LT, int S0, int S1, int S2, int S3>
+__global__ void __launch_bounds__(64, (S0 <= 17) ? DSG_SOAP_MIN_BLOCKS : (S0 <= 21 ? 5 : 4))
 soap_kernel(const SoapArgs a) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem_all[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warps = blockDim.x >> 5;
-    const int ci = blockIdx.x * warps + warp;
+    // block-wide tables: 2^(j/64) and (if small enough) the Loewdin matrices
+    double* exp_tab = smem_all;
+    double* bmat_s = smem_all + kExpTab;
+    for (int i = threadIdx.x; i < kExpTab; i += blockDim.x) exp_tab[i] = a.exp_tab[i];
+    for (int i = threadIdx.x; i < a.bmat_smem_doubles; i += blockDim.x) bmat_s[i] = a.bmat[i];
+    __syncthreads();
+    const double* __restrict__ bmat = a.bmat_smem_doubles > 0 ? bmat_s : a.bmat;
+    double* smem = smem_all + kExpTab + a.bmat_smem_doubles;
     const int f = blockIdx.y;
-    if (ci >= a.n_cent) return;  // warps are independent: only __syncwarp below
+    // each warp walks a run of consecutive slots of the frame's cell-sorted order: consecutive
+    // centres share their candidate cells (L1 reuse) and the block-wide tables are loaded once
+    const int first = (blockIdx.x * warps + warp) * a.slots_per_warp;
+    const int last = min(a.n_atoms, first + a.slots_per_warp);
+    if (first >= last) return;  // warps are independent from here: only __syncwarp below
 
     const SoapPlan& pl = a.plan;
-    const int n = pl.n_max, L = pl.l_max, P = pl.row_stride, n_lm = pl.n_lm;
+    const int n = pl.n_max, P = pl.row_stride, n_lm = pl.n_lm;
     const int c_doubles = pl.n_species * n_lm * n;
-    const int per_warp = 32 * 4 + kHalfChunk * P + c_doubles;
-    double* nbuf = smem + (size_t)warp * per_warp;   // [32][4] dx dy dz r2
-    double* rbuf = nbuf + 32 * 4;                      // [16][P]
-    double* cbuf = rbuf + kHalfChunk * P;              // [S][n_lm][n]
+    const bool single_pass = pl.n_species * pl.kblocks == 1;
+    const int per_warp = (kListCap * 4 + kCellTab * 4 + pl.rbuf_doubles +
+                          (single_pass ? 0 : c_doubles) + 1) & ~1;  // 16-byte rows
+    double* nbuf = smem + (size_t)warp * per_warp;     // [32][4] dx dy dz r2
+    double* tab_sh = nbuf + kListCap * 4;                // [3][32] image shifts of the cell table
+    int2* tab_q = reinterpret_cast<int2*>(tab_sh + 3 * kCellTab);  // [32] candidate ranges
+    double* rbuf = tab_sh + kCellTab * 4;                // [kChunk][P] harmonics; later G / mixed
+    int cached_cell = -1;
+    // primitive sums G [S][n_lm][n]: a separate buffer only if they must survive several passes
+    double* cbuf = single_pass ? rbuf : rbuf + pl.rbuf_doubles;
 
     const SoapFrame* __restrict__ fr = a.frames + f;
-    const int atom = a.centres[ci];
-    const double* cp = a.wpos + ((size_t)f * a.n_atoms + atom) * 3;
-    const double xc = cp[0], yc = cp[1], zc = cp[2];
-    int cc[3];
-    {
-        double w[3];
-        // the centre's coordinates are already wrapped: locate only recomputes the cell
-        soap_locate(fr, xc, yc, zc, w, cc);
-    }
     int ne[3], mode[3], nc[3], nimg[3];
     double box[3];
 #pragma unroll
@@ -292,7 +405,18 @@ soap_kernel(const SoapArgs a) {
 #pragma unroll
     for (int t = 0; t < kMaxItems; ++t) {
         il[t] = pl.item_l[g][t];
-        ioff[t] = il[t] >= 0 ? il[t] * il[t] : 0;
+        ioff[t] = il[t] >= 0 ? il[t] * (il[t] + 1) : 0;
+    }
+
+    for (int slot_local = first; slot_local < last; ++slot_local) {
+    const size_t slot = (size_t)f * a.n_atoms + slot_local;
+    const int ci = a.centre_of_atom[a.sid[slot]];
+    if (ci < 0) continue;
+    const double xc = a.sx[slot], yc = a.sy[slot], zc = a.sz[slot];
+    int cc[3];
+    {
+        double w[3];
+        soap_locate(fr, xc, yc, zc, w, cc);  // coordinates are already wrapped: recomputes the cell
     }
 
     for (int z_sp = 0; z_sp < pl.n_species; ++z_sp) {
@@ -302,7 +426,7 @@ soap_kernel(const SoapArgs a) {
             double gam[kMaxItems];
 #pragma unroll
             for (int t = 0; t < kMaxItems; ++t)
-                gam[t] = (kact && il[t] >= 0) ? a.gamma[il[t] * n + k] : 0.0;
+                gam[t] = (kact && il[t] >= 0) ? -a.gamma[il[t] * n + k] : 0.0;
             Acc<S0> a0;
             Acc<S1> a1;
             Acc<S2> a2;
@@ -317,115 +441,115 @@ soap_kernel(const SoapArgs a) {
             for (int s = 0; s < S3; ++s) a3.v[s] = 0.0;
 
             auto process = [&](int fill) {
-                for (int h0 = 0; h0 < fill; h0 += kHalfChunk) {
-                    const int nh = min(kHalfChunk, fill - h0);
-                    {   // phase B
-                        const int jj = lane >> 1;
-                        if (jj < nh) {
-                            const double* d = nbuf + (h0 + jj) * 4;
-                            solid_harmonics(d[0], d[1], d[2], d[3], L, lane & 1, rbuf + jj * P);
-                        }
+                for (int h0 = 0; h0 < fill; h0 += kChunk) {
+                    const int nh = min(kChunk, fill - h0);
+                    if (lane < nh) {   // phase B
+                        const double* d = nbuf + (h0 + lane) * 4;
+                        solid_harmonics<LT>(d[0], d[1], d[2], d[3], rbuf + lane * P);
                     }
                     __syncwarp();
+#pragma unroll 2
                     for (int jj = 0; jj < nh; ++jj) {   // phase C
                         const double r2 = nbuf[(h0 + jj) * 4 + 3];
                         const double* __restrict__ rt = rbuf + jj * P;
-                        if (S0 > 0) {
-                            const double e = exp(-gam[0] * r2);
-                            const double* __restrict__ r = rt + ioff[0];
-#pragma unroll
-                            for (int s = 0; s < S0; ++s) a0.v[s] = fma(e, r[s], a0.v[s]);
-                        }
-                        if (S1 > 0) {
-                            const double e = exp(-gam[1] * r2);
-                            const double* __restrict__ r = rt + ioff[1];
-#pragma unroll
-                            for (int s = 0; s < S1; ++s) a1.v[s] = fma(e, r[s], a1.v[s]);
-                        }
-                        if (S2 > 0) {
-                            const double e = exp(-gam[2] * r2);
-                            const double* __restrict__ r = rt + ioff[2];
-#pragma unroll
-                            for (int s = 0; s < S2; ++s) a2.v[s] = fma(e, r[s], a2.v[s]);
-                        }
-                        if (S3 > 0) {
-                            const double e = exp(-gam[3] * r2);
-                            const double* __restrict__ r = rt + ioff[3];
-#pragma unroll
-                            for (int s = 0; s < S3; ++s) a3.v[s] = fma(e, r[s], a3.v[s]);
-                        }
+                        if (S0 > 0) accumulate<S0>(a0, exp_neg(gam[0] * r2, exp_tab), rt + ioff[0]);
+                        if (S1 > 0) accumulate<S1>(a1, exp_neg(gam[1] * r2, exp_tab), rt + ioff[1]);
+                        if (S2 > 0) accumulate<S2>(a2, exp_neg(gam[2] * r2, exp_tab), rt + ioff[2]);
+                        if (S3 > 0) accumulate<S3>(a3, exp_neg(gam[3] * r2, exp_tab), rt + ioff[3]);
                     }
                     __syncwarp();
                 }
             };
 
             // ---- gather ----
+            // The (cell range, image shift) entries around the centre's cell are resolved by the
+            // lanes in parallel into a per-warp table; consecutive centres of the same cell reuse it.
             int fill = 0;
-            for (int ex = 0; ex < ne[0]; ++ex) {
-                int cx;
-                double shx;
-                if (mode[0] == kNarrow) { cx = 0; shx = (double)(ex - nimg[0]) * box[0]; }
-                else {
-                    cx = cc[0] + ex - 1; shx = 0.0;
-                    if (mode[0] == kWide) {
-                        if (cx < 0) { cx += nc[0]; shx = -box[0]; }
-                        else if (cx >= nc[0]) { cx -= nc[0]; shx = box[0]; }
-                    } else if (cx < 0 || cx >= nc[0]) continue;
-                }
-                for (int ey = 0; ey < ne[1]; ++ey) {
-                    int cy;
-                    double shy;
-                    if (mode[1] == kNarrow) { cy = 0; shy = (double)(ey - nimg[1]) * box[1]; }
-                    else {
-                        cy = cc[1] + ey - 1; shy = 0.0;
-                        if (mode[1] == kWide) {
-                            if (cy < 0) { cy += nc[1]; shy = -box[1]; }
-                            else if (cy >= nc[1]) { cy -= nc[1]; shy = box[1]; }
-                        } else if (cy < 0 || cy >= nc[1]) continue;
-                    }
-                    for (int ez = 0; ez < ne[2]; ++ez) {
-                        int cz;
-                        double shz;
-                        if (mode[2] == kNarrow) { cz = 0; shz = (double)(ez - nimg[2]) * box[2]; }
-                        else {
-                            cz = cc[2] + ez - 1; shz = 0.0;
-                            if (mode[2] == kWide) {
-                                if (cz < 0) { cz += nc[2]; shz = -box[2]; }
-                                else if (cz >= nc[2]) { cz -= nc[2]; shz = box[2]; }
-                            } else if (cz < 0 || cz >= nc[2]) continue;
-                        }
-                        const int cell = cell_base + (cx * nc[1] + cy) * nc[2] + cz;
-                        const int qb = a.cell_start[cell], qe = a.cell_start[cell + 1];
-                        for (int q0 = qb; q0 < qe; q0 += 32) {
-                            const int q = q0 + lane;
-                            bool hit = false;
-                            double dx = 0.0, dy = 0.0, dz = 0.0, r2 = 0.0;
-                            if (q < qe) {
-                                dx = a.sx[q] + shx - xc;
-                                dy = a.sy[q] + shy - yc;
-                                dz = a.sz[q] + shz - zc;
-                                r2 = dx * dx + dy * dy + dz * dz;
-                                hit = r2 <= a.r2max && a.sspec[q] == z_sp;
+            const int n_ent_total = ne[0] * ne[1] * ne[2];
+            const int my_cell = (cc[0] * nc[1] + cc[1]) * nc[2] + cc[2];
+            for (int e0 = 0; e0 < n_ent_total; e0 += kCellTab) {
+                if (!(n_ent_total <= kCellTab && cached_cell == my_cell)) {
+                    __syncwarp();
+                    const int e = e0 + lane;
+                    int qb = 0, qe = 0;
+                    double sh[3] = {0.0, 0.0, 0.0};
+                    if (e < n_ent_total) {
+                        int idx[3];
+                        idx[2] = e % ne[2];
+                        idx[1] = (e / ne[2]) % ne[1];
+                        idx[0] = e / (ne[2] * ne[1]);
+                        int cj[3];
+                        bool ok = true;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            if (mode[k] == kNarrow) {
+                                cj[k] = 0;
+                                sh[k] = (double)(idx[k] - nimg[k]) * box[k];
+                            } else {
+                                cj[k] = cc[k] + idx[k] - 1;
+                                if (mode[k] == kWide) {
+                                    if (cj[k] < 0) { cj[k] += nc[k]; sh[k] = -box[k]; }
+                                    else if (cj[k] >= nc[k]) { cj[k] -= nc[k]; sh[k] = box[k]; }
+                                } else if (cj[k] < 0 || cj[k] >= nc[k]) ok = false;
                             }
-                            const unsigned m = __ballot_sync(kFullS, hit);
-                            if (m == 0u) continue;
-                            const int cnt = __popc(m), rank = __popc(m & lt_mask);
-                            const int room = 32 - fill;
-                            if (hit && rank < room) {
-                                double* d = nbuf + (fill + rank) * 4;
+                        }
+                        if (ok) {
+                            const int cell = cell_base + (cj[0] * nc[1] + cj[1]) * nc[2] + cj[2];
+                            qb = a.cell_start[cell];
+                            qe = a.cell_start[cell + 1];
+                        }
+                    }
+                    tab_q[lane] = make_int2(qb, qe);
+                    tab_sh[lane] = sh[0];
+                    tab_sh[kCellTab + lane] = sh[1];
+                    tab_sh[2 * kCellTab + lane] = sh[2];
+                    __syncwarp();
+                    cached_cell = n_ent_total <= kCellTab ? my_cell : -1;
+                }
+                const int n_ent = min(kCellTab, n_ent_total - e0);
+                for (int t = 0; t < n_ent; ++t) {
+                    const int2 qr = tab_q[t];
+                    const int qb = qr.x, qe = qr.y;
+                    if (qb >= qe) continue;
+                    const double shx = tab_sh[t], shy = tab_sh[kCellTab + t];
+                    const double shz = tab_sh[2 * kCellTab + t];
+                    // software pipeline: the loads of batch i+1 are issued before batch i is used
+                    double px = 0.0, py = 0.0, pz = 0.0;
+                    int ps = -1;
+                    if (qb + lane < qe) {
+                        px = a.sx[qb + lane]; py = a.sy[qb + lane]; pz = a.sz[qb + lane];
+                        ps = a.sspec[qb + lane];
+                    }
+                    for (int q0 = qb; q0 < qe; q0 += 32) {
+                        const double vx = px, vy = py, vz = pz;
+                        const int vs = ps;
+                        const int qn = q0 + 32 + lane;
+                        ps = -1;
+                        if (qn < qe) {
+                            px = a.sx[qn]; py = a.sy[qn]; pz = a.sz[qn];
+                            ps = a.sspec[qn];
+                        }
+                        const double dx = vx + shx - xc, dy = vy + shy - yc, dz = vz + shz - zc;
+                        const double r2 = dx * dx + dy * dy + dz * dz;
+                        const bool hit = vs == z_sp && r2 <= a.r2max;
+                        const unsigned m = __ballot_sync(kFullS, hit);
+                        if (m == 0u) continue;
+                        const int cnt = __popc(m), rank = __popc(m & lt_mask);
+                        const int room = kListCap - fill;
+                        if (hit && rank < room) {
+                            double* d = nbuf + (fill + rank) * 4;
+                            d[0] = dx; d[1] = dy; d[2] = dz; d[3] = r2;
+                        }
+                        if (cnt >= room) {
+                            __syncwarp();
+                            process(kListCap);
+                            if (hit && rank >= room) {
+                                double* d = nbuf + (rank - room) * 4;
                                 d[0] = dx; d[1] = dy; d[2] = dz; d[3] = r2;
                             }
-                            if (cnt >= room) {
-                                __syncwarp();
-                                process(32);
-                                if (hit && rank >= room) {
-                                    double* d = nbuf + (rank - room) * 4;
-                                    d[0] = dx; d[1] = dy; d[2] = dz; d[3] = r2;
-                                }
-                                fill = cnt - room;
-                            } else {
-                                fill += cnt;
-                            }
+                            fill = cnt - room;
+                        } else {
+                            fill += cnt;
                         }
                     }
                 }
@@ -436,46 +560,66 @@ soap_kernel(const SoapArgs a) {
             // ---- registers -> shared G[z][lm][k] ----
             if (kact) {
                 double* cz = cbuf + (size_t)z_sp * n_lm * n;
-                if (S0 > 0 && il[0] >= 0) {
-#pragma unroll
-                    for (int s = 0; s < S0; ++s)
-                        if (s < 2 * il[0] + 1) cz[(ioff[0] + s) * n + k] = a0.v[s];
-                }
-                if (S1 > 0 && il[1] >= 0) {
-#pragma unroll
-                    for (int s = 0; s < S1; ++s)
-                        if (s < 2 * il[1] + 1) cz[(ioff[1] + s) * n + k] = a1.v[s];
-                }
-                if (S2 > 0 && il[2] >= 0) {
-#pragma unroll
-                    for (int s = 0; s < S2; ++s)
-                        if (s < 2 * il[2] + 1) cz[(ioff[2] + s) * n + k] = a2.v[s];
-                }
-                if (S3 > 0 && il[3] >= 0) {
-#pragma unroll
-                    for (int s = 0; s < S3; ++s)
-                        if (s < 2 * il[3] + 1) cz[(ioff[3] + s) * n + k] = a3.v[s];
-                }
+                store_item<S0>(a0, il[0], k, n, cz);
+                store_item<S1>(a1, il[1], k, n, cz);
+                store_item<S2>(a2, il[2], k, n, cz);
+                store_item<S3>(a3, il[3], k, n, cz);
             }
             __syncwarp();
         }
     }
 
-    // ---- Loewdin mixing in place: c[z][lm][n'] = sum_k bmat[l][n'][k] G[z][lm][k] ----
-    for (int col = lane; col < pl.n_species * n_lm; col += 32) {
-        const int lm = col % n_lm;
-        const int l = a.lm_l[lm];
-        double* v = cbuf + (size_t)col * n;
-        double gk[kMaxN];
+    // ---- Loewdin mixing: c[z][lm][n'] = sqrt(w_lm) * sum_k bmat[l][n'][k] G[z][lm][k] ----
+    // the harmonics buffer is free now; with a single pass G sits at its start
+    double* mix = single_pass ? rbuf + ((c_doubles + 1) & ~1) : rbuf;
+    const int n_out = pl.n_species * n_lm * n;
+    if (n == 8) {
+        // one column (z, lm) per lane: G[0..8) in registers, 8x8 matrix rows as 128-bit broadcasts
+        for (int col = lane; col < pl.n_species * n_lm; col += 32) {
+            const int lm = col % n_lm;
+            const int l = a.lm_l[lm];
+            const double w = a.swlm[lm];
+            const double2* __restrict__ v2 = reinterpret_cast<const double2*>(cbuf + (size_t)col * 8);
+            const double2 g0 = v2[0], g1 = v2[1], g2 = v2[2], g3 = v2[3];
+            const double2* __restrict__ b2 = reinterpret_cast<const double2*>(bmat + (size_t)l * 64);
+            double2* __restrict__ o2 = reinterpret_cast<double2*>(mix + (size_t)col * 8);
 #pragma unroll
-        for (int k = 0; k < kMaxN; ++k) gk[k] = k < n ? v[k] : 0.0;
-        const double* __restrict__ bm = a.bmat + (size_t)l * n * n;
-        for (int np = 0; np < n; ++np) {
-            double s = 0.0;
+            for (int np = 0; np < 8; np += 2) {
+                double r[2];
 #pragma unroll
-            for (int k = 0; k < kMaxN; ++k)
-                if (k < n) s = fma(bm[np * n + k], gk[k], s);
-            v[np] = s;
+                for (int h = 0; h < 2; ++h) {
+                    const double2 b0 = b2[(np + h) * 4], b1 = b2[(np + h) * 4 + 1];
+                    const double2 b3 = b2[(np + h) * 4 + 2], b4 = b2[(np + h) * 4 + 3];
+                    double sa = b0.x * g0.x, sb = b0.y * g0.y;
+                    sa = fma(b1.x, g1.x, sa); sb = fma(b1.y, g1.y, sb);
+                    sa = fma(b3.x, g2.x, sa); sb = fma(b3.y, g2.y, sb);
+                    sa = fma(b4.x, g3.x, sa); sb = fma(b4.y, g3.y, sb);
+                    r[h] = (sa + sb) * w;
+                }
+                o2[np >> 1] = make_double2(r[0], r[1]);
+            }
+        }
+    } else {
+        int col = lane / n, np = lane - col * n;   // one division per lane, then increments
+        int lm = col % n_lm;
+        const int dcol = 32 / n, dnp = 32 - dcol * n;
+        for (int idx = lane; idx < n_out; idx += 32) {
+            const int l = a.lm_l[lm];
+            const double* __restrict__ v = cbuf + (size_t)col * n;
+            const double* __restrict__ bm = bmat + ((size_t)l * n + np) * n;
+            double s0 = 0.0, s1 = 0.0;
+            int k = 0;
+            for (; k + 1 < n; k += 2) {
+                s0 = fma(bm[k], v[k], s0);
+                s1 = fma(bm[k + 1], v[k + 1], s1);
+            }
+            if (k < n) s0 = fma(bm[k], v[k], s0);
+            mix[idx] = (s0 + s1) * a.swlm[lm];
+            col += dcol;
+            lm += dcol;
+            np += dnp;
+            if (np >= n) { np -= n; ++col; ++lm; }
+            while (lm >= n_lm) lm -= n_lm;
         }
     }
     __syncwarp();
@@ -486,13 +630,14 @@ soap_kernel(const SoapArgs a) {
         const int code = a.decode[c];
         const int zi = code & 15, zj = (code >> 4) & 15, l = (code >> 8) & 15;
         const int na = (code >> 12) & 31, nb = (code >> 17) & 31;
-        const double* __restrict__ ca = cbuf + ((size_t)zi * n_lm + l * l) * n + na;
-        const double* __restrict__ cb = cbuf + ((size_t)zj * n_lm + l * l) * n + nb;
-        const double* __restrict__ w = a.wlm + l * l;
+        const double* __restrict__ ca = mix + ((size_t)zi * n_lm + l * l) * n + na;
+        const double* __restrict__ cb = mix + ((size_t)zj * n_lm + l * l) * n + nb;
         double s = 0.0;
-        for (int mi = 0; mi < 2 * l + 1; ++mi) s = fma(w[mi] * ca[mi * n], cb[mi * n], s);
+        for (int mi = 0; mi < 2 * l + 1; ++mi) s = fma(ca[mi * n], cb[mi * n], s);
         out[c] = s;
     }
+    __syncwarp();
+    }  // slot loop
 }
 
 // ------------------------------------------------------------------------------------------
@@ -502,8 +647,9 @@ struct SoapLayout {
     long long total_cells = 0;
     bool periodic = false;
     size_t off_frames = 0, off_wpos = 0, off_cell_id = 0, off_cnt = 0, off_start = 0;
-    size_t off_sx = 0, off_sy = 0, off_sz = 0, off_sspec = 0, off_tile = 0;
-    size_t off_gamma = 0, off_bmat = 0, off_wlm = 0, off_lml = 0, off_decode = 0;
+    size_t off_sx = 0, off_sy = 0, off_sz = 0, off_sspec = 0, off_sid = 0, off_cmap = 0;
+    size_t off_tile = 0;
+    size_t off_gamma = 0, off_bmat = 0, off_wlm = 0, off_lml = 0, off_decode = 0, off_exptab = 0;
     size_t bytes = 0;
 };
 
@@ -590,26 +736,39 @@ static int soap_layout(int n_frames, int n_atoms, int n_cent, int n_species, int
     L->off_sy = take(8 * fa);
     L->off_sz = take(8 * fa);
     L->off_sspec = take(4 * fa);
+    L->off_sid = take(4 * fa);
+    L->off_cmap = take(4 * (size_t)n_atoms);
     L->off_tile = take(4 * (((size_t)total + kScanTileItems - 1) / kScanTileItems + 1));
     L->off_gamma = take(8 * (size_t)(l_max + 1) * n_max);
-    L->off_bmat = take(8 * (size_t)(l_max + 1) * n_max * n_max);
+    L->off_bmat = take(8 * ((size_t)(l_max + 1) * n_max * n_max + 2));
     L->off_wlm = take(8 * (size_t)n_lm);
     L->off_lml = take(4 * (size_t)n_lm);
     L->off_decode = take(4 * (size_t)n_feat);
+    L->off_exptab = take(8 * (size_t)kExpTab);
     L->bytes = o;
     return DSG_OK;
 }
 
-static void make_plan(int n_species, int n_max, int l_max, int s0, SoapPlan* pl) {
+// lt = compile-time l cap of the instantiation, s0 = its widest item
+static void make_plan(int n_species, int n_max, int l_max, int lt, int s0, SoapPlan* pl) {
     pl->n_max = n_max;
     pl->l_max = l_max;
     pl->n_species = n_species;
     pl->n_feat = dsg_soap_n_features(n_species, n_max, l_max);
     pl->n_lm = (l_max + 1) * (l_max + 1);
-    int p = pl->n_lm + s0;  // over-read padding: item rows are read S_t wide
-    if ((p & 1) == 0) ++p;  // odd stride: conflict-free phase-B stores
-    pl->row_stride = p;
+    // harmonics rows padded to even length: (lt+1)(lt+2) doubles per neighbour; the stride is
+    // = 2 mod 16 so that the phase-B stores of 32 lanes spread over the banks
     pl->kblocks = (n_max + kKBlock - 1) / kKBlock;
+    int p = (lt + 1) * (lt + 2);
+    while (p % 16 != 2) ++p;
+    pl->row_stride = p;
+    int rb = kChunk * p + s0 + 2;  // tail: item rows are read S_t wide past the last row
+    const int mixed = n_species * pl->n_lm * n_max;
+    // single pass: G and the mixed coefficients both live here; otherwise only the mixed ones
+    const int need = (n_species * pl->kblocks == 1) ? 2 * ((mixed + 1) & ~1) : mixed;
+    if (rb < need) rb = need;
+    rb = (rb + 1) & ~1;
+    pl->rbuf_doubles = rb;
     // longest-processing-time packing of l = l_max..0 (size 2l+1) into 4 lane groups
     int load[kGroups] = {0, 0, 0, 0}, cnt[kGroups] = {0, 0, 0, 0};
     for (int g = 0; g < kGroups; ++g)
@@ -649,13 +808,15 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     double* sy = (double*)(ws + L.off_sy);
     double* sz = (double*)(ws + L.off_sz);
     int* sspec = (int*)(ws + L.off_sspec);
+    int* sid = (int*)(ws + L.off_sid);
+    int* cmap = (int*)(ws + L.off_cmap);
     int* tile = (int*)(ws + L.off_tile);
 
     // ---- basis tables (host float64) ----
     const double eta = 0.5;
     const int n_lm = (l_max + 1) * (l_max + 1);
     std::vector<double> gamma((size_t)(l_max + 1) * n_max), bmat((size_t)(l_max + 1) * n_max * n_max),
-        wlm(n_lm);
+        swlm(n_lm);
     std::vector<int> lml(n_lm);
     const double pi = 3.14159265358979323846;
     for (int l = 0; l <= l_max; ++l) {
@@ -673,7 +834,7 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
             double ratio = 1.0;  // (l-|m|)! / (l+|m|)!
             for (int i = l - am + 1; i <= l + am; ++i) ratio /= (double)i;
             const double n2 = (2 * l + 1) / (4.0 * pi) * ratio * (am > 0 ? 2.0 : 1.0);
-            wlm[l * l + mi] = pi * std::sqrt(8.0 / (2 * l + 1)) * n2;
+            swlm[l * l + mi] = std::sqrt(pi * std::sqrt(8.0 / (2 * l + 1)) * n2);
             lml[l * l + mi] = l;
         }
     }
@@ -689,22 +850,21 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
                             decode[c++] = zi | (zj << 4) | (l << 8) | (na << 12) | (nb << 17);
         if (c != n_feat) return set_error(DSG_ERR_INVALID_ARGUMENT, "feature count mismatch");
     }
-    double inv_int[2 * kMaxL + 2];
-    inv_int[0] = 0.0;
-    for (int i = 1; i < 2 * kMaxL + 2; ++i) inv_int[i] = 1.0 / (double)i;
-    DSG_CUDA_CHECK(cudaMemcpyToSymbolAsync(c_inv_int, inv_int, sizeof(inv_int), 0,
-                                           cudaMemcpyHostToDevice, st));
     DSG_CUDA_CHECK(cudaMemcpyAsync(ws + L.off_gamma, gamma.data(), 8 * gamma.size(),
                                    cudaMemcpyHostToDevice, st));
     DSG_CUDA_CHECK(cudaMemcpyAsync(ws + L.off_bmat, bmat.data(), 8 * bmat.size(),
                                    cudaMemcpyHostToDevice, st));
-    DSG_CUDA_CHECK(cudaMemcpyAsync(ws + L.off_wlm, wlm.data(), 8 * wlm.size(),
+    DSG_CUDA_CHECK(cudaMemcpyAsync(ws + L.off_wlm, swlm.data(), 8 * swlm.size(),
                                    cudaMemcpyHostToDevice, st));
     DSG_CUDA_CHECK(cudaMemcpyAsync(ws + L.off_lml, lml.data(), 4 * lml.size(),
                                    cudaMemcpyHostToDevice, st));
     DSG_CUDA_CHECK(cudaMemcpyAsync(ws + L.off_decode, decode.data(), 4 * decode.size(),
                                    cudaMemcpyHostToDevice, st));
     DSG_CUDA_CHECK(cudaMemcpyAsync(d_frames, frames.data(), sizeof(SoapFrame) * n_frames,
+                                   cudaMemcpyHostToDevice, st));
+    double exp_tab[kExpTab];
+    for (int j = 0; j < kExpTab; ++j) exp_tab[j] = std::exp2((double)j / kExpTab);  // 2^(j/16)
+    DSG_CUDA_CHECK(cudaMemcpyAsync(ws + L.off_exptab, exp_tab, sizeof(exp_tab),
                                    cudaMemcpyHostToDevice, st));
 
     // ---- cell list ----
@@ -718,67 +878,85 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
         DSG_LAUNCH_CHECK("soap_open_setup_kernel");
     }
     DSG_CUDA_CHECK(cudaMemsetAsync(cnt, 0, 4 * (size_t)L.total_cells, st));
+    DSG_CUDA_CHECK(cudaMemsetAsync(cmap, 0xff, 4 * (size_t)n_atoms, st));
+    soap_centre_map_kernel<<<(n_cent + 255) / 256, 256, 0, st>>>(d_centres, n_cent, cmap);
+    DSG_LAUNCH_CHECK("soap_centre_map_kernel");
     soap_bin_kernel<T><<<agrid, 256, 0, st>>>(d_pos, n_atoms, d_frames, wpos, cell_id, cnt);
     DSG_LAUNCH_CHECK("soap_bin_kernel");
     rc = run_scan(cnt, L.total_cells, 1, start, tile, nullptr, st);
     if (rc) return rc;
     soap_scatter_kernel<<<agrid, 256, 0, st>>>(wpos, d_species, n_atoms, d_frames, cell_id, cnt,
-                                               start, sx, sy, sz, sspec);
+                                               start, sx, sy, sz, sspec, sid);
     DSG_LAUNCH_CHECK("soap_scatter_kernel");
 
     // ---- main kernel ----
     SoapArgs a;
-    a.wpos = wpos;
     a.sx = sx;
     a.sy = sy;
     a.sz = sz;
     a.sspec = sspec;
+    a.sid = sid;
     a.cell_start = start;
     a.frames = d_frames;
-    a.centres = d_centres;
+    a.centre_of_atom = cmap;
     a.n_atoms = n_atoms;
     a.n_cent = n_cent;
     a.r2max = radius * radius;
     a.gamma = (const double*)(ws + L.off_gamma);
     a.bmat = (const double*)(ws + L.off_bmat);
-    a.wlm = (const double*)(ws + L.off_wlm);
+    a.exp_tab = (const double*)(ws + L.off_exptab);
+    {
+        const size_t bd = (size_t)(l_max + 1) * n_max * n_max;
+        a.bmat_smem_doubles = bd <= 1024 ? (int)((bd + 1) & ~(size_t)1) : 0;
+    }
+    a.swlm = (const double*)(ws + L.off_wlm);
     a.lm_l = (const int*)(ws + L.off_lml);
     a.decode = (const int*)(ws + L.off_decode);
     a.out = d_out;
     a.stride_i = stride_i;
     a.stride_f = stride_f;
 
-    // template instantiation by l_max (slot widths of the packed items, see make_plan)
-    int s0;
-    if (l_max <= 4) s0 = 9;
-    else if (l_max <= 6) s0 = 13;
-    else if (l_max <= 8) s0 = 17;
-    else if (l_max <= 10) s0 = 21;
-    else s0 = 25;
-    make_plan(n_species, n_max, l_max, s0, &a.plan);
+    // template instantiation by l_max: compile-time l cap + slot widths of the packed items
+    int lt, s0;
+    if (l_max <= 4) { lt = 4; s0 = 9; }
+    else if (l_max <= 6) { lt = 6; s0 = 13; }
+    else if (l_max <= 8) { lt = 8; s0 = 17; }
+    else if (l_max <= 10) { lt = 10; s0 = 21; }
+    else { lt = 12; s0 = 25; }
+    make_plan(n_species, n_max, l_max, lt, s0, &a.plan);
+    const bool single_pass = n_species * a.plan.kblocks == 1;
     const size_t per_warp =
-        8 * ((size_t)32 * 4 + (size_t)kHalfChunk * a.plan.row_stride +
-             (size_t)n_species * a.plan.n_lm * n_max);
-    int warps = 4;
-    while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
-    const size_t smem = per_warp * warps;
+        8 * ((((size_t)kListCap * 4 + (size_t)kCellTab * 4 + (size_t)a.plan.rbuf_doubles +
+               (single_pass ? 0 : (size_t)n_species * a.plan.n_lm * n_max)) + 1) & ~(size_t)1);
+    // two warps per block keep several blocks resident per SM
+    const size_t shared_tables = 8 * ((size_t)kExpTab + (size_t)a.bmat_smem_doubles);
+    int warps = 2;
+    if (per_warp * warps + shared_tables > 227 * 1024) warps = 1;
+    const size_t smem = per_warp * warps + shared_tables;
     if (smem > 227 * 1024)
         return set_error(DSG_ERR_UNSUPPORTED,
                          "n_species*n_max*(l_max+1)^2 needs %zu bytes of shared memory per warp",
                          per_warp);
-    dim3 grid((n_cent + warps - 1) / warps, n_frames);
-#define DSG_SOAP_LAUNCH(A, B, C, D)                                                              \
+    // about 16 resident-block generations over the 148 SMs; runs of >= 1 slot per warp
+    const int target_warps = 148 * 12 * 16;
+    int spw = (int)(((long long)n_atoms * n_frames + target_warps - 1) / target_warps);
+    if (spw < 1) spw = 1;
+    if (spw > 64) spw = 64;
+    a.slots_per_warp = spw;
+    const int warps_needed = (n_atoms + spw - 1) / spw;
+    dim3 grid((warps_needed + warps - 1) / warps, n_frames);
+#define DSG_SOAP_LAUNCH(LT, A, B, C, D)                                                          \
     do {                                                                                         \
-        DSG_CUDA_CHECK(cudaFuncSetAttribute(soap_kernel<A, B, C, D>,                             \
+        DSG_CUDA_CHECK(cudaFuncSetAttribute(soap_kernel<LT, A, B, C, D>,                         \
                                             cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                             (int)smem));                                         \
-        soap_kernel<A, B, C, D><<<grid, warps * 32, smem, st>>>(a);                              \
+        soap_kernel<LT, A, B, C, D><<<grid, warps * 32, smem, st>>>(a);                          \
     } while (0)
-    if (l_max <= 4) DSG_SOAP_LAUNCH(9, 1, 0, 0);
-    else if (l_max <= 6) DSG_SOAP_LAUNCH(13, 5, 0, 0);
-    else if (l_max <= 8) DSG_SOAP_LAUNCH(17, 9, 1, 0);
-    else if (l_max <= 10) DSG_SOAP_LAUNCH(21, 13, 5, 0);
-    else DSG_SOAP_LAUNCH(25, 17, 9, 1);
+    if (l_max <= 4) DSG_SOAP_LAUNCH(4, 9, 1, 0, 0);
+    else if (l_max <= 6) DSG_SOAP_LAUNCH(6, 13, 5, 0, 0);
+    else if (l_max <= 8) DSG_SOAP_LAUNCH(8, 17, 9, 1, 0);
+    else if (l_max <= 10) DSG_SOAP_LAUNCH(10, 21, 13, 5, 0);
+    else DSG_SOAP_LAUNCH(12, 25, 17, 9, 1);
 #undef DSG_SOAP_LAUNCH
     DSG_LAUNCH_CHECK("soap_kernel");
     return DSG_OK;

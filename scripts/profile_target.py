@@ -1,0 +1,43 @@
+"""Small single-purpose launcher for ncu: runs one hot-path stage a few times.
+
+usage: python scripts/profile_target.py soap|neigh|tsoap [atoms] [frames]
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from dynsight_b200 import engine  # noqa: E402
+
+what = sys.argv[1] if len(sys.argv) > 1 else "soap"
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
+nf = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+dev = torch.device("cuda")
+g = torch.Generator(device=dev).manual_seed(0)
+if what == "neigh_fluid":
+    box_l = (n / 0.8) ** (1 / 3)
+    r_cut = 1.5
+else:
+    box_l = (n / 0.0334) ** (1 / 3)
+    r_cut = 5.0
+pos = (torch.rand((nf, n, 3), device=dev, generator=g, dtype=torch.float64) * box_l).float()
+pos.clamp_(max=float(np.nextafter(np.float32(box_l), np.float32(0))))
+box = np.full(3, np.float32(box_l), dtype=np.float32)
+sp = torch.zeros(n, dtype=torch.int32, device=dev)
+cen = torch.arange(n, dtype=torch.int32, device=dev)
+for it in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    if what == "soap":
+        out = engine.soap_power_spectrum(pos, sp, cen, box, 5.0, 8, 8)
+    elif what in ("neigh", "neigh_fluid"):
+        nb = engine.neighbor_lists(pos, box, r_cut)
+        out = engine.lens_pairs(nb, 1)
+    else:
+        soap = torch.rand((n, nf, 324), device=dev, dtype=torch.float64)
+        out = engine.timesoap_device(soap, 1)
+    e1.record()
+    torch.cuda.synchronize()
+    print(what, n, nf, f"{e0.elapsed_time(e1):.3f} ms", f"{n * nf / e0.elapsed_time(e1) * 1e3:.3e} pf/s")
