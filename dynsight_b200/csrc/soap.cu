@@ -632,9 +632,13 @@ soap_kernel(const SoapArgs a) {
         const int na = (code >> 12) & 31, nb = (code >> 17) & 31;
         const double* __restrict__ ca = mix + ((size_t)zi * n_lm + l * l) * n + na;
         const double* __restrict__ cb = mix + ((size_t)zj * n_lm + l * l) * n + nb;
-        double s = 0.0;
-        for (int mi = 0; mi < 2 * l + 1; ++mi) s = fma(ca[mi * n], cb[mi * n], s);
-        out[c] = s;
+        // 2l+1 terms: one leading term, then pairs on two independent chains
+        double s0 = ca[0] * cb[0], s1 = 0.0;
+        for (int mi = 1; mi < 2 * l + 1; mi += 2) {
+            s0 = fma(ca[mi * n], cb[mi * n], s0);
+            s1 = fma(ca[(mi + 1) * n], cb[(mi + 1) * n], s1);
+        }
+        out[c] = s0 + s1;
     }
     __syncwarp();
     }  // slot loop
