@@ -45,6 +45,14 @@ SIGNATURES: dict[str, tuple] = {
         [_c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_int, _c_ptr, _c_dbl, _c_int, _c_ptr, _c_size,
          _c_ptr, _c_ptr, _c_ptr, _c_ptr],
     ),
+    "dsg_neigh_rows": (
+        _c_int,
+        [_c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_int, _c_ptr, _c_dbl, _c_int, _c_ptr, _c_size,
+         _c_ptr, _c_ptr, _c_ptr, _c_i64, _c_ptr, _c_ptr],
+    ),
+    "dsg_lens_pairs_rows": (
+        _c_int, [_c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_ptr, _c_i64, _c_i64, _c_ptr],
+    ),
     "dsg_lens_pairs": (
         _c_int, [_c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_ptr, _c_i64, _c_i64, _c_ptr],
     ),

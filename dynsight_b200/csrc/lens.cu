@@ -38,6 +38,26 @@ __device__ __forceinline__ int warp_intersect(const int* __restrict__ ra, int na
     return inter;
 }
 
+// |A n B| for two UNSORTED rows of distinct int32 (rows path): all chunk pairs are compared.
+__device__ __forceinline__ int warp_intersect_unsorted(const int* __restrict__ ra, int na,
+                                                       const int* __restrict__ rb, int nb,
+                                                       int lane) {
+    int inter = 0;
+    for (int a0 = 0; a0 < na; a0 += 32) {
+        const int ia = a0 + lane;
+        const int va = ia < na ? ra[ia] : -1;
+        bool hit = false;
+        for (int b0 = 0; b0 < nb; b0 += 32) {
+            const int ib = b0 + lane;
+            const int vb = ib < nb ? rb[ib] : -2;
+            const int b_last = min(31, nb - b0 - 1);
+            for (int j = 0; j <= b_last; ++j) hit |= (va == __shfl_sync(kFullMask, vb, j));
+        }
+        inter += __popc(__ballot_sync(kFullMask, hit));
+    }
+    return inter;
+}
+
 __device__ __forceinline__ double lens_value(int a, int b, int inter) {
     const int denom = a + b;                 // lens.py:170
     if (denom <= 0) return 0.0;              // lens.py:171-173
@@ -65,6 +85,25 @@ lens_pairs_kernel(const int* __restrict__ indptr, const long long* __restrict__ 
     if (na > 0 && nb > 0)
         inter = warp_intersect(indices + frame_off[k] + s1, na, indices + frame_off[k + delay] + s2,
                                nb, lane);
+    if (lane == 0) out[(long long)i * ld_out + col0 + k] = lens_value(na, nb, inter);
+}
+
+// rows path: per-centre (row_start, count) instead of a canonical CSR; rows are unsorted
+__global__ void __launch_bounds__(kLensWarps * 32)
+lens_pairs_rows_kernel(const int* __restrict__ counts, const long long* __restrict__ row_start,
+                       const int* __restrict__ rows, int n_pairs, int n_cent, int delay,
+                       double* __restrict__ out, long long ld_out, long long col0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = blockIdx.x * kLensWarps + warp;
+    const int i = blockIdx.y;
+    if (k >= n_pairs) return;
+    const size_t i1 = (size_t)k * n_cent + i, i2 = (size_t)(k + delay) * n_cent + i;
+    const int na = counts[i1], nb = counts[i2];
+    int inter = 0;
+    if (na > 0 && nb > 0) {
+        const long long s1 = row_start[i1], s2 = row_start[i2];
+        if (s1 >= 0 && s2 >= 0) inter = warp_intersect_unsorted(rows + s1, na, rows + s2, nb, lane);
+    }
     if (lane == 0) out[(long long)i * ld_out + col0 + k] = lens_value(na, nb, inter);
 }
 
@@ -153,5 +192,26 @@ extern "C" int dsg_counts_to_f64(const int32_t* d_counts, int n_frames, int n_ce
     counts_to_f64_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_counts, n_frames, n_cent, d_out,
                                                                 ld_out, col0);
     DSG_LAUNCH_CHECK("counts_to_f64_kernel");
+    return DSG_OK;
+}
+
+extern "C" int dsg_lens_pairs_rows(const int32_t* d_counts, const int64_t* d_row_start,
+                                   const int32_t* d_rows, int n_frames, int n_cent, int delay,
+                                   double* d_out, int64_t ld_out, int64_t col0, void* stream) {
+    if (!d_counts || !d_row_start || !d_rows || !d_out)
+        return set_error(DSG_ERR_INVALID_ARGUMENT, "NULL device pointer argument");
+    if (n_cent < 1) return set_error(DSG_ERR_INVALID_ARGUMENT, "n_cent=%d out of range", n_cent);
+    if (delay < 1 || delay >= n_frames)
+        return set_error(DSG_ERR_INVALID_ARGUMENT, "delay=%d must be in [1, n_frames=%d)", delay,
+                         n_frames);
+    const int n_pairs = n_frames - delay;
+    for (int i0 = 0; i0 < n_cent; i0 += 65535) {
+        const int ni = n_cent - i0 < 65535 ? n_cent - i0 : 65535;
+        dim3 grid((n_pairs + kLensWarps - 1) / kLensWarps, ni);
+        lens_pairs_rows_kernel<<<grid, kLensWarps * 32, 0, (cudaStream_t)stream>>>(
+            d_counts + i0, (const long long*)d_row_start + i0, d_rows, n_pairs, n_cent, delay,
+            d_out + (long long)i0 * ld_out, ld_out, col0);
+        DSG_LAUNCH_CHECK("lens_pairs_rows_kernel");
+    }
     return DSG_OK;
 }

@@ -31,6 +31,7 @@ struct FrameParams {
     float r2_lo, r2_hi;      // float32 guard band
     float boxf[3];
     float inv_boxf[3];
+    int shift_mode[3];       // rows path: image chosen by the neighbour-cell wrap, not by rint
 };
 
 constexpr int kWarpsPerBlock = 8;
@@ -202,10 +203,13 @@ cell_assign_kernel(const T* __restrict__ pos, int n_atoms, FrameParams* __restri
         az = fmaxf(az, __shfl_xor_sync(kFull, az, off));
     }
     if ((threadIdx.x & 31) == 0) {
-        // non-negative floats order like their bit patterns
-        atomicMax(&fp[f].amax_bits[0], __float_as_uint(ax));
-        atomicMax(&fp[f].amax_bits[1], __float_as_uint(ay));
-        atomicMax(&fp[f].amax_bits[2], __float_as_uint(az));
+        // non-negative floats order like their bit patterns; the plain read skips the atomic once
+        // the running maximum is already at least this large (almost always)
+        const unsigned bx = __float_as_uint(ax), by = __float_as_uint(ay), bz = __float_as_uint(az);
+        volatile unsigned* cur = fp[f].amax_bits;
+        if (bx > cur[0]) atomicMax(&fp[f].amax_bits[0], bx);
+        if (by > cur[1]) atomicMax(&fp[f].amax_bits[1], by);
+        if (bz > cur[2]) atomicMax(&fp[f].amax_bits[2], bz);
     }
 }
 
@@ -513,6 +517,7 @@ static int make_layout(int n_frames, int n_env, int n_cent, bool same, const dou
                 p.amax_bits[k] = 0u;
                 p.boxf[k] = 0.f;
                 p.inv_boxf[k] = 0.f;
+                p.shift_mode[k] = 0;
             }
             p.cell_base = (int)total;
             p.r2_lo = p.r2_hi = 0.f;
@@ -652,6 +657,370 @@ static int neigh_impl(bool fill, const void* d_pos_env, const void* d_pos_cent, 
     return DSG_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Rows path: one traversal, unsorted rows at atomically reserved offsets (LENS fast path)
+// ------------------------------------------------------------------------------------------
+// compute_lens never returns the lists, so for LENS the rows need neither the canonical CSR
+// order nor sorting (the warp merge in lens.cu compares all pairs).  Each warp (= one centre cell)
+//   1. stages the candidates of its 27 cells once, with the periodic shift of the neighbour cell
+//      already applied (axes with >= 6 cells: the image is implied by the cell offset, so the inner
+//      test needs no rint; see DESIGN.md "shift mode"),
+//   2. tests every centre of the cell against the tile and keeps the hit ballots in registers,
+//   3. reserves space for all rows of the cell with ONE atomicAdd on one of 256 cursors,
+//   4. writes the rows from the saved ballots (no second distance evaluation).
+// Membership is decided exactly as in neigh_kernel (float32 guard band + float64 confirmation).
+constexpr int kRowParts = 256;
+
+struct RowsArgs {
+    const void* pos_env;
+    const void* pos_cent;
+    int n_env, n_cent;
+    const FrameParams* fp;
+    const int* env_start;
+    const int* cent_start;
+    const float4* env_sorted;   // local representatives on shift-mode axes
+    const float4* cent_sorted;
+    int respect_pbc;
+    double r2;
+    int* counts;               // (F, M)
+    long long* row_start;      // (F, M) absolute index into rows, -1 if the reservation overflowed
+    int* rows;
+    long long part_cap;        // capacity of each of the n_parts regions
+    int n_parts;               // power of two <= kRowParts
+    unsigned long long* cursors;  // [kRowParts]
+    long long* status;         // [0] overflow flag
+};
+
+// scatter with local representatives: on a shift-mode axis the stored coordinate is the periodic
+// image of x closest to the centre of the atom's (reference-formula) cell.
+template <typename T>
+__global__ void __launch_bounds__(256)
+cell_scatter_local_kernel(const T* __restrict__ pos, int n_atoms,
+                          const FrameParams* __restrict__ fp, const unsigned* __restrict__ cell_id,
+                          int* __restrict__ cell_cnt, const int* __restrict__ cell_start,
+                          float4* __restrict__ sorted) {
+    const int f = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_atoms) return;
+    const FrameParams* p = fp + f;
+    const size_t a = (size_t)f * n_atoms + i;
+    const int c = (int)cell_id[a];
+    const int gc = p->cell_base + c;
+    const int slot = cell_start[gc] + atomicSub(&cell_cnt[gc], 1) - 1;
+    const int ny = p->ncell[1], nz = p->ncell[2];
+    const int ck[3] = {c / (ny * nz), (c / nz) % ny, c % nz};
+    float out[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double x = (double)pos[a * 3 + k];
+        if (p->shift_mode[k]) {
+            const double edge = p->box[k] / (double)p->ncell[k];
+            x -= rint((x - ((double)ck[k] + 0.5) * edge) / p->box[k]) * p->box[k];
+        }
+        out[k] = (float)x;
+    }
+    sorted[slot] = make_float4(out[0], out[1], out[2], __int_as_float(i));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+neigh_rows_kernel(const RowsArgs a) {
+    __shared__ float4 stage_all[kWarpsPerBlock][kStageCap];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.y;
+    const FrameParams* __restrict__ p = a.fp + f;
+    const int nx = p->ncell[0], ny = p->ncell[1], nz = p->ncell[2];
+    const int c = blockIdx.x * kWarpsPerBlock + warp;
+    if (c >= nx * ny * nz) return;
+    const int base_cell = p->cell_base;
+    const int cbeg = a.cent_start[base_cell + c];
+    const int cend = a.cent_start[base_cell + c + 1];
+    if (cbeg == cend) return;
+
+    float4* stage = stage_all[warp];
+    const int cz = c % nz, cy = (c / nz) % ny, cx = c / (nz * ny);
+    const bool pbc = a.respect_pbc != 0;
+    const bool sx_mode = pbc && p->shift_mode[0], sy_mode = pbc && p->shift_mode[1],
+               sz_mode = pbc && p->shift_mode[2];
+    const float bx = p->boxf[0], by = p->boxf[1], bz = p->boxf[2];
+
+    int run_start = 0, run_len = 0;
+    float rsx = 0.f, rsy = 0.f, rsz = 0.f;  // periodic shift of this lane's run
+    if (lane < 27) {
+        const int ddx = lane / 9 - 1, ddy = (lane / 3) % 3 - 1, ddz = lane % 3 - 1;
+        const int ax = cx + ddx, ay = cy + ddy, az = cz + ddz;
+        const int cc = (wrap_cell(ax, nx) * ny + wrap_cell(ay, ny)) * nz + wrap_cell(az, nz);
+        run_start = a.env_start[base_cell + cc];
+        run_len = a.env_start[base_cell + cc + 1] - run_start;
+        if (sx_mode) rsx = ax < 0 ? -bx : (ax >= nx ? bx : 0.f);
+        if (sy_mode) rsy = ay < 0 ? -by : (ay >= ny ? by : 0.f);
+        if (sz_mode) rsz = az < 0 ? -bz : (az >= nz ? bz : 0.f);
+    }
+    const int run_incl = warp_incl_scan(run_len, lane);
+    const int run_excl = run_incl - run_len;
+    const int n_cand = __shfl_sync(kFull, run_incl, 31);
+
+    const float ibx = p->inv_boxf[0], iby = p->inv_boxf[1], ibz = p->inv_boxf[2];
+    const bool px = pbc && p->box[0] > 0.0 && !sx_mode, py = pbc && p->box[1] > 0.0 && !sy_mode,
+               pz = pbc && p->box[2] > 0.0 && !sz_mode;
+    const float r2_lo = p->r2_lo, r2_hi = p->r2_hi;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const T* __restrict__ pos_env_f = (const T*)a.pos_env + (size_t)f * a.n_env * 3;
+    const T* __restrict__ pos_cent_f = (const T*)a.pos_cent + (size_t)f * a.n_cent * 3;
+    const double r2 = a.r2;
+    const int part = (c + f * 131) & (a.n_parts - 1);
+    if (c == 0 && f == 0 && lane == 0) a.status[1] = a.n_parts;
+
+    // stage candidates [base, base+clen) with the run's shift applied
+    auto stage_chunk = [&](int base, int clen) {
+        for (int q0 = 0; q0 < clen; q0 += 32) {
+            const int q = base + q0 + lane;
+            const bool valid = q0 + lane < clen;
+            int r = 0;
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+                const int v = __shfl_sync(kFull, run_incl, (r + s - 1) & 31);
+                if (v <= q) r += s;
+            }
+            r = valid ? r : 0;
+            const int src = __shfl_sync(kFull, run_start, r) + (q - __shfl_sync(kFull, run_excl, r));
+            const float ox = __shfl_sync(kFull, rsx, r), oy = __shfl_sync(kFull, rsy, r);
+            const float oz = __shfl_sync(kFull, rsz, r);
+            if (valid) {
+                float4 v = a.env_sorted[src];
+                v.x += ox; v.y += oy; v.z += oz;
+                stage[q0 + lane] = v;
+            }
+        }
+    };
+    auto test = [&](const float4 cd, bool valid, float ccx, float ccy, float ccz, int cid) -> bool {
+        const int j = __float_as_int(cd.w);
+        float dx = cd.x - ccx, dy = cd.y - ccy, dz = cd.z - ccz;
+        if (px) dx = fmaf(-rintf(dx * ibx), bx, dx);
+        if (py) dy = fmaf(-rintf(dy * iby), by, dy);
+        if (pz) dz = fmaf(-rintf(dz * ibz), bz, dz);
+        const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+        bool hit = d2 < r2_lo;
+        if (valid && !hit && !(d2 > r2_hi))
+            hit = exact_test<T>(pos_env_f + (size_t)j * 3, pos_cent_f + (size_t)cid * 3, p->box, pbc,
+                                r2);
+        return hit && valid && (j != cid);  // lens.py:104 "j != i"
+    };
+    // reserve `total` row entries for this warp; returns the absolute base or -1 on overflow
+    auto reserve = [&](int total) -> long long {
+        long long base = 0;
+        if (lane == 0) {
+            const unsigned long long off = atomicAdd(&a.cursors[part], (unsigned long long)total);
+            if ((long long)(off + total) > a.part_cap) {
+                a.status[0] = 1;
+                base = -1;
+            } else {
+                base = (long long)part * a.part_cap + (long long)off;
+            }
+        }
+        return __shfl_sync(kFull, base, 0);
+    };
+
+    const bool fast = n_cand <= kStageCap;
+    if (fast) {
+        stage_chunk(0, n_cand);
+        __syncwarp();
+    }
+    for (int cb = cbeg; cb < cend; cb += 32) {
+        const int nb = min(32, cend - cb);
+        float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < nb) me = a.cent_sorted[cb + lane];
+        const int my_id = __float_as_int(me.w);
+        int my_cnt = 0;
+        if (fast) {
+            unsigned mk0 = 0u, mk1 = 0u, mk2 = 0u, mk3 = 0u;
+            for (int ci = 0; ci < nb; ++ci) {
+                const float ccx = __shfl_sync(kFull, me.x, ci), ccy = __shfl_sync(kFull, me.y, ci);
+                const float ccz = __shfl_sync(kFull, me.z, ci);
+                const int cid = __shfl_sync(kFull, my_id, ci);
+                unsigned m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
+                m0 = __ballot_sync(kFull, test(stage[lane], lane < n_cand, ccx, ccy, ccz, cid));
+                if (n_cand > 32)
+                    m1 = __ballot_sync(kFull, test(stage[32 + lane], 32 + lane < n_cand, ccx, ccy,
+                                                   ccz, cid));
+                if (n_cand > 64)
+                    m2 = __ballot_sync(kFull, test(stage[64 + lane], 64 + lane < n_cand, ccx, ccy,
+                                                   ccz, cid));
+                if (n_cand > 96)
+                    m3 = __ballot_sync(kFull, test(stage[96 + lane], 96 + lane < n_cand, ccx, ccy,
+                                                   ccz, cid));
+                if (lane == ci) {
+                    mk0 = m0; mk1 = m1; mk2 = m2; mk3 = m3;
+                    my_cnt = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+                }
+            }
+            const int incl = warp_incl_scan(my_cnt, lane);
+            const int total = __shfl_sync(kFull, incl, 31);
+            const long long base = total > 0 ? reserve(total) : 0;
+            const long long my_row = base < 0 ? -1 : base + (long long)(incl - my_cnt);
+            if (lane < nb) {
+                a.counts[(size_t)f * a.n_cent + my_id] = my_cnt;
+                a.row_start[(size_t)f * a.n_cent + my_id] = my_row;
+            }
+            if (base >= 0 && total > 0) {
+                for (int ci = 0; ci < nb; ++ci) {
+                    const long long row = __shfl_sync(kFull, my_row, ci);
+                    const unsigned m0 = __shfl_sync(kFull, mk0, ci), m1 = __shfl_sync(kFull, mk1, ci);
+                    const unsigned m2 = __shfl_sync(kFull, mk2, ci), m3 = __shfl_sync(kFull, mk3, ci);
+                    int* __restrict__ dst = a.rows + row;
+                    int cum = 0;
+                    if ((m0 >> lane) & 1u) dst[__popc(m0 & lt_mask)] = __float_as_int(stage[lane].w);
+                    cum = __popc(m0);
+                    if ((m1 >> lane) & 1u)
+                        dst[cum + __popc(m1 & lt_mask)] = __float_as_int(stage[32 + lane].w);
+                    cum += __popc(m1);
+                    if ((m2 >> lane) & 1u)
+                        dst[cum + __popc(m2 & lt_mask)] = __float_as_int(stage[64 + lane].w);
+                    cum += __popc(m2);
+                    if ((m3 >> lane) & 1u)
+                        dst[cum + __popc(m3 & lt_mask)] = __float_as_int(stage[96 + lane].w);
+                }
+            }
+        } else {
+            // many candidates: chunked count traversal, one reservation, chunked fill traversal
+            long long my_row = 0;
+            for (int pass = 0; pass < 2; ++pass) {
+                int run_cnt = 0;  // entries of my centre written / counted so far
+                for (int base = 0; base < n_cand; base += kStageCap) {
+                    const int clen = min(kStageCap, n_cand - base);
+                    __syncwarp();
+                    stage_chunk(base, clen);
+                    __syncwarp();
+                    for (int ci = 0; ci < nb; ++ci) {
+                        const float ccx = __shfl_sync(kFull, me.x, ci);
+                        const float ccy = __shfl_sync(kFull, me.y, ci);
+                        const float ccz = __shfl_sync(kFull, me.z, ci);
+                        const int cid = __shfl_sync(kFull, my_id, ci);
+                        const long long row = __shfl_sync(kFull, my_row, ci);
+                        const int cur = __shfl_sync(kFull, run_cnt, ci);
+                        int add = 0;
+                        for (int q0 = 0; q0 < clen; q0 += 32) {
+                            const bool valid = q0 + lane < clen;
+                            const float4 cd = stage[valid ? q0 + lane : 0];
+                            const bool hit = test(cd, valid, ccx, ccy, ccz, cid);
+                            const unsigned m = __ballot_sync(kFull, hit);
+                            if (pass == 1 && hit && row >= 0)
+                                a.rows[row + cur + add + __popc(m & lt_mask)] = __float_as_int(cd.w);
+                            add += __popc(m);
+                        }
+                        if (lane == ci) run_cnt += add;
+                    }
+                }
+                if (pass == 0) {
+                    my_cnt = run_cnt;
+                    const int incl = warp_incl_scan(my_cnt, lane);
+                    const int total = __shfl_sync(kFull, incl, 31);
+                    const long long base = total > 0 ? reserve(total) : 0;
+                    my_row = base < 0 ? -1 : base + (long long)(incl - my_cnt);
+                    if (lane < nb) {
+                        a.counts[(size_t)f * a.n_cent + my_id] = my_cnt;
+                        a.row_start[(size_t)f * a.n_cent + my_id] = my_row;
+                    }
+                    if (total == 0) break;
+                }
+            }
+        }
+    }
+}
+
+template <typename T>
+static int neigh_rows_impl(const void* d_pos_env, const void* d_pos_cent, int n_frames, int n_env,
+                           int n_cent, const double* h_box, double r_cut, int respect_pbc,
+                           void* d_ws, size_t ws_bytes, int32_t* d_counts, int64_t* d_row_start,
+                           int32_t* d_rows, int64_t rows_capacity, int64_t* d_status,
+                           cudaStream_t st) {
+    const bool same = d_pos_cent == nullptr;
+    if (same && n_cent != n_env)
+        return set_error(DSG_ERR_INVALID_ARGUMENT,
+                         "d_pos_cent is NULL (centres == env) but n_cent=%d != n_env=%d", n_cent,
+                         n_env);
+    NeighLayout L;
+    std::vector<FrameParams> fps;
+    int rc = make_layout(n_frames, n_env, n_cent, same, h_box, r_cut, &L, &fps);
+    if (rc) return rc;
+    if (!d_ws || ws_bytes < L.bytes)
+        return set_error(DSG_ERR_WORKSPACE_TOO_SMALL, "workspace has %zu bytes, %zu needed",
+                         ws_bytes, L.bytes);
+    if (!d_pos_env || !d_counts || !d_row_start || !d_rows || !d_status)
+        return set_error(DSG_ERR_INVALID_ARGUMENT, "NULL device pointer argument");
+    if (rows_capacity < kRowParts)
+        return set_error(DSG_ERR_INVALID_ARGUMENT, "rows_capacity=%lld is too small",
+                         (long long)rows_capacity);
+    for (auto& p : fps)
+        for (int k = 0; k < 3; ++k) p.shift_mode[k] = (respect_pbc && p.ncell[k] >= 6) ? 1 : 0;
+    char* ws = (char*)d_ws;
+    FrameParams* d_fp = (FrameParams*)(ws + L.off_fp);
+    unsigned* cid_e = (unsigned*)(ws + L.off_cell_id_e);
+    int* cnt_e = (int*)(ws + L.off_cnt_e);
+    int* start_e = (int*)(ws + L.off_start_e);
+    float4* sorted_e = (float4*)(ws + L.off_sorted_e);
+    unsigned* cid_c = (unsigned*)(ws + L.off_cell_id_c);
+    int* cnt_c = (int*)(ws + L.off_cnt_c);
+    int* start_c = (int*)(ws + L.off_start_c);
+    float4* sorted_c = (float4*)(ws + L.off_sorted_c);
+    int* tile_tmp = (int*)(ws + L.off_tile_tmp);
+    const double rc_eff = r_cut - 1e-6;  // lens.py:78
+    const double r2 = rc_eff * rc_eff;
+
+    DSG_CUDA_CHECK(cudaMemcpyAsync(d_fp, fps.data(), sizeof(FrameParams) * n_frames,
+                                   cudaMemcpyHostToDevice, st));
+    DSG_CUDA_CHECK(cudaMemsetAsync(d_status, 0, 8 * (2 + kRowParts), st));
+    auto build = [&](const T* pos, int n_atoms, unsigned* cid, int* cnt, int* start,
+                     float4* sorted) -> int {
+        dim3 grid((n_atoms + 255) / 256, n_frames);
+        DSG_CUDA_CHECK(cudaMemsetAsync(cnt, 0, 4 * (size_t)L.total_cells, st));
+        cell_assign_kernel<T><<<grid, 256, 0, st>>>(pos, n_atoms, d_fp, cid, cnt);
+        DSG_LAUNCH_CHECK("cell_assign_kernel");
+        int r = run_scan(cnt, L.total_cells, 1, start, tile_tmp, nullptr, st);
+        if (r) return r;
+        cell_scatter_local_kernel<T><<<grid, 256, 0, st>>>(pos, n_atoms, d_fp, cid, cnt, start,
+                                                           sorted);
+        DSG_LAUNCH_CHECK("cell_scatter_local_kernel");
+        return DSG_OK;
+    };
+    rc = build((const T*)d_pos_env, n_env, cid_e, cnt_e, start_e, sorted_e);
+    if (rc) return rc;
+    if (!same) {
+        rc = build((const T*)d_pos_cent, n_cent, cid_c, cnt_c, start_c, sorted_c);
+        if (rc) return rc;
+    }
+    frame_finalize_kernel<<<(n_frames + 127) / 128, 128, 0, st>>>(d_fp, n_frames, r_cut, r2);
+    DSG_LAUNCH_CHECK("frame_finalize_kernel");
+
+    RowsArgs a;
+    a.pos_env = d_pos_env;
+    a.pos_cent = same ? d_pos_env : d_pos_cent;
+    a.n_env = n_env;
+    a.n_cent = n_cent;
+    a.fp = d_fp;
+    a.env_start = start_e;
+    a.cent_start = start_c;
+    a.env_sorted = sorted_e;
+    a.cent_sorted = sorted_c;
+    a.respect_pbc = respect_pbc;
+    a.r2 = r2;
+    a.counts = d_counts;
+    a.row_start = (long long*)d_row_start;
+    a.rows = d_rows;
+    // few, large cells: fewer regions (atomics are no bottleneck then, balance is)
+    int n_parts = 1;
+    while (n_parts < kRowParts && (long long)n_parts * 512 <= L.total_cells) n_parts <<= 1;
+    a.n_parts = n_parts;
+    a.part_cap = rows_capacity / n_parts;
+    a.status = (long long*)d_status;
+    a.cursors = (unsigned long long*)(d_status + 2);
+    dim3 grid((L.max_cells + kWarpsPerBlock - 1) / kWarpsPerBlock, n_frames);
+    neigh_rows_kernel<T><<<grid, kWarpsPerBlock * 32, 0, st>>>(a);
+    DSG_LAUNCH_CHECK("neigh_rows_kernel");
+    return DSG_OK;
+}
+
 }  // namespace dsg
 
 using namespace dsg;
@@ -700,6 +1069,25 @@ extern "C" int dsg_neigh_fill(const void* d_pos_env, const void* d_pos_cent, int
                                   r_cut, respect_pbc, d_workspace, workspace_bytes, nullptr,
                                   const_cast<int32_t*>(d_indptr),
                                   const_cast<int64_t*>(d_frame_off), d_indices, st);
+    return set_error(DSG_ERR_INVALID_ARGUMENT, "pos_dtype=%d is neither DSG_F32 nor DSG_F64",
+                     pos_dtype);
+}
+
+extern "C" int dsg_neigh_rows(const void* d_pos_env, const void* d_pos_cent, int pos_dtype,
+                              int n_frames, int n_env, int n_cent, const double* h_box,
+                              double r_cut, int respect_pbc, void* d_workspace,
+                              size_t workspace_bytes, int32_t* d_counts, int64_t* d_row_start,
+                              int32_t* d_rows, int64_t rows_capacity, int64_t* d_status,
+                              void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pos_dtype == DSG_F32)
+        return neigh_rows_impl<float>(d_pos_env, d_pos_cent, n_frames, n_env, n_cent, h_box, r_cut,
+                                      respect_pbc, d_workspace, workspace_bytes, d_counts,
+                                      d_row_start, d_rows, rows_capacity, d_status, st);
+    if (pos_dtype == DSG_F64)
+        return neigh_rows_impl<double>(d_pos_env, d_pos_cent, n_frames, n_env, n_cent, h_box,
+                                       r_cut, respect_pbc, d_workspace, workspace_bytes, d_counts,
+                                       d_row_start, d_rows, rows_capacity, d_status, st);
     return set_error(DSG_ERR_INVALID_ARGUMENT, "pos_dtype=%d is neither DSG_F32 nor DSG_F64",
                      pos_dtype);
 }

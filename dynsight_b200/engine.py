@@ -148,6 +148,124 @@ def neighbor_lists(
     return NeighborBatch(counts, indptr, frame_off, indices[:nnz], n_frames, n_cent)
 
 
+@dataclass
+class NeighborRows:
+    """Unsorted neighbour rows of a batch of frames at atomically reserved offsets (LENS fast path).
+
+    Row ``i`` of frame ``f`` is ``rows[row_start[f, i] : row_start[f, i] + counts[f, i]]``.
+    """
+
+    counts: torch.Tensor  # (F, M) int32
+    row_start: torch.Tensor  # (F, M) int64
+    rows: torch.Tensor  # (capacity,) int32
+    status: torch.Tensor  # (2 + 256,) int64: [0] overflow flag, [2:] region cursors
+    n_frames: int
+    n_cent: int
+
+    def overflowed(self) -> bool:
+        return bool(self.status[0].item() != 0)
+
+    def needed_capacity(self) -> int:
+        return int(self.status[2:].max().item()) * max(1, int(self.status[1].item()))
+
+
+_ROW_PARTS = 256
+
+
+def neighbor_rows(
+    pos_env: torch.Tensor,
+    box: np.ndarray | torch.Tensor,
+    r_cut: float,
+    pos_cent: torch.Tensor | None = None,
+    respect_pbc: bool = True,
+    capacity: int | None = None,
+) -> NeighborRows:
+    """Single-traversal neighbour rows (same membership as :func:`neighbor_lists`, rows unsorted).
+
+    The caller must check ``overflowed()`` once the work is done (one host sync) and retry with
+    ``needed_capacity()``; :func:`lens_from_positions` does that.
+    """
+    lib = _lib.load()
+    _require_cuda(pos_env, "pos_env")
+    n_frames, n_env, _ = pos_env.shape
+    code = _dtype_code(pos_env)
+    if pos_cent is not None:
+        _require_cuda(pos_cent, "pos_cent")
+        n_cent = pos_cent.shape[1]
+    else:
+        n_cent = n_env
+    h_box = _host_box(box, n_frames)
+    dev = pos_env.device
+    if capacity is None:
+        vol = np.prod(np.maximum(h_box, 1e-30), axis=1)
+        k_est = np.minimum(n_env, n_env / vol * 4.18879 * float(r_cut) ** 3)
+        capacity = int(1.3 * float(np.sum(k_est)) * n_cent) + _ROW_PARTS * 2048
+    capacity = max(int(capacity), _ROW_PARTS) // _ROW_PARTS * _ROW_PARTS
+    ws_bytes = ctypes.c_size_t(0)
+    _lib.check(
+        lib.dsg_neigh_workspace_bytes(
+            n_frames, n_env, n_cent, int(pos_cent is None), h_box.ctypes.data, float(r_cut),
+            ctypes.byref(ws_bytes),
+        )
+    )  # fmt: skip
+    workspace = torch.empty(ws_bytes.value, dtype=torch.uint8, device=dev)
+    counts = torch.empty((n_frames, n_cent), dtype=torch.int32, device=dev)
+    row_start = torch.empty((n_frames, n_cent), dtype=torch.int64, device=dev)
+    rows = torch.empty(capacity, dtype=torch.int32, device=dev)
+    status = torch.empty(2 + _ROW_PARTS, dtype=torch.int64, device=dev)
+    _lib.check(
+        lib.dsg_neigh_rows(
+            pos_env.data_ptr(), pos_cent.data_ptr() if pos_cent is not None else None, code,
+            n_frames, n_env, n_cent, h_box.ctypes.data, float(r_cut), int(bool(respect_pbc)),
+            workspace.data_ptr(), ws_bytes.value, counts.data_ptr(), row_start.data_ptr(),
+            rows.data_ptr(), capacity, status.data_ptr(), _stream_ptr(),
+        )
+    )  # fmt: skip
+    return NeighborRows(counts, row_start, rows, status, n_frames, n_cent)
+
+
+def lens_pairs_rows(
+    nr: NeighborRows, delay: int = 1, out: torch.Tensor | None = None, col0: int = 0
+) -> torch.Tensor:
+    """LENS of frames (a, a+delay) inside one rows batch -> (M, n_pairs) float64."""
+    lib = _lib.load()
+    n_pairs = nr.n_frames - delay
+    if n_pairs < 1:
+        msg = "No valid pairs found."
+        raise RuntimeError(msg)
+    if out is None:
+        out = torch.empty((nr.n_cent, n_pairs), dtype=torch.float64, device=nr.counts.device)
+        col0 = 0
+    _lib.check(
+        lib.dsg_lens_pairs_rows(
+            nr.counts.data_ptr(), nr.row_start.data_ptr(), nr.rows.data_ptr(), nr.n_frames,
+            nr.n_cent, int(delay), out.data_ptr(), out.stride(0), int(col0), _stream_ptr(),
+        )
+    )  # fmt: skip
+    return out
+
+
+def lens_from_positions(
+    pos_env: torch.Tensor,
+    box: np.ndarray | torch.Tensor,
+    r_cut: float,
+    delay: int = 1,
+    pos_cent: torch.Tensor | None = None,
+    respect_pbc: bool = True,
+    out: torch.Tensor | None = None,
+    col0: int = 0,
+    capacity: int | None = None,
+) -> tuple[torch.Tensor, NeighborRows]:
+    """LENS for all frame pairs of a batch straight from positions (rows path + retry on the rare
+    reservation overflow).  Returns the (M, n_pairs) result and the rows batch (for the counts)."""
+    while True:
+        nr = neighbor_rows(pos_env, box, r_cut, pos_cent, respect_pbc, capacity)
+        res = lens_pairs_rows(nr, delay, out=out, col0=col0)
+        if not nr.overflowed():
+            return res, nr
+        capacity = int(nr.needed_capacity() * 1.1) + _ROW_PARTS * 2048
+
+
 def lens_pairs(
     batch: NeighborBatch, delay: int = 1, out: torch.Tensor | None = None, col0: int = 0
 ) -> torch.Tensor:

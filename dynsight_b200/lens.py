@@ -58,8 +58,9 @@ def compute_lens_device(
         box = frames.lens_boxes(fb, 1.01)
         pos_env = fb.select(ix_env, n_all)
         pos_cent = None if same else fb.select(ix_cent, n_all)
-        nb = engine.neighbor_lists(pos_env, box, r_cut, pos_cent, respect_pbc)
-        engine.lens_pairs(nb, delay, out=out, col0=fb.seq0)
+        engine.lens_from_positions(
+            pos_env, box, r_cut, delay, pos_cent, respect_pbc, out=out, col0=fb.seq0
+        )
     return out
 
 

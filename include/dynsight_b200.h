@@ -88,6 +88,25 @@ int dsg_neigh_fill(const void* d_pos_env, const void* d_pos_cent, int pos_dtype,
                    void* d_workspace, size_t workspace_bytes, const int32_t* d_indptr,
                    const int64_t* d_frame_off, int32_t* d_indices, void* stream);
 
+/* Rows path (LENS fast path): ONE traversal.  compute_lens (lens.py:192-310) never returns the
+ * lists, so for LENS the rows need neither canonical CSR order nor sorting.  Membership is decided
+ * exactly as above (same sets), but row i of frame f is stored UNSORTED at
+ *   d_rows[d_row_start[f*n_cent+i] ... + d_counts[f*n_cent+i])
+ * where the start was reserved with an atomic add on one of 256 cursors.  d_status must hold
+ * 2+256 int64: after the call status[0] != 0 means that at least one reservation did not fit
+ * (those rows have row_start = -1): retry with rows_capacity >= status[1]*max(status[2..258)) * 1.05
+ * (status[1] = number of regions actually used, a power of two <= 256). */
+int dsg_neigh_rows(const void* d_pos_env, const void* d_pos_cent, int pos_dtype, int n_frames,
+                   int n_env, int n_cent, const double* h_box, double r_cut, int respect_pbc,
+                   void* d_workspace, size_t workspace_bytes, int32_t* d_counts,
+                   int64_t* d_row_start, int32_t* d_rows, int64_t rows_capacity,
+                   int64_t* d_status, void* stream);
+
+/* LENS over the rows of dsg_neigh_rows (same output contract as dsg_lens_pairs). */
+int dsg_lens_pairs_rows(const int32_t* d_counts, const int64_t* d_row_start,
+                        const int32_t* d_rows, int n_frames, int n_cent, int delay, double* d_out,
+                        int64_t ld_out, int64_t col0, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * LENS (replaces lens/lens.py:150-189 lens_from_two_csr, batched over frame pairs).
  *

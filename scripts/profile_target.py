@@ -33,8 +33,11 @@ for it in range(3):
     if what == "soap":
         out = engine.soap_power_spectrum(pos, sp, cen, box, 5.0, 8, 8)
     elif what in ("neigh", "neigh_fluid"):
-        nb = engine.neighbor_lists(pos, box, r_cut)
-        out = engine.lens_pairs(nb, 1)
+        if len(sys.argv) > 4 and sys.argv[4] == "csr":
+            nb = engine.neighbor_lists(pos, box, r_cut)
+            out = engine.lens_pairs(nb, 1)
+        else:
+            out, _ = engine.lens_from_positions(pos, box, r_cut, 1)
     else:
         soap = torch.rand((n, nf, 324), device=dev, dtype=torch.float64)
         out = engine.timesoap_device(soap, 1)

@@ -245,3 +245,98 @@ def test_large_fluid_properties():
         got = set(ix_h[indptr_h[c] : indptr_h[c + 1]].tolist())
         # env atom with index == k is skipped by the oracle call; tolerate exactly that one id
         assert got - {k} == want - {k}, (k, c)
+
+
+# ---------------------------------------------------------------------------------------------
+# rows path (single traversal, unsorted rows, atomically reserved offsets) -- the LENS fast path
+# ---------------------------------------------------------------------------------------------
+def _check_rows_vs_oracle(nr, pos_env, pos_cent, box, r_cut, pbc):
+    assert not nr.overflowed()
+    counts = nr.counts.cpu().numpy()
+    starts = nr.row_start.cpu().numpy()
+    rows = nr.rows.cpu().numpy()
+    for f in range(pos_env.shape[0]):
+        bx = box[f] if np.ndim(box) == 2 else box  # noqa: PLR2004
+        ip, ix = lo.neighbors(pos_env[f], pos_env[f] if pos_cent is None else pos_cent[f], r_cut, bx,
+                              pbc)  # fmt: skip
+        assert np.array_equal(counts[f], np.diff(ip)), f"counts differ in frame {f}"
+        for i in range(len(ip) - 1):
+            got = np.sort(rows[starts[f, i] : starts[f, i] + counts[f, i]])
+            assert np.array_equal(got, ix[ip[i] : ip[i + 1]]), (f, i)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_rows_path_random_cases(numba_cases, dtype):
+    from dynsight_b200 import engine
+
+    for k, case in enumerate(random_csr_cases()):
+        pe = _dev(case["pos_env"][None], dtype)
+        same = case["pos_cent"] is case["pos_env"]
+        pc = None if same else _dev(case["pos_cent"][None], dtype)
+        nr = engine.neighbor_rows(pe, case["box"], case["r_cut"], pc, case["pbc"])
+        assert not nr.overflowed()
+        counts = nr.counts[0].cpu().numpy()
+        starts = nr.row_start[0].cpu().numpy()
+        rows = nr.rows.cpu().numpy()
+        ip, ix = numba_cases[f"csr{k}_indptr"], numba_cases[f"csr{k}_indices"]
+        assert np.array_equal(counts, np.diff(ip)), k
+        for i in range(len(ip) - 1):
+            assert np.array_equal(np.sort(rows[starts[i] : starts[i] + counts[i]]),
+                                  ix[ip[i] : ip[i + 1]]), (k, i)  # fmt: skip
+
+
+def test_rows_path_shift_mode_with_atoms_outside_box():
+    """>= 6 cells per axis (image implied by the cell offset) with atoms several boxes away,
+    per-frame boxes, explicit centres, pbc on and off."""
+    from dynsight_b200 import engine
+
+    rng = np.random.default_rng(17)
+    n_frames, n, m = 4, 900, 300
+    box = (rng.random((n_frames, 3)) * 4 + 12).astype(np.float32)  # 12..16 with r_cut 1.5 -> 8+ cells
+    pe = ((rng.random((n_frames, n, 3)) * 3.4 - 1.2) * box[:, None, :]).astype(np.float32)
+    pc = ((rng.random((n_frames, m, 3)) * 3.4 - 1.2) * box[:, None, :]).astype(np.float32)
+    for pbc in (True, False):
+        nr = engine.neighbor_rows(_dev(pe), box, 1.5, _dev(pc), pbc)
+        _check_rows_vs_oracle(nr, pe, pc, box, 1.5, pbc)
+        nr = engine.neighbor_rows(_dev(pe), box, 1.5, None, pbc)
+        _check_rows_vs_oracle(nr, pe, None, box, 1.5, pbc)
+    pe64 = (rng.random((2, n, 3)) * 1.6 - 0.3) * box[:2, None, :].astype(np.float64)
+    nr = engine.neighbor_rows(_dev(pe64), box[:2], 1.5, None, True)
+    _check_rows_vs_oracle(nr, pe64, None, box[:2], 1.5, True)
+
+
+def test_rows_path_dense_cells_and_overflow_retry():
+    """More than 128 candidates per cell (chunked traversal) and a deliberately small capacity."""
+    from dynsight_b200 import engine
+
+    rng = np.random.default_rng(23)
+    box = np.array([6.0, 6.0, 6.0], dtype=np.float32)
+    pe = (rng.random((3, 1200, 3)) * box).astype(np.float32)
+    nr = engine.neighbor_rows(_dev(pe), box, 1.9, None, True)
+    _check_rows_vs_oracle(nr, pe, None, box, 1.9, True)
+    small = engine.neighbor_rows(_dev(pe), box, 1.9, None, True, capacity=256 * 8)
+    assert small.overflowed() and small.needed_capacity() > 256 * 8
+    dims = np.tile(np.concatenate([box, [90, 90, 90]]).astype(np.float32), (3, 1))
+    want = lo.compute_lens_arrays(pe, dims, 1.9)
+    lens, nr2 = engine.lens_from_positions(_dev(pe), box, 1.9, 1, capacity=256 * 8)
+    assert not nr2.overflowed()
+    assert np.array_equal(lens.cpu().numpy(), want)
+
+
+def test_rows_path_lens_goldens(balls7, ref_lens, numba_cases):
+    from dynsight_b200 import engine
+
+    pos, dims = balls7["positions"], balls7["dims"]
+    lens, nr = engine.lens_from_positions(_dev(pos), dims[:, :3], 15.0, 1)
+    assert np.array_equal(lens.cpu().numpy(), ref_lens["trj_lens"])
+    assert np.array_equal(engine.coordination_numbers(nr.counts).cpu().numpy(), ref_lens["trj_n_c"])
+    posf, box, r_cut = fluid_case()
+    lens, nr = engine.lens_from_positions(_dev(posf), box, r_cut, 1)
+    assert np.array_equal(lens.cpu().numpy(), numba_cases["fluid_lens"])
+    assert np.array_equal(
+        engine.coordination_numbers(nr.counts).cpu().numpy(), numba_cases["fluid_counts"]
+    )
+    for pbc in (True, False):
+        p2, d2 = lens_2d_inputs()
+        lens, _ = engine.lens_from_positions(_dev(p2), d2[:, :3], 0.1, 1, respect_pbc=pbc)
+        assert np.array_equal(lens.cpu().numpy(), ref_lens["lens_2d_pbc" if pbc else "lens_2d_fbc"])
