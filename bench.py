@@ -298,6 +298,10 @@ def run_b200(args: argparse.Namespace) -> None:
     halo_recv = torch.empty((DELAY, n_atoms, 3), dtype=torch.float32, device=dev)
 
     ev = {k: [] for k in ("neigh", "lens", "soap", "tsoap")}
+    # rows-path capacity: generous fixed estimate, verified after the timed region (no mid-step sync)
+    k_est = RHO * 4.18879 * R_CUT_LENS**3
+    rows_capacity = [int(1.4 * k_est * n_atoms * (bsz + 1)) + 256 * 4096]
+    last_rows = [None]
 
     def step(b: int, record: bool) -> None:
         lo = (b % args.pool_blocks) * bsz
@@ -317,11 +321,12 @@ def run_b200(args: argparse.Namespace) -> None:
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if record else None
         if marks:
             marks[0].record()
-        nb = engine.neighbor_lists(block, box, R_CUT_LENS)
+        nb = engine.neighbor_rows(block, box, R_CUT_LENS, capacity=rows_capacity[0])
         if marks:
             marks[1].record()
-        engine.lens_pairs(nb, DELAY, out=lens_out, col0=0)
+        engine.lens_pairs_rows(nb, DELAY, out=lens_out, col0=0)
         engine.coordination_numbers(nb.counts, out=nc_out, col0=0)
+        last_rows[0] = nb
         if marks:
             marks[2].record()
         engine.soap_power_spectrum(block, species, centres, box, R_CUT_SOAP, N_MAX, L_MAX,
@@ -352,6 +357,8 @@ def run_b200(args: argparse.Namespace) -> None:
     t_stop.record()
     barrier()
     ms = t_start.elapsed_time(t_stop)
+    if last_rows[0].overflowed():
+        raise SystemExit("bench.py: neighbour rows capacity overflow -- timing invalid")
     launches = engine.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
     if world > 1:
@@ -409,7 +416,7 @@ def run_b200(args: argparse.Namespace) -> None:
     }  # fmt: skip
     rooflines_hbm = [
         {
-            "kernel": "neighbour CSR (cell list, count, scan, fill) + lens_pairs_kernel",
+            "kernel": "cell list + neigh_rows_kernel (single traversal) + lens_rows_run_kernel",
             "bound": "hbm", "achieved": lens_gbs, "peak": hbm_peak, "unit": "GB/s",
             "frac": lens_gbs / hbm_peak, "traffic": None,
             "algorithmic_bytes_per_pf": lens_bytes_pf, "mean_neighbours": k_mean_lens,
@@ -535,8 +542,7 @@ def lens_cfg3_section(engine, dev, hbm_peak: float, hbm_src: str) -> dict:
     for it in range(6):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        nb = engine.neighbor_lists(pools[it % 2], box, 1.5)
-        engine.lens_pairs(nb, 1, out=out, col0=0)
+        _, nb = engine.lens_from_positions(pools[it % 2], box, 1.5, 1, out=out, col0=0)
         e1.record()
         torch.cuda.synchronize()
         if it >= 2:

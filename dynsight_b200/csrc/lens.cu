@@ -107,6 +107,61 @@ lens_pairs_rows_kernel(const int* __restrict__ counts, const long long* __restri
     if (lane == 0) out[(long long)i * ld_out + col0 + k] = lens_value(na, nb, inter);
 }
 
+// rows path, delay == 1: one warp owns one centre and a run of kRunPairs consecutive pairs.  The
+// kRunPairs+1 rows are loaded once (all loads in flight together), consecutive rows are compared
+// in registers, and the run's results leave as one 64-byte store.
+constexpr int kRunPairs = 8;
+__global__ void __launch_bounds__(kLensWarps * 32)
+lens_rows_run_kernel(const int* __restrict__ counts, const long long* __restrict__ row_start,
+                     const int* __restrict__ rows, int n_pairs, int n_cent,
+                     double* __restrict__ out, long long ld_out, long long col0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.y * kLensWarps + warp;
+    const int k0 = blockIdx.x * kRunPairs;
+    if (i >= n_cent || k0 >= n_pairs) return;
+    const int np = min(kRunPairs, n_pairs - k0);
+    int cnt = 0;
+    long long st = 0;
+    if (lane <= np) {
+        const size_t idx = (size_t)(k0 + lane) * n_cent + i;
+        cnt = counts[idx];
+        st = row_start[idx];
+        if (st < 0) cnt = 0;
+    }
+    int maxc = cnt;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) maxc = max(maxc, __shfl_xor_sync(kFullMask, maxc, off));
+    double res = 0.0;
+    if (maxc <= 32) {
+        int rowv[kRunPairs + 1];
+#pragma unroll
+        for (int j = 0; j <= kRunPairs; ++j) {
+            const int cj = __shfl_sync(kFullMask, cnt, j);
+            const long long sj = __shfl_sync(kFullMask, st, j);
+            rowv[j] = (j <= np && lane < cj) ? rows[sj + lane] : -1 - j;  // distinct sentinels
+        }
+#pragma unroll
+        for (int k = 0; k < kRunPairs; ++k) {
+            if (k < np) {
+                const int ca = __shfl_sync(kFullMask, cnt, k), cb = __shfl_sync(kFullMask, cnt, k + 1);
+                bool hit = false;
+                for (int j = 0; j < cb; ++j) hit |= (rowv[k] == __shfl_sync(kFullMask, rowv[k + 1], j));
+                const int inter = __popc(__ballot_sync(kFullMask, hit));
+                if (lane == k) res = lens_value(ca, cb, inter);
+            }
+        }
+    } else {
+        for (int k = 0; k < np; ++k) {
+            const int ca = __shfl_sync(kFullMask, cnt, k), cb = __shfl_sync(kFullMask, cnt, k + 1);
+            const long long sa = __shfl_sync(kFullMask, st, k), sb = __shfl_sync(kFullMask, st, k + 1);
+            int inter = 0;
+            if (ca > 0 && cb > 0) inter = warp_intersect_unsorted(rows + sa, ca, rows + sb, cb, lane);
+            if (lane == k) res = lens_value(ca, cb, inter);
+        }
+    }
+    if (lane < np) out[(long long)i * ld_out + col0 + k0 + lane] = res;
+}
+
 __global__ void __launch_bounds__(kLensWarps * 32)
 lens_two_csr_kernel(const int* __restrict__ indptr1, const int* __restrict__ indices1,
                     const int* __restrict__ indptr2, const int* __restrict__ indices2, int n_cent,
@@ -205,6 +260,18 @@ extern "C" int dsg_lens_pairs_rows(const int32_t* d_counts, const int64_t* d_row
         return set_error(DSG_ERR_INVALID_ARGUMENT, "delay=%d must be in [1, n_frames=%d)", delay,
                          n_frames);
     const int n_pairs = n_frames - delay;
+    if (delay == 1) {
+        const int rows_per_launch = 65535 * kLensWarps;
+        for (int i0 = 0; i0 < n_cent; i0 += rows_per_launch) {
+            const int ni = n_cent - i0 < rows_per_launch ? n_cent - i0 : rows_per_launch;
+            dim3 grid((n_pairs + kRunPairs - 1) / kRunPairs, (ni + kLensWarps - 1) / kLensWarps);
+            lens_rows_run_kernel<<<grid, kLensWarps * 32, 0, (cudaStream_t)stream>>>(
+                d_counts + i0, (const long long*)d_row_start + i0, d_rows, n_pairs, n_cent,
+                d_out + (long long)i0 * ld_out, ld_out, col0);
+            DSG_LAUNCH_CHECK("lens_rows_run_kernel");
+        }
+        return DSG_OK;
+    }
     for (int i0 = 0; i0 < n_cent; i0 += 65535) {
         const int ni = n_cent - i0 < 65535 ? n_cent - i0 : 65535;
         dim3 grid((n_pairs + kLensWarps - 1) / kLensWarps, ni);

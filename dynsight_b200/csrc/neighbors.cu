@@ -723,8 +723,9 @@ cell_scatter_local_kernel(const T* __restrict__ pos, int n_atoms,
     sorted[slot] = make_float4(out[0], out[1], out[2], __int_as_float(i));
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+// RINT = some axis still needs the rint minimum image (fewer than 6 cells along it)
+template <typename T, bool RINT>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 neigh_rows_kernel(const RowsArgs a) {
     __shared__ float4 stage_all[kWarpsPerBlock][kStageCap];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -739,7 +740,16 @@ neigh_rows_kernel(const RowsArgs a) {
     if (cbeg == cend) return;
 
     float4* stage = stage_all[warp];
-    const int cz = c % nz, cy = (c / nz) % ny, cx = c / (nz * ny);
+    int cx, cy, cz;
+    if (nx * ny * nz < (1 << 20)) {
+        // float reciprocals are exact for floor((c + 1/2) / n) below 2^20 cells
+        const int xy = (int)(((float)c + 0.5f) * __frcp_rn((float)nz));
+        cz = c - xy * nz;
+        cx = (int)(((float)xy + 0.5f) * __frcp_rn((float)ny));
+        cy = xy - cx * ny;
+    } else {
+        cz = c % nz; cy = (c / nz) % ny; cx = c / (nz * ny);
+    }
     const bool pbc = a.respect_pbc != 0;
     const bool sx_mode = pbc && p->shift_mode[0], sy_mode = pbc && p->shift_mode[1],
                sz_mode = pbc && p->shift_mode[2];
@@ -750,7 +760,10 @@ neigh_rows_kernel(const RowsArgs a) {
     if (lane < 27) {
         const int ddx = lane / 9 - 1, ddy = (lane / 3) % 3 - 1, ddz = lane % 3 - 1;
         const int ax = cx + ddx, ay = cy + ddy, az = cz + ddz;
-        const int cc = (wrap_cell(ax, nx) * ny + wrap_cell(ay, ny)) * nz + wrap_cell(az, nz);
+        const int wx = ax < 0 ? ax + nx : (ax >= nx ? ax - nx : ax);
+        const int wy = ay < 0 ? ay + ny : (ay >= ny ? ay - ny : ay);
+        const int wz = az < 0 ? az + nz : (az >= nz ? az - nz : az);
+        const int cc = (wx * ny + wy) * nz + wz;
         run_start = a.env_start[base_cell + cc];
         run_len = a.env_start[base_cell + cc + 1] - run_start;
         if (sx_mode) rsx = ax < 0 ? -bx : (ax >= nx ? bx : 0.f);
@@ -762,8 +775,9 @@ neigh_rows_kernel(const RowsArgs a) {
     const int n_cand = __shfl_sync(kFull, run_incl, 31);
 
     const float ibx = p->inv_boxf[0], iby = p->inv_boxf[1], ibz = p->inv_boxf[2];
-    const bool px = pbc && p->box[0] > 0.0 && !sx_mode, py = pbc && p->box[1] > 0.0 && !sy_mode,
-               pz = pbc && p->box[2] > 0.0 && !sz_mode;
+    const bool px = RINT && pbc && p->box[0] > 0.0 && !sx_mode,
+               py = RINT && pbc && p->box[1] > 0.0 && !sy_mode,
+               pz = RINT && pbc && p->box[2] > 0.0 && !sz_mode;
     const float r2_lo = p->r2_lo, r2_hi = p->r2_hi;
     const unsigned lt_mask = (1u << lane) - 1u;
     const T* __restrict__ pos_env_f = (const T*)a.pos_env + (size_t)f * a.n_env * 3;
@@ -797,9 +811,11 @@ neigh_rows_kernel(const RowsArgs a) {
     auto test = [&](const float4 cd, bool valid, float ccx, float ccy, float ccz, int cid) -> bool {
         const int j = __float_as_int(cd.w);
         float dx = cd.x - ccx, dy = cd.y - ccy, dz = cd.z - ccz;
-        if (px) dx = fmaf(-rintf(dx * ibx), bx, dx);
-        if (py) dy = fmaf(-rintf(dy * iby), by, dy);
-        if (pz) dz = fmaf(-rintf(dz * ibz), bz, dz);
+        if (RINT) {
+            if (px) dx = fmaf(-rintf(dx * ibx), bx, dx);
+            if (py) dy = fmaf(-rintf(dy * iby), by, dy);
+            if (pz) dz = fmaf(-rintf(dz * ibz), bz, dz);
+        }
         const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
         bool hit = d2 < r2_lo;
         if (valid && !hit && !(d2 > r2_hi))
@@ -1016,7 +1032,12 @@ static int neigh_rows_impl(const void* d_pos_env, const void* d_pos_cent, int n_
     a.status = (long long*)d_status;
     a.cursors = (unsigned long long*)(d_status + 2);
     dim3 grid((L.max_cells + kWarpsPerBlock - 1) / kWarpsPerBlock, n_frames);
-    neigh_rows_kernel<T><<<grid, kWarpsPerBlock * 32, 0, st>>>(a);
+    bool any_rint = false;
+    if (respect_pbc)
+        for (const auto& p : fps)
+            for (int k = 0; k < 3; ++k) any_rint = any_rint || !p.shift_mode[k];
+    if (any_rint) neigh_rows_kernel<T, true><<<grid, kWarpsPerBlock * 32, 0, st>>>(a);
+    else neigh_rows_kernel<T, false><<<grid, kWarpsPerBlock * 32, 0, st>>>(a);
     DSG_LAUNCH_CHECK("neigh_rows_kernel");
     return DSG_OK;
 }
