@@ -33,9 +33,13 @@ constexpr int kMaxSpecies = 16;
 constexpr int kKBlock = 8;       // radial indices handled per pass (lanes: 4 groups x 8)
 constexpr int kGroups = 4;
 constexpr int kMaxItems = 4;
+#ifndef DSG_SOAP_UNROLL
+#define DSG_SOAP_UNROLL 1
+#endif
 #ifndef DSG_SOAP_CHUNK
 #define DSG_SOAP_CHUNK 16
 #endif
+constexpr int kUnrollC = DSG_SOAP_UNROLL;  // phase-C neighbours unrolled together
 constexpr int kChunk = DSG_SOAP_CHUNK;  // neighbours per phase-B/C pass (one lane each in phase B)
 constexpr int kOpenCellsPerAxis = 32;
 #ifndef DSG_SOAP_MIN_BLOCKS
@@ -43,6 +47,8 @@ constexpr int kOpenCellsPerAxis = 32;
 #endif
 constexpr int kListCap = 32;     // displacement list entries per warp
 constexpr int kCellTab = 32;     // (cell range, shift) entries resolved per pass
+constexpr int kBatchCap = 64;    // 32-candidate batches listed per pass
+constexpr int kBatchDoubles = kBatchCap * 3 / 2;  // int2 + int per batch
 
 enum AxisMode : int { kWide = 0, kNarrow = 1, kOpen = 2 };
 
@@ -376,13 +382,15 @@ soap_kernel(const SoapArgs a) {
     const int n = pl.n_max, P = pl.row_stride, n_lm = pl.n_lm;
     const int c_doubles = pl.n_species * n_lm * n;
     const bool single_pass = pl.n_species * pl.kblocks == 1;
-    const int per_warp = (kListCap * 4 + kCellTab * 4 + pl.rbuf_doubles +
+    const int per_warp = (kListCap * 4 + kCellTab * 4 + kBatchDoubles + pl.rbuf_doubles +
                           (single_pass ? 0 : c_doubles) + 1) & ~1;  // 16-byte rows
     double* nbuf = smem + (size_t)warp * per_warp;     // [32][4] dx dy dz r2
     double* tab_sh = nbuf + kListCap * 4;                // [3][32] image shifts of the cell table
     int2* tab_q = reinterpret_cast<int2*>(tab_sh + 3 * kCellTab);  // [32] candidate ranges
-    double* rbuf = tab_sh + kCellTab * 4;                // [kChunk][P] harmonics; later G / mixed
-    int cached_cell = -1;
+    int2* bl_q = reinterpret_cast<int2*>(tab_sh + kCellTab * 4);   // [64] batch (start, count)
+    int* bl_e = reinterpret_cast<int*>(bl_q + kBatchCap);             // [64] batch -> table entry
+    double* rbuf = tab_sh + kCellTab * 4 + kBatchDoubles;  // [kChunk][P] harmonics; later G / mixed
+    int cached_cell = -1, n_batches = -1;
     // primitive sums G [S][n_lm][n]: a separate buffer only if they must survive several passes
     double* cbuf = single_pass ? rbuf : rbuf + pl.rbuf_doubles;
 
@@ -448,7 +456,7 @@ soap_kernel(const SoapArgs a) {
                         solid_harmonics<LT>(d[0], d[1], d[2], d[3], rbuf + lane * P);
                     }
                     __syncwarp();
-#pragma unroll 2
+#pragma unroll kUnrollC
                     for (int jj = 0; jj < nh; ++jj) {   // phase C
                         const double r2 = nbuf[(h0 + jj) * 4 + 3];
                         const double* __restrict__ rt = rbuf + jj * P;
@@ -503,53 +511,91 @@ soap_kernel(const SoapArgs a) {
                     tab_sh[lane] = sh[0];
                     tab_sh[kCellTab + lane] = sh[1];
                     tab_sh[2 * kCellTab + lane] = sh[2];
+                    // flat list of 32-candidate batches so that loads can be prefetched across cells
+                    const int nbat = qe > qb ? (qe - qb + 31) >> 5 : 0;
+                    int incl = nbat;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const int t = __shfl_up_sync(kFullS, incl, off);
+                        if (lane >= off) incl += t;
+                    }
+                    n_batches = __shfl_sync(kFullS, incl, 31);
+                    if (n_batches <= kBatchCap) {
+                        for (int i = 0; i < nbat; ++i) {
+                            bl_q[incl - nbat + i] = make_int2(qb + 32 * i, min(32, qe - qb - 32 * i));
+                            bl_e[incl - nbat + i] = lane;
+                        }
+                    }
                     __syncwarp();
                     cached_cell = n_ent_total <= kCellTab ? my_cell : -1;
                 }
-                const int n_ent = min(kCellTab, n_ent_total - e0);
-                for (int t = 0; t < n_ent; ++t) {
-                    const int2 qr = tab_q[t];
-                    const int qb = qr.x, qe = qr.y;
-                    if (qb >= qe) continue;
-                    const double shx = tab_sh[t], shy = tab_sh[kCellTab + t];
-                    const double shz = tab_sh[2 * kCellTab + t];
-                    // software pipeline: the loads of batch i+1 are issued before batch i is used
-                    double px = 0.0, py = 0.0, pz = 0.0;
-                    int ps = -1;
-                    if (qb + lane < qe) {
-                        px = a.sx[qb + lane]; py = a.sy[qb + lane]; pz = a.sz[qb + lane];
-                        ps = a.sspec[qb + lane];
+                auto consume = [&](double dx, double dy, double dz, double r2, bool hit) {
+                    const unsigned m = __ballot_sync(kFullS, hit);
+                    if (m == 0u) return;
+                    const int cnt = __popc(m), rank = __popc(m & lt_mask);
+                    const int room = kListCap - fill;
+                    if (hit && rank < room) {
+                        double* d = nbuf + (fill + rank) * 4;
+                        d[0] = dx; d[1] = dy; d[2] = dz; d[3] = r2;
                     }
-                    for (int q0 = qb; q0 < qe; q0 += 32) {
-                        const double vx = px, vy = py, vz = pz;
-                        const int vs = ps;
-                        const int qn = q0 + 32 + lane;
-                        ps = -1;
-                        if (qn < qe) {
-                            px = a.sx[qn]; py = a.sy[qn]; pz = a.sz[qn];
-                            ps = a.sspec[qn];
-                        }
-                        const double dx = vx + shx - xc, dy = vy + shy - yc, dz = vz + shz - zc;
-                        const double r2 = dx * dx + dy * dy + dz * dz;
-                        const bool hit = vs == z_sp && r2 <= a.r2max;
-                        const unsigned m = __ballot_sync(kFullS, hit);
-                        if (m == 0u) continue;
-                        const int cnt = __popc(m), rank = __popc(m & lt_mask);
-                        const int room = kListCap - fill;
-                        if (hit && rank < room) {
-                            double* d = nbuf + (fill + rank) * 4;
+                    if (cnt >= room) {
+                        __syncwarp();
+                        process(kListCap);
+                        if (hit && rank >= room) {
+                            double* d = nbuf + (rank - room) * 4;
                             d[0] = dx; d[1] = dy; d[2] = dz; d[3] = r2;
                         }
-                        if (cnt >= room) {
-                            __syncwarp();
-                            process(kListCap);
-                            if (hit && rank >= room) {
-                                double* d = nbuf + (rank - room) * 4;
-                                d[0] = dx; d[1] = dy; d[2] = dz; d[3] = r2;
+                        fill = cnt - room;
+                    } else {
+                        fill += cnt;
+                    }
+                };
+                if (n_batches <= kBatchCap) {
+                    // two batches in flight ahead of the one being tested
+                    double x1 = 0.0, y1 = 0.0, z1 = 0.0, x2 = 0.0, y2 = 0.0, z2 = 0.0;
+                    int s1 = -1, s2 = -1;
+                    auto fetch = [&](int b, double& x, double& y, double& z, int& sp) {
+                        sp = -1;
+                        if (b < n_batches) {
+                            const int2 q = bl_q[b];
+                            if (lane < q.y) {
+                                x = a.sx[q.x + lane]; y = a.sy[q.x + lane]; z = a.sz[q.x + lane];
+                                sp = a.sspec[q.x + lane];
                             }
-                            fill = cnt - room;
-                        } else {
-                            fill += cnt;
+                        }
+                    };
+                    fetch(0, x1, y1, z1, s1);
+                    fetch(1, x2, y2, z2, s2);
+                    for (int b = 0; b < n_batches; ++b) {
+                        const int e = bl_e[b];
+                        const double vx = x1, vy = y1, vz = z1;
+                        const int vs = s1;
+                        x1 = x2; y1 = y2; z1 = z2; s1 = s2;
+                        fetch(b + 2, x2, y2, z2, s2);
+                        const double dx = vx + tab_sh[e] - xc, dy = vy + tab_sh[kCellTab + e] - yc;
+                        const double dz = vz + tab_sh[2 * kCellTab + e] - zc;
+                        const double r2 = dx * dx + dy * dy + dz * dz;
+                        consume(dx, dy, dz, r2, vs == z_sp && r2 <= a.r2max);
+                    }
+                } else {
+                    const int n_ent = min(kCellTab, n_ent_total - e0);
+                    for (int t = 0; t < n_ent; ++t) {
+                        const int2 qr = tab_q[t];
+                        const int qb = qr.x, qe = qr.y;
+                        if (qb >= qe) continue;
+                        const double shx = tab_sh[t], shy = tab_sh[kCellTab + t];
+                        const double shz = tab_sh[2 * kCellTab + t];
+                        for (int q0 = qb; q0 < qe; q0 += 32) {
+                            const int q = q0 + lane;
+                            double dx = 0.0, dy = 0.0, dz = 0.0, r2 = 0.0;
+                            bool hit = false;
+                            if (q < qe) {
+                                dx = a.sx[q] + shx - xc; dy = a.sy[q] + shy - yc;
+                                dz = a.sz[q] + shz - zc;
+                                r2 = dx * dx + dy * dy + dz * dz;
+                                hit = a.sspec[q] == z_sp && r2 <= a.r2max;
+                            }
+                            consume(dx, dy, dz, r2, hit);
                         }
                     }
                 }
@@ -930,7 +976,8 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     make_plan(n_species, n_max, l_max, lt, s0, &a.plan);
     const bool single_pass = n_species * a.plan.kblocks == 1;
     const size_t per_warp =
-        8 * ((((size_t)kListCap * 4 + (size_t)kCellTab * 4 + (size_t)a.plan.rbuf_doubles +
+        8 * ((((size_t)kListCap * 4 + (size_t)kCellTab * 4 + (size_t)kBatchDoubles +
+               (size_t)a.plan.rbuf_doubles +
                (single_pass ? 0 : (size_t)n_species * a.plan.n_lm * n_max)) + 1) & ~(size_t)1);
     // two warps per block keep several blocks resident per SM
     const size_t shared_tables = 8 * ((size_t)kExpTab + (size_t)a.bmat_smem_doubles);

@@ -233,7 +233,7 @@ def timesoap_from_trajectory(
     n_all = len(universe.atoms)
     if batch_frames is None:
         per_frame = max(1, n_cent) * n_feat * 8.0
-        batch_frames = int(max(delay + 1, min(512, 2e9 // per_frame)))
+        batch_frames = int(max(delay + 1, min(512, 16e9 // per_frame)))
     batch_frames = max(batch_frames, delay + 1)
     for fb in frames.iter_batches(universe, fr_idx, batch_frames, overlap=delay):
         box = frames.soap_boxes(fb, bool(soap_respectpbc))
