@@ -40,13 +40,21 @@ ATOMIC_NUMBERS = {sym: z for z, sym in enumerate(_SYMBOLS)}
 def _species_indices(types: np.ndarray) -> tuple[np.ndarray, int]:
     """Atom types are used as element symbols (saponify.py:108,111-116); DScribe orders species
     by atomic number.  Returns per-atom species index and the species count."""
+    symbols, inverse = np.unique(np.asarray(types).astype(str), return_inverse=True)
     try:
-        z = np.asarray([ATOMIC_NUMBERS[str(t)] for t in types], dtype=np.int64)
+        z_of_symbol = np.asarray([ATOMIC_NUMBERS[str(sym)] for sym in symbols], dtype=np.int64)
     except KeyError as exc:
         msg = f"atom type {exc.args[0]!r} is not a chemical symbol (SOAP uses types as elements)"
         raise KeyError(msg) from None
-    uniq, inverse = np.unique(z, return_inverse=True)
-    return inverse.astype(np.int32), int(uniq.size)
+    uniq, rank = np.unique(z_of_symbol, return_inverse=True)  # several symbols may share a Z
+    return rank[inverse].astype(np.int32), int(uniq.size)
+
+
+def _centre_positions(sel: Any, centers: str) -> np.ndarray:
+    """Selection-local indices of the centre atoms, in selection order (saponify.py:92-95)."""
+    sel_ix = np.asarray(sel.indices)
+    cen_ix = np.asarray(sel.select_atoms(centers).indices)
+    return np.nonzero(np.isin(sel_ix, cen_ix))[0].astype(np.int32)
 
 
 def saponify_trajectory_device(
@@ -65,8 +73,7 @@ def saponify_trajectory_device(
         trajslice = slice(None)
     sel = universe.select_atoms(selection)
     sel_ix = np.asarray(sel.indices)
-    centers_ids = set(np.asarray(sel.select_atoms(centers).indices).tolist())
-    centers_list = [i for i, idx in enumerate(sel_ix.tolist()) if idx in centers_ids]
+    centers_list = _centre_positions(sel, centers)
     sp_idx, n_species = _species_indices(np.asarray(sel.atoms.types))
     fr_idx = frames.frame_sequence(universe.trajectory.n_frames, trajslice)
     dev = frames.device()
@@ -76,7 +83,7 @@ def saponify_trajectory_device(
     if not fr_idx or n_cent == 0:
         return out
     species_t = torch.as_tensor(sp_idx, device=dev)
-    centres_t = torch.as_tensor(np.asarray(centers_list, dtype=np.int32), device=dev)
+    centres_t = torch.as_tensor(centers_list, device=dev)
     n_all = len(universe.atoms)
     if batch_frames is None:
         batch_frames = frames.pick_batch_frames(sel_ix.size, 80.0, 1, maximum=1024)
@@ -217,8 +224,7 @@ def timesoap_from_trajectory(
         trajslice = slice(None)
     sel = universe.select_atoms(selection)
     sel_ix = np.asarray(sel.indices)
-    centers_ids = set(np.asarray(sel.select_atoms(centers).indices).tolist())
-    centers_list = [i for i, idx in enumerate(sel_ix.tolist()) if idx in centers_ids]
+    centers_list = _centre_positions(sel, centers)
     sp_idx, n_species = _species_indices(np.asarray(sel.atoms.types))
     fr_idx = frames.frame_sequence(universe.trajectory.n_frames, trajslice)
     if delay < 1 or delay >= len(fr_idx):
@@ -229,7 +235,7 @@ def timesoap_from_trajectory(
     n_feat = soap_basis.n_features(n_species, soapnmax, soaplmax)
     out = torch.empty((n_cent, len(fr_idx) - delay), dtype=torch.float64, device=dev)
     species_t = torch.as_tensor(sp_idx, device=dev)
-    centres_t = torch.as_tensor(np.asarray(centers_list, dtype=np.int32), device=dev)
+    centres_t = torch.as_tensor(centers_list, device=dev)
     n_all = len(universe.atoms)
     if batch_frames is None:
         per_frame = max(1, n_cent) * n_feat * 8.0
