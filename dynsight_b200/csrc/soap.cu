@@ -435,6 +435,9 @@ soap_kernel(const SoapArgs a) {
 #pragma unroll
             for (int t = 0; t < kMaxItems; ++t)
                 gam[t] = (kact && il[t] >= 0) ? -a.gamma[il[t] * n + k] : 0.0;
+            // l = 0: lane (jq, k) sums exp(-gamma_0k r^2) over the neighbours jj = jq (mod 4)
+            const double gam0 = kact ? -a.gamma[k] : 0.0;
+            double acc00 = 0.0;
             Acc<S0> a0;
             Acc<S1> a1;
             Acc<S2> a2;
@@ -464,6 +467,11 @@ soap_kernel(const SoapArgs a) {
                         if (S1 > 0) accumulate<S1>(a1, exp_neg(gam[1] * r2, exp_tab), rt + ioff[1]);
                         if (S2 > 0) accumulate<S2>(a2, exp_neg(gam[2] * r2, exp_tab), rt + ioff[2]);
                         if (S3 > 0) accumulate<S3>(a3, exp_neg(gam[3] * r2, exp_tab), rt + ioff[3]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < kChunk / 4; ++q) {   // l = 0, a quarter of the chunk per lane
+                        const int jj = (lane >> 3) + 4 * q;
+                        if (jj < nh) acc00 += exp_neg(gam0 * nbuf[(h0 + jj) * 4 + 3], exp_tab);
                     }
                     __syncwarp();
                 }
@@ -604,8 +612,11 @@ soap_kernel(const SoapArgs a) {
             if (fill > 0) process(fill);
 
             // ---- registers -> shared G[z][lm][k] ----
+            acc00 += __shfl_xor_sync(kFullS, acc00, 8);
+            acc00 += __shfl_xor_sync(kFullS, acc00, 16);
             if (kact) {
                 double* cz = cbuf + (size_t)z_sp * n_lm * n;
+                if (g == 0) cz[k] = acc00;  // lm = 0: S_0^0 = 1
                 store_item<S0>(a0, il[0], k, n, cz);
                 store_item<S1>(a1, il[1], k, n, cz);
                 store_item<S2>(a2, il[2], k, n, cz);
@@ -819,11 +830,12 @@ static void make_plan(int n_species, int n_max, int l_max, int lt, int s0, SoapP
     if (rb < need) rb = need;
     rb = (rb + 1) & ~1;
     pl->rbuf_doubles = rb;
-    // longest-processing-time packing of l = l_max..0 (size 2l+1) into 4 lane groups
+    // longest-processing-time packing of l = l_max..1 (size 2l+1) into 4 lane groups
     int load[kGroups] = {0, 0, 0, 0}, cnt[kGroups] = {0, 0, 0, 0};
     for (int g = 0; g < kGroups; ++g)
         for (int t = 0; t < kMaxItems; ++t) pl->item_l[g][t] = -1;
-    for (int l = l_max; l >= 0; --l) {
+    // l = 0 (a single m, weight exp(-gamma_0k r^2) only) is accumulated cooperatively by all lanes
+    for (int l = l_max; l >= 1; --l) {
         int best = 0;
         for (int g = 1; g < kGroups; ++g)
             if (load[g] < load[best]) best = g;
@@ -1003,11 +1015,11 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
                                             (int)smem));                                         \
         soap_kernel<LT, A, B, C, D><<<grid, warps * 32, smem, st>>>(a);                          \
     } while (0)
-    if (l_max <= 4) DSG_SOAP_LAUNCH(4, 9, 1, 0, 0);
+    if (l_max <= 4) DSG_SOAP_LAUNCH(4, 9, 0, 0, 0);
     else if (l_max <= 6) DSG_SOAP_LAUNCH(6, 13, 5, 0, 0);
-    else if (l_max <= 8) DSG_SOAP_LAUNCH(8, 17, 9, 1, 0);
+    else if (l_max <= 8) DSG_SOAP_LAUNCH(8, 17, 9, 0, 0);
     else if (l_max <= 10) DSG_SOAP_LAUNCH(10, 21, 13, 5, 0);
-    else DSG_SOAP_LAUNCH(12, 25, 17, 9, 1);
+    else DSG_SOAP_LAUNCH(12, 25, 17, 9, 0);
 #undef DSG_SOAP_LAUNCH
     DSG_LAUNCH_CHECK("soap_kernel");
     return DSG_OK;
