@@ -58,6 +58,16 @@ SIGNATURES: dict[str, tuple] = {
     ),
     "dsg_lens_from_two_csr": (_c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_ptr, _c_ptr]),
     "dsg_counts_to_f64": (_c_int, [_c_ptr, _c_int, _c_int, _c_ptr, _c_i64, _c_i64, _c_ptr]),
+    "dsg_orientational_op": (
+        _c_int,
+        [_c_ptr, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_ptr, _c_i64, _c_i64,
+         _c_ptr],
+    ),
+    "dsg_velocity_alignment": (
+        _c_int,
+        [_c_ptr, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_ptr, _c_i64, _c_i64,
+         _c_ptr],
+    ),
     "dsg_timesoap": (
         _c_int,
         [_c_ptr, _c_int, _c_int, _c_int, _c_i64, _c_i64, _c_int, _c_ptr, _c_i64, _c_i64, _c_ptr],

@@ -436,3 +436,54 @@ def soap_power_spectrum(
         )
     )  # fmt: skip
     return out
+
+
+def orientational_op_device(
+    pos: torch.Tensor, batch: NeighborBatch, order: int = 6, out: torch.Tensor | None = None,
+    col0: int = 0,
+) -> torch.Tensor:  # fmt: skip
+    """|psi_order| for every atom and frame of a batch -> (N, F) float64 (misc.py:15-95).
+    ``batch`` must hold the lists of all atoms (centres == selection == all)."""
+    lib = _lib.load()
+    _require_cuda(pos, "pos")
+    n_frames, n_atoms, _ = pos.shape
+    if batch.n_frames != n_frames or batch.n_cent != n_atoms:
+        msg = "neighbour lists and positions disagree in shape"
+        raise ValueError(msg)
+    if out is None:
+        out = torch.empty((n_atoms, n_frames), dtype=torch.float64, device=pos.device)
+        col0 = 0
+    _lib.check(
+        lib.dsg_orientational_op(
+            pos.data_ptr(), _dtype_code(pos), batch.indptr.data_ptr(), batch.frame_off.data_ptr(),
+            batch.indices.data_ptr(), n_frames, n_atoms, int(order), out.data_ptr(), out.stride(0),
+            int(col0), _stream_ptr(),
+        )
+    )  # fmt: skip
+    return out
+
+
+def velocity_alignment_device(
+    vec: torch.Tensor, batch: NeighborBatch, displacement: bool, out: torch.Tensor | None = None,
+    col0: int = 0,
+) -> torch.Tensor:  # fmt: skip
+    """phi (misc.py:98-219).  ``displacement=True``: ``vec`` = positions (F, N, 3), output (N, F-1)
+    uses pos[f+1]-pos[0] with the rows of frame f; else ``vec`` = velocities (F, N, 3) -> (N, F)."""
+    lib = _lib.load()
+    _require_cuda(vec, "vec")
+    n_f, n_atoms, _ = vec.shape
+    n_out = n_f - 1 if displacement else n_f
+    if n_out < 1 or batch.n_cent != n_atoms or batch.n_frames < n_out:
+        msg = "neighbour lists and vectors disagree in shape"
+        raise ValueError(msg)
+    if out is None:
+        out = torch.empty((n_atoms, n_out), dtype=torch.float64, device=vec.device)
+        col0 = 0
+    _lib.check(
+        lib.dsg_velocity_alignment(
+            vec.data_ptr(), _dtype_code(vec), int(bool(displacement)), batch.indptr.data_ptr(),
+            batch.frame_off.data_ptr(), batch.indices.data_ptr(), n_out, n_atoms, out.data_ptr(),
+            out.stride(0), int(col0), _stream_ptr(),
+        )
+    )  # fmt: skip
+    return out

@@ -2,11 +2,12 @@
 
 ``Trj`` mirrors ``dynsight._internal.trajectory.trajectory.Trj`` (trajectory.py:32-320: the
 constructors, ``get_coordinates``, ``with_slice`` and the four descriptor entry points
-``get_coord_number`` / ``get_lens`` / ``get_soap`` / ``get_timesoap``) and ``Insight`` mirrors
+``get_coord_number`` / ``get_lens`` / ``get_soap`` / ``get_timesoap``, plus the neighbour-list
+consumers ``get_orientational_op`` / ``get_velocity_alignment``, :322-423) and ``Insight`` mirrors
 ``dynsight._internal.trajectory.insight.Insight`` (insight.py:23-92, 136-155: container,
 JSON+NPY dump/load, ``get_angular_velocity``).  Meta dictionaries, return types and error
 messages are the reference's.  Everything else in those classes (tICA, onion clustering, RDF,
-orientational order, ...) is outside the hot path and not provided.
+spatial average, ...) is outside the hot path and not provided.
 """
 
 from __future__ import annotations
@@ -18,6 +19,7 @@ from typing import Any, Literal
 
 import numpy as np
 
+from dynsight_b200 import descriptors as _descriptors
 from dynsight_b200 import lens as _lens
 from dynsight_b200 import soap as _soap
 from dynsight_b200.logs import logger
@@ -199,6 +201,67 @@ class Trj:
         }
         logger.log(f"Computed coord_number using args {attr_dict}.")
         return neigcounts, Insight(dataset=counts.astype(np.float64), meta=attr_dict)
+
+    def get_orientational_op(
+        self,
+        r_cut: float,
+        order: int = 6,
+        centers: str = "all",
+        selection: str = "all",
+        respect_pbc: bool = True,
+        neigcounts: Any | None = None,
+        n_jobs: int = 1,
+    ) -> tuple[Any, Insight]:
+        """Compute the magnitude of the orientational order parameter (trajectory.py:322-373).
+
+        Returns the neighbour list and an Insight with meta: name, r_cut, order, centers,
+        selection.
+        """
+        if neigcounts is None:
+            neigcounts = _lens.list_neighbours_along_trajectory(
+                universe=self.universe, r_cut=r_cut, centers=centers, selection=selection,
+                trajslice=self.trajslice, respect_pbc=respect_pbc, n_jobs=n_jobs,
+            )  # fmt: skip
+        psi = _descriptors.orientational_order_param(
+            self.universe, neigh_list_per_frame=neigcounts, order=order
+        )
+        attr_dict = {
+            "name": "orientational_op",
+            "r_cut": r_cut,
+            "order": order,
+            "centers": centers,
+            "selection": selection,
+        }
+        logger.log(f"Computed orientational order parameter using args {attr_dict}.")
+        return neigcounts, Insight(dataset=psi, meta=attr_dict)
+
+    def get_velocity_alignment(
+        self,
+        r_cut: float,
+        centers: str = "all",
+        selection: str = "all",
+        respect_pbc: bool = True,
+        neigcounts: Any | None = None,
+        n_jobs: int = 1,
+    ) -> tuple[Any, Insight]:
+        """Compute the average velocity alignment (trajectory.py:375-423).
+
+        Returns the neighbour list and an Insight with meta: name, r_cut, centers, selection.
+        """
+        if neigcounts is None:
+            neigcounts = _lens.list_neighbours_along_trajectory(
+                universe=self.universe, r_cut=r_cut, centers=centers, selection=selection,
+                trajslice=self.trajslice, respect_pbc=respect_pbc, n_jobs=n_jobs,
+            )  # fmt: skip
+        phi = _descriptors.velocity_alignment(self.universe, neigh_list_per_frame=neigcounts)
+        attr_dict = {
+            "name": "velocity_alignement",
+            "r_cut": r_cut,
+            "centers": centers,
+            "selection": selection,
+        }
+        logger.log(f"Computed average velocity alignment using args {attr_dict}.")
+        return neigcounts, Insight(dataset=phi, meta=attr_dict)
 
     def get_lens(
         self,

@@ -130,6 +130,29 @@ int dsg_counts_to_f64(const int32_t* d_counts, int n_frames, int n_cent, double*
                       int64_t ld_out, int64_t col0, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Neighbour-list consumers (replace descriptors/misc.py:15-219).
+ * Both take the canonical CSR of dsg_neigh_count/fill with centres == selection == all atoms.
+ *
+ * dsg_orientational_op: |psi_n| of misc.py:76-93 -- out[i*ld_out + col0 + f] =
+ *   |sum_{j in row, j != i} e^{i n theta_ij}| / len(row), 0 if len(row) <= 1; theta from the raw
+ *   (x, y) differences (no minimum image, z ignored), like the reference.
+ * dsg_velocity_alignment: phi of misc.py:98-219 -- mean cosine similarity between the vector of
+ *   atom i and those of its neighbours (zero vectors and j == i skipped).  displacement != 0:
+ *   d_vec holds positions (n_out+1, n_atoms, 3) and the vector of output f is
+ *   pos[f+1] - pos[0] (the reference never advances r_0, misc.py:207-213) with the rows of frame
+ *   f; displacement == 0: d_vec holds (n_out, n_atoms, 3) velocities, rows of the same frame.
+ * ------------------------------------------------------------------------------------------ */
+int dsg_orientational_op(const void* d_pos, int pos_dtype, const int32_t* d_indptr,
+                         const int64_t* d_frame_off, const int32_t* d_indices, int n_frames,
+                         int n_atoms, int order, double* d_out, int64_t ld_out, int64_t col0,
+                         void* stream);
+
+int dsg_velocity_alignment(const void* d_vec, int dtype, int displacement,
+                           const int32_t* d_indptr, const int64_t* d_frame_off,
+                           const int32_t* d_indices, int n_out, int n_atoms, double* d_out,
+                           int64_t ld_out, int64_t col0, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * timeSOAP (replaces timesoap/timesoap.py:13-179: normalize_soap + soap_distance + timesoap).
  *
  * soap is addressed as soap[i*stride_i + f*stride_f + c] (element strides, float64), which covers

@@ -16,7 +16,10 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
 nf = int(sys.argv[3]) if len(sys.argv) > 3 else 8
 dev = torch.device("cuda")
 g = torch.Generator(device=dev).manual_seed(0)
-if what == "neigh_fluid":
+if what == "soap3":  # cfg4-like: 3 species, l_max = 10, metal density
+    box_l = (n / 0.0857) ** (1 / 3)
+    r_cut = 5.0
+elif what == "neigh_fluid":
     box_l = (n / 0.8) ** (1 / 3)
     r_cut = 1.5
 else:
@@ -32,6 +35,9 @@ for it in range(3):
     e0.record()
     if what == "soap":
         out = engine.soap_power_spectrum(pos, sp, cen, box, 5.0, 8, 8)
+    elif what == "soap3":
+        sp3 = (torch.arange(n, device=dev, dtype=torch.int32) * 7919 % 3).to(torch.int32)
+        out = engine.soap_power_spectrum(pos, sp3, cen, box, 5.0, 8, 10, n_species=3)
     elif what in ("neigh", "neigh_fluid"):
         if len(sys.argv) > 4 and sys.argv[4] == "csr":
             nb = engine.neighbor_lists(pos, box, r_cut)

@@ -12,8 +12,9 @@ What it writes (all small, committed):
                          doctest known answers (saponify.py:86-87, :174; timesoap.py:50-52,
                          :115-116, :172-173).
 * ``ref_lens.npz``    -- the reference's own LENS / coordination-number golden arrays
-                         (tests/trajectory/files/{lens,n_c}.npy, tests/systems/lens_2d_{pbc,fbc}.npy,
-                         tests/lens/test_lens/c0-c5, tests/neighbors/test_nn/c0-c4).
+                         (tests/trajectory/files/{lens,n_c,psi,phi}.npy,
+                         tests/systems/lens_2d_{pbc,fbc}.npy, tests/lens/test_lens/c0-c5,
+                         tests/neighbors/test_nn/c0-c4) and the psi / phi doctest answers.
 * ``ref_soap.npz``    -- the reference's SOAP goldens (tests/soap/test_soap/c0-c5,
                          tests/trajectory/files/soap.npy) at frames 0::10 (21 of 201 frames, to keep
                          the fixture small) and the timeSOAP goldens in full
@@ -82,6 +83,11 @@ def main() -> None:
         "trj_n_c": np.load(REF_TESTS / "trajectory/files/n_c.npy"),
         "lens_2d_pbc": np.load(REF_TESTS / "systems/lens_2d_pbc.npy"),
         "lens_2d_fbc": np.load(REF_TESTS / "systems/lens_2d_fbc.npy"),
+        # neighbour-list consumers (tests/trajectory/test_trj.py:80,97-99; doctests misc.py:68,187)
+        "trj_psi": np.load(REF_TESTS / "trajectory/files/psi.npy"),
+        "trj_phi": np.load(REF_TESTS / "trajectory/files/phi.npy"),
+        "kat_psi00": np.float64(0.09556616097688675),
+        "kat_phi00": np.float64(0.38268664479255676),
     }
     for f in sorted((REF_TESTS / "lens/test_lens").glob("c*.npy")):
         d["lens_" + f.name.split("_")[0]] = np.load(f)

@@ -204,3 +204,51 @@ def test_multi_species_via_types():
     assert (np.abs(got - want) / scale).max() < 1e-8
     with pytest.raises(KeyError, match="not a chemical symbol"):
         dsoap.saponify_trajectory(ArrayUniverse(pos, dims, names=["Qq"] * n, types=["Qq"] * n), 4.5)
+
+
+def test_psi_phi_like_test_trj(trj, ref_lens):
+    """tests/trajectory/test_trj.py:80,92,97-99 through Trj."""
+    neigcounts, phi = trj.get_velocity_alignment(r_cut=15.0)
+    assert phi.meta == {"name": "velocity_alignement", "r_cut": 15.0, "centers": "all",
+                        "selection": "all"}  # fmt: skip
+    np.testing.assert_allclose(ref_lens["trj_phi"], phi.dataset, rtol=1e-4, atol=1e-6)
+    _, psi = trj.get_orientational_op(r_cut=15.0, neigcounts=neigcounts)
+    assert psi.meta["name"] == "orientational_op" and psi.meta["order"] == 6
+    np.testing.assert_allclose(ref_lens["trj_psi"], psi.dataset, rtol=1e-3, atol=1e-6)
+    # a plain list[list[AtomGroup]] works too
+    plain = [list(fr) for fr in neigcounts]
+    from dynsight_b200 import descriptors
+
+    psi2 = descriptors.orientational_order_param(trj.universe, plain, order=6)
+    assert np.array_equal(psi2, psi.dataset)
+
+
+def test_psi_phi_doctest_and_random_vs_oracle(xyz60, ref_lens):
+    from dynsight_b200 import descriptors
+    from dynsight_b200.trajectory import Trj
+    from dynsight_b200.universe import ArrayUniverse
+    from golden_cases import fluid_case
+
+    from oracle import descriptors_oracle as do
+    from oracle import lens_oracle as lo
+
+    t60 = Trj(ArrayUniverse(xyz60["positions"], None, names=xyz60["types"]))
+    neig, _ = t60.get_coord_number(r_cut=3.0)
+    psi = descriptors.orientational_order_param(t60.universe, neig)
+    phi = descriptors.velocity_alignment(t60.universe, neig)
+    assert np.isclose(psi[0][0], float(ref_lens["kat_psi00"]))
+    assert np.isclose(phi[0][0], float(ref_lens["kat_phi00"]))
+    # random fluid, several orders, against the restated reference loops
+    pos, box, r_cut = fluid_case(n_side=7, n_frames=4)
+    pos[2, 5] = pos[0, 5]  # a zero displacement vector
+    dims = np.tile(np.concatenate([box, [90, 90, 90]]).astype(np.float32), (4, 1))
+    u = ArrayUniverse(pos, dims)
+    tr = Trj(u)
+    neig, _ = tr.get_coord_number(r_cut=r_cut)
+    csr = [lo.neighbors(pos[f], pos[f], r_cut, box, True) for f in range(4)]
+    for order in (1, 4, 6):
+        got = descriptors.orientational_order_param(u, neig, order=order)
+        np.testing.assert_allclose(got, do.orientational_order_param(pos, csr, order), rtol=1e-5,
+                                   atol=1e-6)  # fmt: skip
+    np.testing.assert_allclose(descriptors.velocity_alignment(u, neig),
+                               do.velocity_alignment(pos, csr), rtol=1e-5, atol=1e-6)  # fmt: skip

@@ -176,3 +176,30 @@ def test_soap_c_oracle_matches_numpy_oracle(balls7):
         a = so.soap_frame(p7, np.full(7, 6), np.arange(7), cell, 8.0, 4, 4)
         b = so.soap_frame_c(p7, np.full(7, 6), np.arange(7), cell, 8.0, 4, 4)
         assert np.abs(a - b).max() <= 1e-11 * np.abs(a).max()
+
+
+def test_psi_phi_oracle_vs_reference_goldens(balls7, ref_lens):
+    """tests/trajectory/test_trj.py:80,92,97-99: phi rtol 1e-4 / atol 1e-6, psi rtol 1e-3."""
+    from oracle import descriptors_oracle as do
+
+    pos, dims = balls7["positions"], balls7["dims"]
+    csr = [lo.neighbors(pos[f], pos[f], 15.0, dims[f, :3], True) for f in range(pos.shape[0])]
+    psi = do.orientational_order_param(pos, csr, 6)
+    phi = do.velocity_alignment(pos, csr)
+    np.testing.assert_allclose(ref_lens["trj_psi"], psi, rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(ref_lens["trj_phi"], phi, rtol=1e-4, atol=1e-6)
+
+
+def test_psi_phi_doctest_known_answers(xyz60, ref_lens):
+    """misc.py:56-68 and :176-187: trajectory.xyz, r_cut=3.0, no box (bounding box, no 1.01)."""
+    from oracle import descriptors_oracle as do
+
+    pos = xyz60["positions"]
+    csr = []
+    for f in range(pos.shape[0]):
+        box = lo.frame_box(pos[f], None, None)
+        csr.append(lo.neighbors(pos[f], pos[f], 3.0, box, True))
+    psi = do.orientational_order_param(pos, csr, 6)
+    phi = do.velocity_alignment(pos, csr)
+    assert np.isclose(psi[0][0], float(ref_lens["kat_psi00"]))
+    assert np.isclose(phi[0][0], float(ref_lens["kat_phi00"]))
