@@ -165,6 +165,10 @@ class NeighborRows:
     def overflowed(self) -> bool:
         return bool(self.status[0].item() != 0)
 
+    def needs_warp_kernel(self) -> bool:
+        """The thread-per-centre kernel met a row longer than its staging tile (status 2)."""
+        return bool(self.status[0].item() == 2)
+
     def needed_capacity(self) -> int:
         return int(self.status[2:].max().item()) * max(1, int(self.status[1].item()))
 
@@ -179,8 +183,12 @@ def neighbor_rows(
     pos_cent: torch.Tensor | None = None,
     respect_pbc: bool = True,
     capacity: int | None = None,
+    force_warp_kernel: bool = False,
 ) -> NeighborRows:
     """Single-traversal neighbour rows (same membership as :func:`neighbor_lists`, rows unsorted).
+
+    The library picks one thread per centre for sparse cells and one warp per cell otherwise;
+    ``force_warp_kernel`` disables the former.
 
     The caller must check ``overflowed()`` once the work is done (one host sync) and retry with
     ``needed_capacity()``; :func:`lens_from_positions` does that.
@@ -216,7 +224,8 @@ def neighbor_rows(
     _lib.check(
         lib.dsg_neigh_rows(
             pos_env.data_ptr(), pos_cent.data_ptr() if pos_cent is not None else None, code,
-            n_frames, n_env, n_cent, h_box.ctypes.data, float(r_cut), int(bool(respect_pbc)),
+            n_frames, n_env, n_cent, h_box.ctypes.data, float(r_cut),
+            int(bool(respect_pbc)) | (2 if force_warp_kernel else 0),
             workspace.data_ptr(), ws_bytes.value, counts.data_ptr(), row_start.data_ptr(),
             rows.data_ptr(), capacity, status.data_ptr(), _stream_ptr(),
         )
@@ -258,12 +267,16 @@ def lens_from_positions(
 ) -> tuple[torch.Tensor, NeighborRows]:
     """LENS for all frame pairs of a batch straight from positions (rows path + retry on the rare
     reservation overflow).  Returns the (M, n_pairs) result and the rows batch (for the counts)."""
+    force_warp = False
     while True:
-        nr = neighbor_rows(pos_env, box, r_cut, pos_cent, respect_pbc, capacity)
+        nr = neighbor_rows(pos_env, box, r_cut, pos_cent, respect_pbc, capacity, force_warp)
         res = lens_pairs_rows(nr, delay, out=out, col0=col0)
         if not nr.overflowed():
             return res, nr
-        capacity = int(nr.needed_capacity() * 1.1) + _ROW_PARTS * 2048
+        if nr.needs_warp_kernel():
+            force_warp = True  # rows longer than the thread kernel's tile: one warp per cell
+        else:
+            capacity = int(nr.needed_capacity() * 1.1) + _ROW_PARTS * 2048
 
 
 def lens_pairs(

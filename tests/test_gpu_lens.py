@@ -323,6 +323,28 @@ def test_rows_path_dense_cells_and_overflow_retry():
     assert np.array_equal(lens.cpu().numpy(), want)
 
 
+def test_rows_path_thread_and_warp_kernels_agree():
+    """Sparse fluid: the thread-per-centre kernel (auto) and the warp-per-cell kernel (forced) give
+    the same rows; a dense spot makes the thread kernel hand over (status 2)."""
+    from dynsight_b200 import engine
+
+    pos, box, r_cut = fluid_case(n_side=16, n_frames=3)
+    dims = np.tile(np.concatenate([box, [90, 90, 90]]).astype(np.float32), (3, 1))
+    for pbc in (True, False):
+        auto = engine.neighbor_rows(_dev(pos), box, r_cut, None, pbc)
+        warp = engine.neighbor_rows(_dev(pos), box, r_cut, None, pbc, force_warp_kernel=True)
+        _check_rows_vs_oracle(auto, pos, None, box, r_cut, pbc)
+        _check_rows_vs_oracle(warp, pos, None, box, r_cut, pbc)
+    # 60 atoms packed into one corner -> more than 32 neighbours for those centres
+    dense = pos.copy()
+    dense[:, :60] = (dense[:, :60] % 1.0) * 0.9 + 0.05
+    nr = engine.neighbor_rows(_dev(dense), box, r_cut, None, True)
+    assert nr.needs_warp_kernel()
+    lens, nr2 = engine.lens_from_positions(_dev(dense), box, r_cut, 1)
+    assert not nr2.overflowed()
+    assert np.array_equal(lens.cpu().numpy(), lo.compute_lens_arrays(dense, dims, r_cut))
+
+
 def test_rows_path_lens_goldens(balls7, ref_lens, numba_cases):
     from dynsight_b200 import engine
 
