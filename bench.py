@@ -403,7 +403,10 @@ def run_b200(args: argparse.Namespace) -> None:
         "peak": fp64_peak_tflops,
         "unit": "TFLOP/s",
         "frac": soap_tflops / fp64_peak_tflops if fp64_peak_tflops else None,
-        "traffic": None,
+        # dram__bytes_read+write of this kernel from the ncu --set full capture summarised in
+        # profiles/r1_soap_kernel_v5_summary.txt: 2290 B per centre-frame, scaled to this launch
+        "traffic": 2290.0 * soap_pf,
+        "traffic_source": "profiles/r1_soap_kernel_v5_summary.txt (2290 B per centre-frame)",
         "peak_source": "dsg_fp64_fma_probe measured in this run (not in MEASURED_PEAKS.json)",
         "algorithmic_flops_per_pf": fl,
         "exps_per_pf_not_counted_as_flops": ex,
@@ -418,7 +421,9 @@ def run_b200(args: argparse.Namespace) -> None:
         {
             "kernel": "cell list + neigh_rows_kernel (single traversal) + lens_rows_run_kernel",
             "bound": "hbm", "achieved": lens_gbs, "peak": hbm_peak, "unit": "GB/s",
-            "frac": lens_gbs / hbm_peak, "traffic": None,
+            "frac": lens_gbs / hbm_peak, "traffic": 87.0 * n_atoms * (bsz + 1),
+            "traffic_source": "profiles/r1_neigh_rows_warp_kernel_summary.txt (87 B per centre-frame, "
+                              "neighbour kernel only)",
             "algorithmic_bytes_per_pf": lens_bytes_pf, "mean_neighbours": k_mean_lens,
             "ms_per_step": part_ms["neigh"] + part_ms["lens"], "peak_source": hbm_src,
         },
