@@ -193,7 +193,7 @@ def run_reference(args: argparse.Namespace) -> None:
         return  # rank 0 alone runs the host path
     threads = os.cpu_count() or 1
     pos, box = host_trajectory(args.atoms, 2, seed=0)
-    n_c = 20000
+    n_c = args.atoms
     for _ in range(max(1, min(args.warmup, 1))):
         cpu_reference_step(pos, box, 500, threads)
     t0 = time.perf_counter()
@@ -476,13 +476,18 @@ def run_b200(args: argparse.Namespace) -> None:
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         hpos = block[:2].cpu().numpy()
-        res = cpu_reference_step(hpos, box, 20000, threads)
+        cpu_reference_step(hpos, box, 500, threads)  # warm the thread pool and page in the libs
+        reps = [cpu_reference_step(hpos, box, n_atoms, threads) for _ in range(4)]
+        secs = sum(r["seconds"] for r in reps)
         cpu_baseline = {
-            "value": res["pf_per_s"], "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": (f"LENS on 1 frame pair of {n_atoms} atoms, SOAP on 20000 centres x 2 frames, "
-                       f"timeSOAP on 20000 pairs ({res['seconds']:.1f} s of CPU work)"),
-            "lens_pf_per_s": res["lens_pf_per_s"], "soap_pf_per_s": res["soap_pf_per_s"],
-            "timesoap_pf_per_s": res["timesoap_pf_per_s"],
+            "value": float(np.mean([r["pf_per_s"] for r in reps])), "unit": UNIT,
+            "cores": threads, "kind": "port",
+            "sample": (f"4 x (LENS on 1 frame pair of {n_atoms} atoms, SOAP on all {n_atoms} "
+                       f"centres x 2 frames, timeSOAP on {n_atoms} pairs): {secs:.1f} s of CPU "
+                       "work"),
+            "lens_pf_per_s": float(np.mean([r["lens_pf_per_s"] for r in reps])),
+            "soap_pf_per_s": float(np.mean([r["soap_pf_per_s"] for r in reps])),
+            "timesoap_pf_per_s": float(np.mean([r["timesoap_pf_per_s"] for r in reps])),
         }  # fmt: skip
 
     if rank == 0:
