@@ -45,6 +45,9 @@ constexpr int kOpenCellsPerAxis = 32;
 #ifndef DSG_SOAP_MIN_BLOCKS
 #define DSG_SOAP_MIN_BLOCKS 6
 #endif
+#ifndef DSG_SOAP_MIN_BLOCKS_L10
+#define DSG_SOAP_MIN_BLOCKS_L10 4
+#endif
 constexpr int kListCap = 32;     // displacement list entries per warp
 constexpr int kCellTab = 32;     // (cell range, shift) entries resolved per pass
 constexpr int kBatchCap = 64;    // 32-candidate batches listed per pass
@@ -59,7 +62,8 @@ struct SoapFrame {
     int nc[3];
     int mode[3];
     int nimg[3];
-    int cell_base;
+    int cell_base;        // first (species 0) cell of the frame in the batch-wide cell arrays
+    int spec_stride;      // cells per species block: the sort key is species * spec_stride + cell
     unsigned lo_bits[3];  // open mode: encoded min / max (atomics)
     unsigned hi_bits[3];
 };
@@ -77,7 +81,6 @@ struct SoapArgs {
     const double* sx;       // cell-sorted SoA (wrapped / shifted coordinates)
     const double* sy;
     const double* sz;
-    const int* sspec;
     const int* sid;         // original atom index of a sorted slot
     const int* cell_start;
     const SoapFrame* frames;
@@ -94,6 +97,7 @@ struct SoapArgs {
     const int* decode;      // (n_feat)
     double* out;
     long long stride_i, stride_f;
+    double* gscr;           // split mode: primitive sums G (n_frames, n_cent, S, n_lm, n)
     SoapPlan plan;
 };
 
@@ -183,9 +187,9 @@ __device__ __forceinline__ void soap_locate(const SoapFrame* __restrict__ p, dou
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-soap_bin_kernel(const T* __restrict__ pos, int n_atoms, const SoapFrame* __restrict__ fr,
-                double* __restrict__ wpos, unsigned* __restrict__ cell_id,
-                int* __restrict__ cell_cnt) {
+soap_bin_kernel(const T* __restrict__ pos, const int* __restrict__ species, int n_atoms,
+                const SoapFrame* __restrict__ fr, double* __restrict__ wpos,
+                unsigned* __restrict__ cell_id, int* __restrict__ cell_cnt) {
     const int f = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_atoms) return;
@@ -197,17 +201,19 @@ soap_bin_kernel(const T* __restrict__ pos, int n_atoms, const SoapFrame* __restr
     wpos[a * 3] = w[0];
     wpos[a * 3 + 1] = w[1];
     wpos[a * 3 + 2] = w[2];
-    const int cell = (c[0] * p->nc[1] + c[1]) * p->nc[2] + c[2];
+    // species-major key: every species has its own complete cell-sorted array, so a gather for
+    // one species reads only that species' atoms and x-adjacent cells stay contiguous
+    const int cell = species[i] * p->spec_stride + (c[0] * p->nc[1] + c[1]) * p->nc[2] + c[2];
     cell_id[a] = (unsigned)cell;
     atomicAdd(&cell_cnt[p->cell_base + cell], 1);
 }
 
 __global__ void __launch_bounds__(256)
-soap_scatter_kernel(const double* __restrict__ wpos, const int* __restrict__ species, int n_atoms,
+soap_scatter_kernel(const double* __restrict__ wpos, int n_atoms,
                     const SoapFrame* __restrict__ fr, const unsigned* __restrict__ cell_id,
                     int* __restrict__ cell_cnt, const int* __restrict__ cell_start,
                     double* __restrict__ sx, double* __restrict__ sy, double* __restrict__ sz,
-                    int* __restrict__ sspec, int* __restrict__ sid) {
+                    int* __restrict__ sid) {
     const int f = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_atoms) return;
@@ -217,7 +223,6 @@ soap_scatter_kernel(const double* __restrict__ wpos, const int* __restrict__ spe
     sx[slot] = wpos[a * 3];
     sy[slot] = wpos[a * 3 + 1];
     sz[slot] = wpos[a * 3 + 2];
-    sspec[slot] = species[i];
     sid[slot] = i;
 }
 
@@ -357,278 +362,16 @@ __device__ __forceinline__ void store_item(const Acc<S>& a, int l, int k, int n,
         if (s < 2 * l + 1) cz[(l * l + s) * n + k] = a.v[s];
 }
 
-template <int LT, int S0, int S1, int S2, int S3>
-__global__ void __launch_bounds__(64, (S0 <= 17) ? DSG_SOAP_MIN_BLOCKS : (S0 <= 21 ? 5 : 4))
-soap_kernel(const SoapArgs a) {
-    extern __shared__ __align__(16) double smem_all[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int warps = blockDim.x >> 5;
-    // block-wide tables: 2^(j/64) and (if small enough) the Loewdin matrices
-    double* exp_tab = smem_all;
-    double* bmat_s = smem_all + kExpTab;
-    for (int i = threadIdx.x; i < kExpTab; i += blockDim.x) exp_tab[i] = a.exp_tab[i];
-    for (int i = threadIdx.x; i < a.bmat_smem_doubles; i += blockDim.x) bmat_s[i] = a.bmat[i];
-    __syncthreads();
-    const double* __restrict__ bmat = a.bmat_smem_doubles > 0 ? bmat_s : a.bmat;
-    double* smem = smem_all + kExpTab + a.bmat_smem_doubles;
-    const int f = blockIdx.y;
-    // each warp walks a run of consecutive slots of the frame's cell-sorted order: consecutive
-    // centres share their candidate cells (L1 reuse) and the block-wide tables are loaded once
-    const int first = (blockIdx.x * warps + warp) * a.slots_per_warp;
-    const int last = min(a.n_atoms, first + a.slots_per_warp);
-    if (first >= last) return;  // warps are independent from here: only __syncwarp below
-
+// Loewdin mixing + power spectrum of one centre.  G [S][n_lm][n] may sit in shared or global
+// memory; the mixed coefficients c[z][lm][n'] = sqrt(w_lm) * sum_k bmat[l][n'][k] G[z][lm][k] go to
+// the shared buffer `mix`, then one lane per output contracts over m and the warp writes the
+// spectrum coalesced.
+__device__ __forceinline__ void mix_and_spectrum(const SoapArgs& a, const double* __restrict__ gsum,
+                                                 double* __restrict__ mix,
+                                                 const double* __restrict__ bmat,
+                                                 double* __restrict__ out, int lane) {
     const SoapPlan& pl = a.plan;
-    const int n = pl.n_max, P = pl.row_stride, n_lm = pl.n_lm;
-    const int c_doubles = pl.n_species * n_lm * n;
-    const bool single_pass = pl.n_species * pl.kblocks == 1;
-    const int per_warp = (kListCap * 4 + kCellTab * 4 + kBatchDoubles + pl.rbuf_doubles +
-                          (single_pass ? 0 : c_doubles) + 1) & ~1;  // 16-byte rows
-    double* nbuf = smem + (size_t)warp * per_warp;     // [32][4] dx dy dz r2
-    double* tab_sh = nbuf + kListCap * 4;                // [3][32] image shifts of the cell table
-    int2* tab_q = reinterpret_cast<int2*>(tab_sh + 3 * kCellTab);  // [32] candidate ranges
-    int2* bl_q = reinterpret_cast<int2*>(tab_sh + kCellTab * 4);   // [64] batch (start, count)
-    int* bl_e = reinterpret_cast<int*>(bl_q + kBatchCap);             // [64] batch -> table entry
-    double* rbuf = tab_sh + kCellTab * 4 + kBatchDoubles;  // [kChunk][P] harmonics; later G / mixed
-    int cached_cell = -1, n_batches = -1;
-    // primitive sums G [S][n_lm][n]: a separate buffer only if they must survive several passes
-    double* cbuf = single_pass ? rbuf : rbuf + pl.rbuf_doubles;
-
-    const SoapFrame* __restrict__ fr = a.frames + f;
-    int ne[3], mode[3], nc[3], nimg[3];
-    double box[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        mode[k] = fr->mode[k];
-        nc[k] = fr->nc[k];
-        nimg[k] = fr->nimg[k];
-        box[k] = fr->box[k];
-        ne[k] = mode[k] == kNarrow ? 2 * nimg[k] + 1 : 3;
-    }
-    const int cell_base = fr->cell_base;
-
-    const int g = lane >> 3, kk = lane & 7;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    int il[kMaxItems], ioff[kMaxItems];
-#pragma unroll
-    for (int t = 0; t < kMaxItems; ++t) {
-        il[t] = pl.item_l[g][t];
-        ioff[t] = il[t] >= 0 ? il[t] * (il[t] + 1) : 0;
-    }
-
-    for (int slot_local = first; slot_local < last; ++slot_local) {
-    const size_t slot = (size_t)f * a.n_atoms + slot_local;
-    const int ci = a.centre_of_atom[a.sid[slot]];
-    if (ci < 0) continue;
-    const double xc = a.sx[slot], yc = a.sy[slot], zc = a.sz[slot];
-    int cc[3];
-    {
-        double w[3];
-        soap_locate(fr, xc, yc, zc, w, cc);  // coordinates are already wrapped: recomputes the cell
-    }
-
-    for (int z_sp = 0; z_sp < pl.n_species; ++z_sp) {
-        for (int kb = 0; kb < pl.kblocks; ++kb) {
-            const int k = kb * kKBlock + kk;
-            const bool kact = k < n;
-            double gam[kMaxItems];
-#pragma unroll
-            for (int t = 0; t < kMaxItems; ++t)
-                gam[t] = (kact && il[t] >= 0) ? -a.gamma[il[t] * n + k] : 0.0;
-            // l = 0: lane (jq, k) sums exp(-gamma_0k r^2) over the neighbours jj = jq (mod 4)
-            const double gam0 = kact ? -a.gamma[k] : 0.0;
-            double acc00 = 0.0;
-            Acc<S0> a0;
-            Acc<S1> a1;
-            Acc<S2> a2;
-            Acc<S3> a3;
-#pragma unroll
-            for (int s = 0; s < S0; ++s) a0.v[s] = 0.0;
-#pragma unroll
-            for (int s = 0; s < S1; ++s) a1.v[s] = 0.0;
-#pragma unroll
-            for (int s = 0; s < S2; ++s) a2.v[s] = 0.0;
-#pragma unroll
-            for (int s = 0; s < S3; ++s) a3.v[s] = 0.0;
-
-            auto process = [&](int fill) {
-                for (int h0 = 0; h0 < fill; h0 += kChunk) {
-                    const int nh = min(kChunk, fill - h0);
-                    if (lane < nh) {   // phase B
-                        const double* d = nbuf + (h0 + lane) * 4;
-                        solid_harmonics<LT>(d[0], d[1], d[2], d[3], rbuf + lane * P);
-                    }
-                    __syncwarp();
-#pragma unroll kUnrollC
-                    for (int jj = 0; jj < nh; ++jj) {   // phase C
-                        const double r2 = nbuf[(h0 + jj) * 4 + 3];
-                        const double* __restrict__ rt = rbuf + jj * P;
-                        if (S0 > 0) accumulate<S0>(a0, exp_neg(gam[0] * r2, exp_tab), rt + ioff[0]);
-                        if (S1 > 0) accumulate<S1>(a1, exp_neg(gam[1] * r2, exp_tab), rt + ioff[1]);
-                        if (S2 > 0) accumulate<S2>(a2, exp_neg(gam[2] * r2, exp_tab), rt + ioff[2]);
-                        if (S3 > 0) accumulate<S3>(a3, exp_neg(gam[3] * r2, exp_tab), rt + ioff[3]);
-                    }
-#pragma unroll
-                    for (int q = 0; q < kChunk / 4; ++q) {   // l = 0, a quarter of the chunk per lane
-                        const int jj = (lane >> 3) + 4 * q;
-                        if (jj < nh) acc00 += exp_neg(gam0 * nbuf[(h0 + jj) * 4 + 3], exp_tab);
-                    }
-                    __syncwarp();
-                }
-            };
-
-            // ---- gather ----
-            // The (cell range, image shift) entries around the centre's cell are resolved by the
-            // lanes in parallel into a per-warp table; consecutive centres of the same cell reuse it.
-            int fill = 0;
-            const int n_ent_total = ne[0] * ne[1] * ne[2];
-            const int my_cell = (cc[0] * nc[1] + cc[1]) * nc[2] + cc[2];
-            for (int e0 = 0; e0 < n_ent_total; e0 += kCellTab) {
-                if (!(n_ent_total <= kCellTab && cached_cell == my_cell)) {
-                    __syncwarp();
-                    const int e = e0 + lane;
-                    int qb = 0, qe = 0;
-                    double sh[3] = {0.0, 0.0, 0.0};
-                    if (e < n_ent_total) {
-                        int idx[3];
-                        idx[2] = e % ne[2];
-                        idx[1] = (e / ne[2]) % ne[1];
-                        idx[0] = e / (ne[2] * ne[1]);
-                        int cj[3];
-                        bool ok = true;
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            if (mode[k] == kNarrow) {
-                                cj[k] = 0;
-                                sh[k] = (double)(idx[k] - nimg[k]) * box[k];
-                            } else {
-                                cj[k] = cc[k] + idx[k] - 1;
-                                if (mode[k] == kWide) {
-                                    if (cj[k] < 0) { cj[k] += nc[k]; sh[k] = -box[k]; }
-                                    else if (cj[k] >= nc[k]) { cj[k] -= nc[k]; sh[k] = box[k]; }
-                                } else if (cj[k] < 0 || cj[k] >= nc[k]) ok = false;
-                            }
-                        }
-                        if (ok) {
-                            const int cell = cell_base + (cj[0] * nc[1] + cj[1]) * nc[2] + cj[2];
-                            qb = a.cell_start[cell];
-                            qe = a.cell_start[cell + 1];
-                        }
-                    }
-                    tab_q[lane] = make_int2(qb, qe);
-                    tab_sh[lane] = sh[0];
-                    tab_sh[kCellTab + lane] = sh[1];
-                    tab_sh[2 * kCellTab + lane] = sh[2];
-                    // flat list of 32-candidate batches so that loads can be prefetched across cells
-                    const int nbat = qe > qb ? (qe - qb + 31) >> 5 : 0;
-                    int incl = nbat;
-#pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) {
-                        const int t = __shfl_up_sync(kFullS, incl, off);
-                        if (lane >= off) incl += t;
-                    }
-                    n_batches = __shfl_sync(kFullS, incl, 31);
-                    if (n_batches <= kBatchCap) {
-                        for (int i = 0; i < nbat; ++i) {
-                            bl_q[incl - nbat + i] = make_int2(qb + 32 * i, min(32, qe - qb - 32 * i));
-                            bl_e[incl - nbat + i] = lane;
-                        }
-                    }
-                    __syncwarp();
-                    cached_cell = n_ent_total <= kCellTab ? my_cell : -1;
-                }
-                auto consume = [&](double dx, double dy, double dz, double r2, bool hit) {
-                    const unsigned m = __ballot_sync(kFullS, hit);
-                    if (m == 0u) return;
-                    const int cnt = __popc(m), rank = __popc(m & lt_mask);
-                    const int room = kListCap - fill;
-                    if (hit && rank < room) {
-                        double* d = nbuf + (fill + rank) * 4;
-                        d[0] = dx; d[1] = dy; d[2] = dz; d[3] = r2;
-                    }
-                    if (cnt >= room) {
-                        __syncwarp();
-                        process(kListCap);
-                        if (hit && rank >= room) {
-                            double* d = nbuf + (rank - room) * 4;
-                            d[0] = dx; d[1] = dy; d[2] = dz; d[3] = r2;
-                        }
-                        fill = cnt - room;
-                    } else {
-                        fill += cnt;
-                    }
-                };
-                if (n_batches <= kBatchCap) {
-                    // two batches in flight ahead of the one being tested
-                    double x1 = 0.0, y1 = 0.0, z1 = 0.0, x2 = 0.0, y2 = 0.0, z2 = 0.0;
-                    int s1 = -1, s2 = -1;
-                    auto fetch = [&](int b, double& x, double& y, double& z, int& sp) {
-                        sp = -1;
-                        if (b < n_batches) {
-                            const int2 q = bl_q[b];
-                            if (lane < q.y) {
-                                x = a.sx[q.x + lane]; y = a.sy[q.x + lane]; z = a.sz[q.x + lane];
-                                sp = a.sspec[q.x + lane];
-                            }
-                        }
-                    };
-                    fetch(0, x1, y1, z1, s1);
-                    fetch(1, x2, y2, z2, s2);
-                    for (int b = 0; b < n_batches; ++b) {
-                        const int e = bl_e[b];
-                        const double vx = x1, vy = y1, vz = z1;
-                        const int vs = s1;
-                        x1 = x2; y1 = y2; z1 = z2; s1 = s2;
-                        fetch(b + 2, x2, y2, z2, s2);
-                        const double dx = vx + tab_sh[e] - xc, dy = vy + tab_sh[kCellTab + e] - yc;
-                        const double dz = vz + tab_sh[2 * kCellTab + e] - zc;
-                        const double r2 = dx * dx + dy * dy + dz * dz;
-                        consume(dx, dy, dz, r2, vs == z_sp && r2 <= a.r2max);
-                    }
-                } else {
-                    const int n_ent = min(kCellTab, n_ent_total - e0);
-                    for (int t = 0; t < n_ent; ++t) {
-                        const int2 qr = tab_q[t];
-                        const int qb = qr.x, qe = qr.y;
-                        if (qb >= qe) continue;
-                        const double shx = tab_sh[t], shy = tab_sh[kCellTab + t];
-                        const double shz = tab_sh[2 * kCellTab + t];
-                        for (int q0 = qb; q0 < qe; q0 += 32) {
-                            const int q = q0 + lane;
-                            double dx = 0.0, dy = 0.0, dz = 0.0, r2 = 0.0;
-                            bool hit = false;
-                            if (q < qe) {
-                                dx = a.sx[q] + shx - xc; dy = a.sy[q] + shy - yc;
-                                dz = a.sz[q] + shz - zc;
-                                r2 = dx * dx + dy * dy + dz * dz;
-                                hit = a.sspec[q] == z_sp && r2 <= a.r2max;
-                            }
-                            consume(dx, dy, dz, r2, hit);
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-            if (fill > 0) process(fill);
-
-            // ---- registers -> shared G[z][lm][k] ----
-            acc00 += __shfl_xor_sync(kFullS, acc00, 8);
-            acc00 += __shfl_xor_sync(kFullS, acc00, 16);
-            if (kact) {
-                double* cz = cbuf + (size_t)z_sp * n_lm * n;
-                if (g == 0) cz[k] = acc00;  // lm = 0: S_0^0 = 1
-                store_item<S0>(a0, il[0], k, n, cz);
-                store_item<S1>(a1, il[1], k, n, cz);
-                store_item<S2>(a2, il[2], k, n, cz);
-                store_item<S3>(a3, il[3], k, n, cz);
-            }
-            __syncwarp();
-        }
-    }
-
-    // ---- Loewdin mixing: c[z][lm][n'] = sqrt(w_lm) * sum_k bmat[l][n'][k] G[z][lm][k] ----
-    // the harmonics buffer is free now; with a single pass G sits at its start
-    double* mix = single_pass ? rbuf + ((c_doubles + 1) & ~1) : rbuf;
+    const int n = pl.n_max, n_lm = pl.n_lm;
     const int n_out = pl.n_species * n_lm * n;
     if (n == 8) {
         // one column (z, lm) per lane: G[0..8) in registers, 8x8 matrix rows as 128-bit broadcasts
@@ -636,7 +379,7 @@ soap_kernel(const SoapArgs a) {
             const int lm = col % n_lm;
             const int l = a.lm_l[lm];
             const double w = a.swlm[lm];
-            const double2* __restrict__ v2 = reinterpret_cast<const double2*>(cbuf + (size_t)col * 8);
+            const double2* __restrict__ v2 = reinterpret_cast<const double2*>(gsum + (size_t)col * 8);
             const double2 g0 = v2[0], g1 = v2[1], g2 = v2[2], g3 = v2[3];
             const double2* __restrict__ b2 = reinterpret_cast<const double2*>(bmat + (size_t)l * 64);
             double2* __restrict__ o2 = reinterpret_cast<double2*>(mix + (size_t)col * 8);
@@ -662,7 +405,7 @@ soap_kernel(const SoapArgs a) {
         const int dcol = 32 / n, dnp = 32 - dcol * n;
         for (int idx = lane; idx < n_out; idx += 32) {
             const int l = a.lm_l[lm];
-            const double* __restrict__ v = cbuf + (size_t)col * n;
+            const double* __restrict__ v = gsum + (size_t)col * n;
             const double* __restrict__ bm = bmat + ((size_t)l * n + np) * n;
             double s0 = 0.0, s1 = 0.0;
             int k = 0;
@@ -681,8 +424,6 @@ soap_kernel(const SoapArgs a) {
     }
     __syncwarp();
 
-    // ---- power spectrum ----
-    double* __restrict__ out = a.out + (long long)ci * a.stride_i + (long long)f * a.stride_f;
     for (int c = lane; c < pl.n_feat; c += 32) {
         const int code = a.decode[c];
         const int zi = code & 15, zj = (code >> 4) & 15, l = (code >> 8) & 15;
@@ -698,7 +439,311 @@ soap_kernel(const SoapArgs a) {
         out[c] = s0 + s1;
     }
     __syncwarp();
+}
+
+// SPLIT = false: one species and n_max <= 8 -- the primitive sums of a centre are complete after
+// one pass, so mixing and the power spectrum follow in the same kernel (G never leaves the SM).
+// SPLIT = true: several species and/or radial blocks -- the warp walks its run of centres once per
+// (species, radial block) pass and writes that slice of G to a global scratch;
+// soap_spectrum_kernel finishes the centres.  No per-warp coefficient buffer is needed, so the
+// occupancy is the single-species one whatever the number of species.
+template <int LT, int S0, int S1, int S2, int S3, bool SPLIT>
+__global__ void __launch_bounds__(64, (S0 <= 17) ? DSG_SOAP_MIN_BLOCKS
+                                                    : (S0 <= 21 ? DSG_SOAP_MIN_BLOCKS_L10 : 4))
+soap_kernel(const SoapArgs a) {
+    extern __shared__ __align__(16) double smem_all[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warps = blockDim.x >> 5;
+    // block-wide tables: 2^(j/16) and (if small enough) the Loewdin matrices
+    double* exp_tab = smem_all;
+    double* bmat_s = smem_all + kExpTab;
+    const int bmat_stage = SPLIT ? 0 : a.bmat_smem_doubles;
+    for (int i = threadIdx.x; i < kExpTab; i += blockDim.x) exp_tab[i] = a.exp_tab[i];
+    for (int i = threadIdx.x; i < bmat_stage; i += blockDim.x) bmat_s[i] = a.bmat[i];
+    __syncthreads();
+    const double* __restrict__ bmat = bmat_stage > 0 ? bmat_s : a.bmat;
+    double* smem = smem_all + kExpTab + bmat_stage;
+    const int f = blockIdx.y;
+    // each warp walks a run of consecutive slots of the frame's (species, cell)-sorted order:
+    // consecutive centres share their candidate cells (L1 reuse, cached cell table) and the
+    // block-wide tables are loaded once
+    const int first = (blockIdx.x * warps + warp) * a.slots_per_warp;
+    const int last = min(a.n_atoms, first + a.slots_per_warp);
+    if (first >= last) return;  // warps are independent from here: only __syncwarp below
+
+    const SoapPlan& pl = a.plan;
+    const int n = pl.n_max, P = pl.row_stride, n_lm = pl.n_lm;
+    const int c_doubles = pl.n_species * n_lm * n;
+    const int per_warp = (kListCap * 4 + kCellTab * 4 + kBatchDoubles + pl.rbuf_doubles + 1) & ~1;
+    double* nbuf = smem + (size_t)warp * per_warp;     // [32][4] dx dy dz r2
+    double* tab_sh = nbuf + kListCap * 4;                // [3][32] image shifts of the cell table
+    int2* tab_q = reinterpret_cast<int2*>(tab_sh + 3 * kCellTab);  // [32] candidate ranges
+    int2* bl_q = reinterpret_cast<int2*>(tab_sh + kCellTab * 4);   // [64] batch (start, count)
+    int* bl_e = reinterpret_cast<int*>(bl_q + kBatchCap);             // [64] batch -> table entry
+    double* rbuf = tab_sh + kCellTab * 4 + kBatchDoubles;  // [kChunk][P] harmonics; later G / mixed
+
+    const SoapFrame* __restrict__ fr = a.frames + f;
+    int ne[3], mode[3], nc[3], nimg[3];
+    double box[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        mode[k] = fr->mode[k];
+        nc[k] = fr->nc[k];
+        nimg[k] = fr->nimg[k];
+        box[k] = fr->box[k];
+        ne[k] = mode[k] == kNarrow ? 2 * nimg[k] + 1 : 3;
+    }
+    const int spec_stride = fr->spec_stride;
+
+    const int g = lane >> 3, kk = lane & 7;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int il[kMaxItems], ioff[kMaxItems];
+#pragma unroll
+    for (int t = 0; t < kMaxItems; ++t) {
+        il[t] = pl.item_l[g][t];
+        ioff[t] = il[t] >= 0 ? il[t] * (il[t] + 1) : 0;
+    }
+
+    const int n_pass = SPLIT ? pl.n_species * pl.kblocks : 1;
+    for (int pass = 0; pass < n_pass; ++pass) {
+    const int z_sp = SPLIT ? pass / pl.kblocks : 0;
+    const int kb = SPLIT ? pass - z_sp * pl.kblocks : 0;
+    const int cell_base = fr->cell_base + z_sp * spec_stride;  // the species' own cell grid
+    const int k = kb * kKBlock + kk;
+    const bool kact = k < n;
+    int cached_cell = -1, n_batches = -1;
+
+    for (int slot_local = first; slot_local < last; ++slot_local) {
+        const size_t slot = (size_t)f * a.n_atoms + slot_local;
+        const int ci = a.centre_of_atom[a.sid[slot]];
+        if (ci < 0) continue;
+        const double xc = a.sx[slot], yc = a.sy[slot], zc = a.sz[slot];
+        int cc[3];
+        {
+            double w[3];
+            soap_locate(fr, xc, yc, zc, w, cc);  // coordinates are already wrapped: the cell again
+        }
+        double gam[kMaxItems];
+#pragma unroll
+        for (int t = 0; t < kMaxItems; ++t)
+            gam[t] = (kact && il[t] >= 0) ? -a.gamma[il[t] * n + k] : 0.0;
+        // l = 0: lane (jq, k) sums exp(-gamma_0k r^2) over the neighbours jj = jq (mod 4)
+        const double gam0 = kact ? -a.gamma[k] : 0.0;
+        double acc00 = 0.0;
+        Acc<S0> a0;
+        Acc<S1> a1;
+        Acc<S2> a2;
+        Acc<S3> a3;
+#pragma unroll
+        for (int s = 0; s < S0; ++s) a0.v[s] = 0.0;
+#pragma unroll
+        for (int s = 0; s < S1; ++s) a1.v[s] = 0.0;
+#pragma unroll
+        for (int s = 0; s < S2; ++s) a2.v[s] = 0.0;
+#pragma unroll
+        for (int s = 0; s < S3; ++s) a3.v[s] = 0.0;
+
+        auto process = [&](int fill) {
+            for (int h0 = 0; h0 < fill; h0 += kChunk) {
+                const int nh = min(kChunk, fill - h0);
+                if (lane < nh) {   // phase B
+                    const double* d = nbuf + (h0 + lane) * 4;
+                    solid_harmonics<LT>(d[0], d[1], d[2], d[3], rbuf + lane * P);
+                }
+                __syncwarp();
+#pragma unroll kUnrollC
+                for (int jj = 0; jj < nh; ++jj) {   // phase C
+                    const double r2 = nbuf[(h0 + jj) * 4 + 3];
+                    const double* __restrict__ rt = rbuf + jj * P;
+                    if (S0 > 0) accumulate<S0>(a0, exp_neg(gam[0] * r2, exp_tab), rt + ioff[0]);
+                    if (S1 > 0) accumulate<S1>(a1, exp_neg(gam[1] * r2, exp_tab), rt + ioff[1]);
+                    if (S2 > 0) accumulate<S2>(a2, exp_neg(gam[2] * r2, exp_tab), rt + ioff[2]);
+                    if (S3 > 0) accumulate<S3>(a3, exp_neg(gam[3] * r2, exp_tab), rt + ioff[3]);
+                }
+#pragma unroll
+                for (int q = 0; q < kChunk / 4; ++q) {   // l = 0, a quarter of the chunk per lane
+                    const int jj = (lane >> 3) + 4 * q;
+                    if (jj < nh) acc00 += exp_neg(gam0 * nbuf[(h0 + jj) * 4 + 3], exp_tab);
+                }
+                __syncwarp();
+            }
+        };
+
+        // ---- gather ----
+        // The (cell range, image shift) entries around the centre's cell are resolved by the
+        // lanes in parallel into a per-warp table; consecutive centres of the same cell reuse it.
+        int fill = 0;
+        const int n_ent_total = ne[0] * ne[1] * ne[2];
+        const int my_cell = (cc[0] * nc[1] + cc[1]) * nc[2] + cc[2];
+        for (int e0 = 0; e0 < n_ent_total; e0 += kCellTab) {
+            if (!(n_ent_total <= kCellTab && cached_cell == my_cell)) {
+                __syncwarp();
+                const int e = e0 + lane;
+                int qb = 0, qe = 0;
+                double sh[3] = {0.0, 0.0, 0.0};
+                if (e < n_ent_total) {
+                    int idx[3];
+                    idx[2] = e % ne[2];
+                    idx[1] = (e / ne[2]) % ne[1];
+                    idx[0] = e / (ne[2] * ne[1]);
+                    int cj[3];
+                    bool ok = true;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        if (mode[d] == kNarrow) {
+                            cj[d] = 0;
+                            sh[d] = (double)(idx[d] - nimg[d]) * box[d];
+                        } else {
+                            cj[d] = cc[d] + idx[d] - 1;
+                            if (mode[d] == kWide) {
+                                if (cj[d] < 0) { cj[d] += nc[d]; sh[d] = -box[d]; }
+                                else if (cj[d] >= nc[d]) { cj[d] -= nc[d]; sh[d] = box[d]; }
+                            } else if (cj[d] < 0 || cj[d] >= nc[d]) ok = false;
+                        }
+                    }
+                    if (ok) {
+                        const int cell = cell_base + (cj[0] * nc[1] + cj[1]) * nc[2] + cj[2];
+                        qb = a.cell_start[cell];
+                        qe = a.cell_start[cell + 1];
+                    }
+                }
+                tab_q[lane] = make_int2(qb, qe);
+                tab_sh[lane] = sh[0];
+                tab_sh[kCellTab + lane] = sh[1];
+                tab_sh[2 * kCellTab + lane] = sh[2];
+                // flat list of 32-candidate batches so that loads can be prefetched across cells
+                const int nbat = qe > qb ? (qe - qb + 31) >> 5 : 0;
+                int incl = nbat;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int t = __shfl_up_sync(kFullS, incl, off);
+                    if (lane >= off) incl += t;
+                }
+                n_batches = __shfl_sync(kFullS, incl, 31);
+                if (n_batches <= kBatchCap) {
+                    for (int i = 0; i < nbat; ++i) {
+                        bl_q[incl - nbat + i] = make_int2(qb + 32 * i, min(32, qe - qb - 32 * i));
+                        bl_e[incl - nbat + i] = lane;
+                    }
+                }
+                __syncwarp();
+                cached_cell = n_ent_total <= kCellTab ? my_cell : -1;
+            }
+            auto consume = [&](double dx, double dy, double dz, double r2, bool hit) {
+                const unsigned m = __ballot_sync(kFullS, hit);
+                if (m == 0u) return;
+                const int cnt = __popc(m), rank = __popc(m & lt_mask);
+                const int room = kListCap - fill;
+                if (hit && rank < room) {
+                    double* d = nbuf + (fill + rank) * 4;
+                    d[0] = dx; d[1] = dy; d[2] = dz; d[3] = r2;
+                }
+                if (cnt >= room) {
+                    __syncwarp();
+                    process(kListCap);
+                    if (hit && rank >= room) {
+                        double* d = nbuf + (rank - room) * 4;
+                        d[0] = dx; d[1] = dy; d[2] = dz; d[3] = r2;
+                    }
+                    fill = cnt - room;
+                } else {
+                    fill += cnt;
+                }
+            };
+            if (n_batches <= kBatchCap) {
+                // two batches in flight ahead of the one being tested
+                double x1 = 0.0, y1 = 0.0, z1 = 0.0, x2 = 0.0, y2 = 0.0, z2 = 0.0;
+                bool v1 = false, v2 = false;
+                auto fetch = [&](int b, double& x, double& y, double& z, bool& valid) {
+                    valid = false;
+                    if (b < n_batches) {
+                        const int2 q = bl_q[b];
+                        if (lane < q.y) {
+                            x = a.sx[q.x + lane]; y = a.sy[q.x + lane]; z = a.sz[q.x + lane];
+                            valid = true;
+                        }
+                    }
+                };
+                fetch(0, x1, y1, z1, v1);
+                fetch(1, x2, y2, z2, v2);
+                for (int b = 0; b < n_batches; ++b) {
+                    const int e = bl_e[b];
+                    const double vx = x1, vy = y1, vz = z1;
+                    const bool vv = v1;
+                    x1 = x2; y1 = y2; z1 = z2; v1 = v2;
+                    fetch(b + 2, x2, y2, z2, v2);
+                    const double dx = vx + tab_sh[e] - xc, dy = vy + tab_sh[kCellTab + e] - yc;
+                    const double dz = vz + tab_sh[2 * kCellTab + e] - zc;
+                    const double r2 = dx * dx + dy * dy + dz * dz;
+                    consume(dx, dy, dz, r2, vv && r2 <= a.r2max);
+                }
+            } else {
+                const int n_ent = min(kCellTab, n_ent_total - e0);
+                for (int t = 0; t < n_ent; ++t) {
+                    const int2 qr = tab_q[t];
+                    const int qb = qr.x, qe = qr.y;
+                    if (qb >= qe) continue;
+                    const double shx = tab_sh[t], shy = tab_sh[kCellTab + t];
+                    const double shz = tab_sh[2 * kCellTab + t];
+                    for (int q0 = qb; q0 < qe; q0 += 32) {
+                        const int q = q0 + lane;
+                        double dx = 0.0, dy = 0.0, dz = 0.0, r2 = 0.0;
+                        bool hit = false;
+                        if (q < qe) {
+                            dx = a.sx[q] + shx - xc; dy = a.sy[q] + shy - yc;
+                            dz = a.sz[q] + shz - zc;
+                            r2 = dx * dx + dy * dy + dz * dz;
+                            hit = r2 <= a.r2max;
+                        }
+                        consume(dx, dy, dz, r2, hit);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (fill > 0) process(fill);
+
+        // ---- registers -> G[z][lm][k] (shared: fused epilogue; global: split mode) ----
+        acc00 += __shfl_xor_sync(kFullS, acc00, 8);
+        acc00 += __shfl_xor_sync(kFullS, acc00, 16);
+        double* cz = SPLIT ? a.gscr + ((size_t)f * a.n_cent + ci) * c_doubles +
+                                 (size_t)z_sp * n_lm * n
+                           : rbuf;
+        if (kact) {
+            if (g == 0) cz[k] = acc00;  // lm = 0: S_0^0 = 1
+            store_item<S0>(a0, il[0], k, n, cz);
+            store_item<S1>(a1, il[1], k, n, cz);
+            store_item<S2>(a2, il[2], k, n, cz);
+            store_item<S3>(a3, il[3], k, n, cz);
+        }
+        __syncwarp();
+        if (!SPLIT) {
+            // the harmonics buffer is free now: G sits at its start, the mixed coefficients follow
+            mix_and_spectrum(a, rbuf, rbuf + ((c_doubles + 1) & ~1), bmat,
+                             a.out + (long long)ci * a.stride_i + (long long)f * a.stride_f, lane);
+        }
     }  // slot loop
+    }  // pass loop
+}
+
+// Split mode, second kernel: one warp per (centre, frame) reads the primitive sums from the
+// scratch (coalesced), mixes them into shared memory and writes the power spectrum.  HBM/L2-bound:
+// 8 S n_lm n bytes read + 8 C bytes written per centre.
+__global__ void __launch_bounds__(128)
+soap_spectrum_kernel(const SoapArgs a) {
+    extern __shared__ __align__(16) double smem_all[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* bmat_s = smem_all;
+    for (int i = threadIdx.x; i < a.bmat_smem_doubles; i += blockDim.x) bmat_s[i] = a.bmat[i];
+    __syncthreads();
+    const double* __restrict__ bmat = a.bmat_smem_doubles > 0 ? bmat_s : a.bmat;
+    const int c_doubles = a.plan.n_species * a.plan.n_lm * a.plan.n_max;
+    double* mix = smem_all + a.bmat_smem_doubles + (size_t)warp * ((c_doubles + 1) & ~1);
+    const int f = blockIdx.y;
+    const int ci = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (ci >= a.n_cent) return;
+    mix_and_spectrum(a, a.gscr + ((size_t)f * a.n_cent + ci) * c_doubles, mix, bmat,
+                     a.out + (long long)ci * a.stride_i + (long long)f * a.stride_f, lane);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -708,11 +753,16 @@ struct SoapLayout {
     long long total_cells = 0;
     bool periodic = false;
     size_t off_frames = 0, off_wpos = 0, off_cell_id = 0, off_cnt = 0, off_start = 0;
-    size_t off_sx = 0, off_sy = 0, off_sz = 0, off_sspec = 0, off_sid = 0, off_cmap = 0;
-    size_t off_tile = 0;
+    size_t off_sx = 0, off_sy = 0, off_sz = 0, off_sid = 0, off_cmap = 0;
+    size_t off_tile = 0, off_gscr = 0;
     size_t off_gamma = 0, off_bmat = 0, off_wlm = 0, off_lml = 0, off_decode = 0, off_exptab = 0;
     size_t bytes = 0;
 };
+
+// several (species, radial block) passes per centre -> accumulate kernel + spectrum kernel
+static bool soap_split(int n_species, int n_max) {
+    return n_species * ((n_max + kKBlock - 1) / kKBlock) > 1;
+}
 
 static double soap_radius(double r_cut) { return r_cut + std::sqrt(-2.0 * std::log(1e-3)); }
 
@@ -773,7 +823,8 @@ static int soap_layout(int n_frames, int n_atoms, int n_cent, int n_species, int
             }
         }
         fr.cell_base = (int)total;
-        total += cells;
+        fr.spec_stride = (int)cells;
+        total += cells * n_species;
         if (total >= 0x7fffffffLL)
             return set_error(DSG_ERR_OVERFLOW, "cell grid too large; use fewer frames per batch");
         if (frames) (*frames)[f] = fr;
@@ -796,7 +847,6 @@ static int soap_layout(int n_frames, int n_atoms, int n_cent, int n_species, int
     L->off_sx = take(8 * fa);
     L->off_sy = take(8 * fa);
     L->off_sz = take(8 * fa);
-    L->off_sspec = take(4 * fa);
     L->off_sid = take(4 * fa);
     L->off_cmap = take(4 * (size_t)n_atoms);
     L->off_tile = take(4 * (((size_t)total + kScanTileItems - 1) / kScanTileItems + 1));
@@ -806,6 +856,8 @@ static int soap_layout(int n_frames, int n_atoms, int n_cent, int n_species, int
     L->off_lml = take(4 * (size_t)n_lm);
     L->off_decode = take(4 * (size_t)n_feat);
     L->off_exptab = take(8 * (size_t)kExpTab);
+    if (soap_split(n_species, n_max))  // primitive sums between the two kernels
+        L->off_gscr = take(8 * (size_t)n_frames * n_cent * n_species * n_lm * n_max);
     L->bytes = o;
     return DSG_OK;
 }
@@ -824,9 +876,8 @@ static void make_plan(int n_species, int n_max, int l_max, int lt, int s0, SoapP
     while (p % 16 != 2) ++p;
     pl->row_stride = p;
     int rb = kChunk * p + s0 + 2;  // tail: item rows are read S_t wide past the last row
-    const int mixed = n_species * pl->n_lm * n_max;
-    // single pass: G and the mixed coefficients both live here; otherwise only the mixed ones
-    const int need = (n_species * pl->kblocks == 1) ? 2 * ((mixed + 1) & ~1) : mixed;
+    // fused epilogue: G and the mixed coefficients both live here (split mode: neither)
+    const int need = soap_split(n_species, n_max) ? 0 : 2 * ((pl->n_lm * n_max + 1) & ~1);
     if (rb < need) rb = need;
     rb = (rb + 1) & ~1;
     pl->rbuf_doubles = rb;
@@ -869,7 +920,6 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     double* sx = (double*)(ws + L.off_sx);
     double* sy = (double*)(ws + L.off_sy);
     double* sz = (double*)(ws + L.off_sz);
-    int* sspec = (int*)(ws + L.off_sspec);
     int* sid = (int*)(ws + L.off_sid);
     int* cmap = (int*)(ws + L.off_cmap);
     int* tile = (int*)(ws + L.off_tile);
@@ -943,12 +993,13 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     DSG_CUDA_CHECK(cudaMemsetAsync(cmap, 0xff, 4 * (size_t)n_atoms, st));
     soap_centre_map_kernel<<<(n_cent + 255) / 256, 256, 0, st>>>(d_centres, n_cent, cmap);
     DSG_LAUNCH_CHECK("soap_centre_map_kernel");
-    soap_bin_kernel<T><<<agrid, 256, 0, st>>>(d_pos, n_atoms, d_frames, wpos, cell_id, cnt);
+    soap_bin_kernel<T><<<agrid, 256, 0, st>>>(d_pos, d_species, n_atoms, d_frames, wpos, cell_id,
+                                              cnt);
     DSG_LAUNCH_CHECK("soap_bin_kernel");
     rc = run_scan(cnt, L.total_cells, 1, start, tile, nullptr, st);
     if (rc) return rc;
-    soap_scatter_kernel<<<agrid, 256, 0, st>>>(wpos, d_species, n_atoms, d_frames, cell_id, cnt,
-                                               start, sx, sy, sz, sspec, sid);
+    soap_scatter_kernel<<<agrid, 256, 0, st>>>(wpos, n_atoms, d_frames, cell_id, cnt, start, sx,
+                                               sy, sz, sid);
     DSG_LAUNCH_CHECK("soap_scatter_kernel");
 
     // ---- main kernel ----
@@ -956,7 +1007,6 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     a.sx = sx;
     a.sy = sy;
     a.sz = sz;
-    a.sspec = sspec;
     a.sid = sid;
     a.cell_start = start;
     a.frames = d_frames;
@@ -986,20 +1036,21 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     else if (l_max <= 10) { lt = 10; s0 = 21; }
     else { lt = 12; s0 = 25; }
     make_plan(n_species, n_max, l_max, lt, s0, &a.plan);
-    const bool single_pass = n_species * a.plan.kblocks == 1;
+    const bool split = soap_split(n_species, n_max);
+    a.gscr = split ? (double*)(ws + L.off_gscr) : nullptr;
     const size_t per_warp =
         8 * ((((size_t)kListCap * 4 + (size_t)kCellTab * 4 + (size_t)kBatchDoubles +
-               (size_t)a.plan.rbuf_doubles +
-               (single_pass ? 0 : (size_t)n_species * a.plan.n_lm * n_max)) + 1) & ~(size_t)1);
+               (size_t)a.plan.rbuf_doubles) + 1) & ~(size_t)1);
     // two warps per block keep several blocks resident per SM
-    const size_t shared_tables = 8 * ((size_t)kExpTab + (size_t)a.bmat_smem_doubles);
+    const size_t shared_tables = 8 * ((size_t)kExpTab + (split ? 0 : (size_t)a.bmat_smem_doubles));
     int warps = 2;
     if (per_warp * warps + shared_tables > 227 * 1024) warps = 1;
     const size_t smem = per_warp * warps + shared_tables;
-    if (smem > 227 * 1024)
+    const size_t mix_bytes = 8 * (((size_t)n_species * n_lm * n_max + 1) & ~(size_t)1);
+    if (smem > 227 * 1024 || (split && mix_bytes + 8 * (size_t)a.bmat_smem_doubles > 227 * 1024))
         return set_error(DSG_ERR_UNSUPPORTED,
                          "n_species*n_max*(l_max+1)^2 needs %zu bytes of shared memory per warp",
-                         per_warp);
+                         split ? mix_bytes : per_warp);
     // about 16 resident-block generations over the 148 SMs; runs of >= 1 slot per warp
     const int target_warps = 148 * 12 * 16;
     int spw = (int)(((long long)n_atoms * n_frames + target_warps - 1) / target_warps);
@@ -1010,10 +1061,17 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     dim3 grid((warps_needed + warps - 1) / warps, n_frames);
 #define DSG_SOAP_LAUNCH(LT, A, B, C, D)                                                          \
     do {                                                                                         \
-        DSG_CUDA_CHECK(cudaFuncSetAttribute(soap_kernel<LT, A, B, C, D>,                         \
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                            (int)smem));                                         \
-        soap_kernel<LT, A, B, C, D><<<grid, warps * 32, smem, st>>>(a);                          \
+        if (split) {                                                                             \
+            DSG_CUDA_CHECK(cudaFuncSetAttribute(soap_kernel<LT, A, B, C, D, true>,               \
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                                (int)smem));                                     \
+            soap_kernel<LT, A, B, C, D, true><<<grid, warps * 32, smem, st>>>(a);                \
+        } else {                                                                                 \
+            DSG_CUDA_CHECK(cudaFuncSetAttribute(soap_kernel<LT, A, B, C, D, false>,              \
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                                (int)smem));                                     \
+            soap_kernel<LT, A, B, C, D, false><<<grid, warps * 32, smem, st>>>(a);               \
+        }                                                                                        \
     } while (0)
     if (l_max <= 4) DSG_SOAP_LAUNCH(4, 9, 0, 0, 0);
     else if (l_max <= 6) DSG_SOAP_LAUNCH(6, 13, 5, 0, 0);
@@ -1022,6 +1080,17 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     else DSG_SOAP_LAUNCH(12, 25, 17, 9, 0);
 #undef DSG_SOAP_LAUNCH
     DSG_LAUNCH_CHECK("soap_kernel");
+    if (split) {
+        // spectrum kernel: as many warps per block as the mixed coefficients allow (<= 4)
+        int sw = 4;
+        while (sw > 1 && mix_bytes * sw + 8 * (size_t)a.bmat_smem_doubles > 100 * 1024) --sw;
+        const size_t ssm = mix_bytes * sw + 8 * (size_t)a.bmat_smem_doubles;
+        DSG_CUDA_CHECK(cudaFuncSetAttribute(soap_spectrum_kernel,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+        dim3 sgrid((n_cent + sw - 1) / sw, n_frames);
+        soap_spectrum_kernel<<<sgrid, sw * 32, ssm, st>>>(a);
+        DSG_LAUNCH_CHECK("soap_spectrum_kernel");
+    }
     return DSG_OK;
 }
 

@@ -86,7 +86,9 @@ def saponify_trajectory_device(
     centres_t = torch.as_tensor(centers_list, device=dev)
     n_all = len(universe.atoms)
     if batch_frames is None:
-        batch_frames = frames.pick_batch_frames(sel_ix.size, 80.0, 1, maximum=1024)
+        # workspace per atom-frame: sorted copies + (several species / n_max > 8) primitive sums
+        scratch = soap_basis.scratch_doubles(n_species, soapnmax, soaplmax) * 8.0
+        batch_frames = frames.pick_batch_frames(sel_ix.size, 80.0 + scratch, 1, maximum=1024)
     for fb in frames.iter_batches(universe, fr_idx, batch_frames):
         box = frames.soap_boxes(fb, bool(soap_respectpbc))
         pos = fb.select(sel_ix, n_all)
@@ -238,7 +240,8 @@ def timesoap_from_trajectory(
     centres_t = torch.as_tensor(centers_list, device=dev)
     n_all = len(universe.atoms)
     if batch_frames is None:
-        per_frame = max(1, n_cent) * n_feat * 8.0
+        scratch = soap_basis.scratch_doubles(n_species, soapnmax, soaplmax)
+        per_frame = max(1, n_cent) * (n_feat + scratch) * 8.0
         batch_frames = int(max(delay + 1, min(512, 16e9 // per_frame)))
     batch_frames = max(batch_frames, delay + 1)
     for fb in frames.iter_batches(universe, fr_idx, batch_frames, overlap=delay):

@@ -74,3 +74,11 @@ def _inv_sqrt_spd(s: np.ndarray) -> np.ndarray:
 def n_features(n_species: int, n_max: int, l_max: int) -> int:
     sn = n_species * n_max
     return sn * (sn + 1) // 2 * (l_max + 1)
+
+
+def scratch_doubles(n_species: int, n_max: int, l_max: int) -> int:
+    """Doubles of device scratch per centre-frame: with several species or n_max > 8 the SOAP
+    kernel keeps the primitive sums ``(S, (l+1)^2, n)`` in global memory between its two passes."""
+    if n_species * ((n_max + 7) // 8) <= 1:
+        return 0
+    return n_species * (l_max + 1) ** 2 * n_max
