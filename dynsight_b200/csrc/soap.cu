@@ -726,24 +726,110 @@ soap_kernel(const SoapArgs a) {
     }  // pass loop
 }
 
-// Split mode, second kernel: one warp per (centre, frame) reads the primitive sums from the
-// scratch (coalesced), mixes them into shared memory and writes the power spectrum.  HBM/L2-bound:
-// 8 S n_lm n bytes read + 8 C bytes written per centre.
+// Split mode, second kernel: one warp per (centre, frame), one angular momentum at a time.  The
+// S(2l+1) columns of G for that l are read from the scratch (one column per lane, coalesced),
+// mixed into shared memory, and the (species pair, n, n') outputs of that l are computed as 2x2
+// register tiles (two 128-bit shared loads per four FMAs).  HBM-bound: 8 S n_lm n bytes read +
+// 8 C bytes written per centre; only S(2 l_max+1) n doubles of shared memory per warp.
+struct SpecTask {
+    int code;   // zi | zj << 4 | na0 << 8 | nb0 << 16
+    int base;   // first feature of the species pair
+    int blk;    // features per l in that pair
+    int pad;
+};
+
 __global__ void __launch_bounds__(128)
-soap_spectrum_kernel(const SoapArgs a) {
+soap_spectrum_kernel(const SoapArgs a, const SpecTask* __restrict__ tasks, int n_tasks) {
     extern __shared__ __align__(16) double smem_all[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* bmat_s = smem_all;
     for (int i = threadIdx.x; i < a.bmat_smem_doubles; i += blockDim.x) bmat_s[i] = a.bmat[i];
     __syncthreads();
     const double* __restrict__ bmat = a.bmat_smem_doubles > 0 ? bmat_s : a.bmat;
-    const int c_doubles = a.plan.n_species * a.plan.n_lm * a.plan.n_max;
-    double* mix = smem_all + a.bmat_smem_doubles + (size_t)warp * ((c_doubles + 1) & ~1);
+    const SoapPlan& pl = a.plan;
+    const int n = pl.n_max, n_lm = pl.n_lm, l_max = pl.l_max, S = pl.n_species;
+    const int np_stride = (n + 1) & ~1;
+    double* mix = smem_all + a.bmat_smem_doubles + (size_t)warp * S * (2 * l_max + 1) * np_stride;
     const int f = blockIdx.y;
     const int ci = blockIdx.x * (blockDim.x >> 5) + warp;
     if (ci >= a.n_cent) return;
-    mix_and_spectrum(a, a.gscr + ((size_t)f * a.n_cent + ci) * c_doubles, mix, bmat,
-                     a.out + (long long)ci * a.stride_i + (long long)f * a.stride_f, lane);
+    const double* __restrict__ gsum = a.gscr + ((size_t)f * a.n_cent + ci) * S * n_lm * n;
+    double* __restrict__ out = a.out + (long long)ci * a.stride_i + (long long)f * a.stride_f;
+
+    for (int l = 0; l <= l_max; ++l) {
+        const int nm = 2 * l + 1, ncol = S * nm;
+        const double* __restrict__ bl = bmat + (size_t)l * n * n;
+        for (int col = lane; col < ncol; col += 32) {
+            const int z = col / nm, m = col - z * nm;
+            const double w = a.swlm[l * l + m];
+            const double* __restrict__ v = gsum + ((size_t)z * n_lm + l * l + m) * n;
+            double* __restrict__ o = mix + (size_t)col * np_stride;
+            if (n == 8) {
+                const double2* __restrict__ v2 = reinterpret_cast<const double2*>(v);
+                const double2 g0 = v2[0], g1 = v2[1], g2 = v2[2], g3 = v2[3];
+                const double2* __restrict__ b2 = reinterpret_cast<const double2*>(bl);
+#pragma unroll
+                for (int np = 0; np < 8; np += 2) {
+                    double r[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const double2 b0 = b2[(np + h) * 4], b1 = b2[(np + h) * 4 + 1];
+                        const double2 b3 = b2[(np + h) * 4 + 2], b4 = b2[(np + h) * 4 + 3];
+                        double sa = b0.x * g0.x, sb = b0.y * g0.y;
+                        sa = fma(b1.x, g1.x, sa); sb = fma(b1.y, g1.y, sb);
+                        sa = fma(b3.x, g2.x, sa); sb = fma(b3.y, g2.y, sb);
+                        sa = fma(b4.x, g3.x, sa); sb = fma(b4.y, g3.y, sb);
+                        r[h] = (sa + sb) * w;
+                    }
+                    reinterpret_cast<double2*>(o)[np >> 1] = make_double2(r[0], r[1]);
+                }
+            } else {
+                for (int np = 0; np < n; ++np) {
+                    const double* __restrict__ bm = bl + (size_t)np * n;
+                    double s0 = 0.0, s1 = 0.0;
+                    int k = 0;
+                    for (; k + 1 < n; k += 2) {
+                        s0 = fma(bm[k], v[k], s0);
+                        s1 = fma(bm[k + 1], v[k + 1], s1);
+                    }
+                    if (k < n) s0 = fma(bm[k], v[k], s0);
+                    o[np] = (s0 + s1) * w;
+                }
+                if (np_stride > n) o[n] = 0.0;
+            }
+        }
+        __syncwarp();
+        for (int t = lane; t < n_tasks; t += 32) {
+            const SpecTask tk = tasks[t];
+            const int zi = tk.code & 15, zj = (tk.code >> 4) & 15;
+            const int na0 = (tk.code >> 8) & 255, nb0 = (tk.code >> 16) & 255;
+            const double2* __restrict__ ca =
+                reinterpret_cast<const double2*>(mix + (size_t)zi * nm * np_stride + na0);
+            const double2* __restrict__ cb =
+                reinterpret_cast<const double2*>(mix + (size_t)zj * nm * np_stride + nb0);
+            double o00 = 0.0, o01 = 0.0, o10 = 0.0, o11 = 0.0;
+            const int step = np_stride >> 1;
+            for (int m = 0; m < nm; ++m) {
+                const double2 u = ca[m * step], v = cb[m * step];
+                o00 = fma(u.x, v.x, o00);
+                o01 = fma(u.x, v.y, o01);
+                o10 = fma(u.y, v.x, o10);
+                o11 = fma(u.y, v.y, o11);
+            }
+            double* __restrict__ ob = out + tk.base + (size_t)l * tk.blk;
+            const bool diag = zi == zj;
+            const double res[4] = {o00, o01, o10, o11};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int na = na0 + (q >> 1), nb = nb0 + (q & 1);
+                if (na < n && nb < n && (!diag || nb >= na)) {
+                    const int off = diag ? na * n - (na * (na - 1)) / 2 + nb - na : na * n + nb;
+                    ob[off] = res[q];
+                }
+            }
+        }
+        __syncwarp();
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -754,7 +840,8 @@ struct SoapLayout {
     bool periodic = false;
     size_t off_frames = 0, off_wpos = 0, off_cell_id = 0, off_cnt = 0, off_start = 0;
     size_t off_sx = 0, off_sy = 0, off_sz = 0, off_sid = 0, off_cmap = 0;
-    size_t off_tile = 0, off_gscr = 0;
+    size_t off_tile = 0, off_gscr = 0, off_tasks = 0;
+    int n_tasks = 0;
     size_t off_gamma = 0, off_bmat = 0, off_wlm = 0, off_lml = 0, off_decode = 0, off_exptab = 0;
     size_t bytes = 0;
 };
@@ -856,8 +943,13 @@ static int soap_layout(int n_frames, int n_atoms, int n_cent, int n_species, int
     L->off_lml = take(4 * (size_t)n_lm);
     L->off_decode = take(4 * (size_t)n_feat);
     L->off_exptab = take(8 * (size_t)kExpTab);
-    if (soap_split(n_species, n_max))  // primitive sums between the two kernels
+    if (soap_split(n_species, n_max)) {  // primitive sums between the two kernels
         L->off_gscr = take(8 * (size_t)n_frames * n_cent * n_species * n_lm * n_max);
+        const int tiles = (n_max + 1) / 2;
+        L->n_tasks = n_species * (tiles * (tiles + 1) / 2) +
+                     n_species * (n_species - 1) / 2 * tiles * tiles;
+        L->off_tasks = take(sizeof(SpecTask) * (size_t)L->n_tasks);
+    }
     L->bytes = o;
     return DSG_OK;
 }
@@ -1046,11 +1138,11 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     int warps = 2;
     if (per_warp * warps + shared_tables > 227 * 1024) warps = 1;
     const size_t smem = per_warp * warps + shared_tables;
-    const size_t mix_bytes = 8 * (((size_t)n_species * n_lm * n_max + 1) & ~(size_t)1);
-    if (smem > 227 * 1024 || (split && mix_bytes + 8 * (size_t)a.bmat_smem_doubles > 227 * 1024))
-        return set_error(DSG_ERR_UNSUPPORTED,
-                         "n_species*n_max*(l_max+1)^2 needs %zu bytes of shared memory per warp",
-                         split ? mix_bytes : per_warp);
+    // spectrum kernel: mixed coefficients of one l per warp
+    const size_t spec_bytes = 8 * (size_t)n_species * (2 * l_max + 1) * ((n_max + 1) & ~1);
+    if (smem > 227 * 1024 || (split && spec_bytes + 8 * (size_t)a.bmat_smem_doubles > 227 * 1024))
+        return set_error(DSG_ERR_UNSUPPORTED, "%zu bytes of shared memory per warp needed",
+                         split ? spec_bytes : per_warp);
     // about 16 resident-block generations over the 148 SMs; runs of >= 1 slot per warp
     const int target_warps = 148 * 12 * 16;
     int spw = (int)(((long long)n_atoms * n_frames + target_warps - 1) / target_warps);
@@ -1081,14 +1173,30 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
 #undef DSG_SOAP_LAUNCH
     DSG_LAUNCH_CHECK("soap_kernel");
     if (split) {
-        // spectrum kernel: as many warps per block as the mixed coefficients allow (<= 4)
-        int sw = 4;
-        while (sw > 1 && mix_bytes * sw + 8 * (size_t)a.bmat_smem_doubles > 100 * 1024) --sw;
-        const size_t ssm = mix_bytes * sw + 8 * (size_t)a.bmat_smem_doubles;
+        std::vector<SpecTask> tasks;
+        int base = 0;
+        const int tiles = (n_max + 1) / 2;
+        for (int zi = 0; zi < n_species; ++zi)
+            for (int zj = zi; zj < n_species; ++zj) {
+                const int blk = zi == zj ? n_max * (n_max + 1) / 2 : n_max * n_max;
+                for (int ta = 0; ta < tiles; ++ta)
+                    for (int tb = (zi == zj ? ta : 0); tb < tiles; ++tb)
+                        tasks.push_back({zi | (zj << 4) | ((2 * ta) << 8) | ((2 * tb) << 16), base,
+                                         blk, 0});
+                base += blk * (l_max + 1);
+            }
+        if ((int)tasks.size() != L.n_tasks || base != n_feat)
+            return set_error(DSG_ERR_INVALID_ARGUMENT, "spectrum task table mismatch");
+        SpecTask* d_tasks = (SpecTask*)(ws + L.off_tasks);
+        DSG_CUDA_CHECK(cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(SpecTask) * tasks.size(),
+                                       cudaMemcpyHostToDevice, st));
+        int sw = 4;  // warps per block, fewer if the coefficients of one l are large
+        while (sw > 1 && sw * spec_bytes + 8 * (size_t)a.bmat_smem_doubles > 227 * 1024) --sw;
+        const size_t ssm = sw * spec_bytes + 8 * (size_t)a.bmat_smem_doubles;
         DSG_CUDA_CHECK(cudaFuncSetAttribute(soap_spectrum_kernel,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
         dim3 sgrid((n_cent + sw - 1) / sw, n_frames);
-        soap_spectrum_kernel<<<sgrid, sw * 32, ssm, st>>>(a);
+        soap_spectrum_kernel<<<sgrid, sw * 32, ssm, st>>>(a, d_tasks, L.n_tasks);
         DSG_LAUNCH_CHECK("soap_spectrum_kernel");
     }
     return DSG_OK;
