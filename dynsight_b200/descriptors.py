@@ -69,7 +69,7 @@ def orientational_order_param(
     """
     pos = _all_positions(universe)
     batch = _device_csr(neigh_list_per_frame, pos.shape[1])
-    return engine.orientational_op_device(pos, batch, order).cpu().numpy()
+    return frames.to_host(engine.orientational_op_device(pos, batch, order))
 
 
 def compute_mean_alignment(
@@ -114,4 +114,6 @@ def velocity_alignment(
     else:
         vec = _all_positions(universe)
     batch = _device_csr(neigh_list_per_frame, vec.shape[1])
-    return engine.velocity_alignment_device(vec, batch, displacement=not has_vel).cpu().numpy()
+    return frames.to_host(
+        engine.velocity_alignment_device(vec, batch, displacement=not has_vel)
+    )

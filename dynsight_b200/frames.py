@@ -130,3 +130,23 @@ def pick_batch_frames(n_atoms: int, bytes_per_atom_frame: float, minimum: int,
     b = int(budget_bytes / max(1.0, n_atoms * bytes_per_atom_frame))
     b = min(b, maximum, max(1, (2**31 - 1) // max(1, n_atoms) - 1))
     return max(b, minimum)
+
+
+_PINNED_RESULT_LIMIT = 2 << 30  # bytes; larger results go through a pageable copy
+
+
+def to_host(t: torch.Tensor) -> np.ndarray:
+    """Device result -> numpy array.  Results up to 2 GiB land in page-locked memory from torch's
+    caching host allocator (DMA at link speed, no first-touch page faults on a fresh numpy buffer);
+    the array keeps the buffer alive and returns it to the cache when it is dropped."""
+    if t.device.type != "cuda":
+        return t.numpy()
+    if 0 < t.numel() * t.element_size() <= _PINNED_RESULT_LIMIT:
+        try:
+            host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        except RuntimeError:
+            return t.cpu().numpy()
+        host.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        return host.numpy()
+    return t.cpu().numpy()

@@ -82,10 +82,8 @@ def compute_lens(
     Raises:
         RuntimeError: "No valid pairs found." when the frame selection is shorter than ``delay``.
     """
-    return (
+    return frames.to_host(
         compute_lens_device(universe, r_cut, delay, centers, selection, trajslice, respect_pbc)
-        .cpu()
-        .numpy()
     )
 
 

@@ -115,12 +115,10 @@ def saponify_trajectory(
     Returns the SOAP spectra for all the particles and frames, shape
     (n_atoms, n_frames, n_components), float64 (DScribe's ordering: species pairs, l, n, n').
     """
-    return (
+    return frames.to_host(
         saponify_trajectory_device(
             universe, soaprcut, soapnmax, soaplmax, selection, soap_respectpbc, centers, trajslice
         )
-        .cpu()
-        .numpy()
     )
 
 
@@ -170,7 +168,7 @@ def normalize_soap(soap: NDArray[np.float64]) -> NDArray[np.float64]:
     arr = np.asarray(soap, dtype=np.float64)
     if arr.size == 0:
         return np.zeros(arr.shape)
-    return engine.normalize_soap_device(_to_device(arr)).cpu().numpy()
+    return frames.to_host(engine.normalize_soap_device(_to_device(arr)))
 
 
 def soap_distance(v_1: NDArray[np.float64], v_2: NDArray[np.float64]) -> NDArray[np.float64]:
@@ -201,7 +199,7 @@ def timesoap(soap: NDArray[np.float64], delay: int = 1) -> NDArray[np.float64]:
     value_error = "delay value outside bounds"
     if delay < 1 or delay >= soap.shape[1]:
         raise ValueError(value_error)
-    return engine.timesoap_device(_to_device(soap), delay).cpu().numpy()
+    return frames.to_host(engine.timesoap_device(_to_device(soap), delay))
 
 
 def timesoap_from_trajectory(
@@ -215,12 +213,14 @@ def timesoap_from_trajectory(
     centers: str = "all",
     trajslice: slice | None = None,
     batch_frames: int | None = None,
-) -> torch.Tensor:
+    as_numpy: bool = False,
+) -> torch.Tensor | NDArray[np.float64]:
     """timeSOAP straight from positions without materialising the (N, F, C) SOAP tensor.
 
     Extension for long trajectories (SURVEY.md section 5 "long-context"): SOAP is computed in
     frame batches that overlap by ``delay`` frames and each batch is reduced to timeSOAP on the
-    device.  Returns a CUDA float64 tensor (n_centers, n_frames - delay).
+    device.  Returns a CUDA float64 tensor (n_centers, n_frames - delay), or the same values as a
+    numpy array (like ``timesoap``) with ``as_numpy=True``.
     """
     if trajslice is None:
         trajslice = slice(None)
@@ -252,4 +252,4 @@ def timesoap_from_trajectory(
             n_species=n_species,
         )  # fmt: skip
         engine.timesoap_device(spectra, delay, out=out, col0=fb.seq0)
-    return out
+    return frames.to_host(out) if as_numpy else out

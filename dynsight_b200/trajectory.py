@@ -183,9 +183,9 @@ class Trj:
                 n_jobs=n_jobs,
             )
         if isinstance(neigcounts, _lens.NeighbourList):
-            from dynsight_b200 import engine
+            from dynsight_b200 import engine, frames
 
-            counts = engine.coordination_numbers(neigcounts.counts_device).cpu().numpy()
+            counts = frames.to_host(engine.coordination_numbers(neigcounts.counts_device))
         else:  # a plain list[list[AtomGroup]] handed in by the caller (trajectory.py:168-174)
             n_frames = len(neigcounts)
             n_atoms = len(neigcounts[0])

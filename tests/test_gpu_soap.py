@@ -104,6 +104,8 @@ def test_doctest_known_answers(xyz60):
         (200, 28.0, 4.5, 6, 3, 2, torch.float32),   # 2 species, odd l_max
         (150, 30.0, 5.5, 12, 2, 1, torch.float32),  # n_max > 8: two radial blocks
         (220, 33.0, 6.0, 3, 12, 2, torch.float32),  # l_max = 12
+        (180, 29.0, 5.0, 9, 4, 2, torch.float32),   # odd n_max > 8 with 2 species (split mode)
+        (120, 12.0, 4.0, 5, 6, 3, torch.float64),   # narrow box, 3 species
     ],
 )
 def test_random_boxes_vs_oracle(n_atoms, box_l, r_cut, n_max, l_max, n_species, dtype):
@@ -121,6 +123,16 @@ def test_random_boxes_vs_oracle(n_atoms, box_l, r_cut, n_max, l_max, n_species, 
         pos, zs[sp_idx], centres, np.tile(box, (2, 1)), r_cut, n_max, l_max
     )
     assert got.shape == want.shape
+    assert _rel_err(got, want) < REL
+
+
+def test_non_periodic_two_species_vs_oracle():
+    rng = np.random.default_rng(9)
+    pos = (rng.normal(size=(2, 400, 3)) * 8.0).astype(np.float32)
+    sp_idx = rng.integers(0, 2, 400)
+    centres = np.arange(0, 400, 13)
+    got = _soap_gpu(pos, sp_idx, centres, None, 5.0, 6, 7)
+    want = so.soap_trajectory(pos, np.array([6, 79])[sp_idx], centres, None, 5.0, 6, 7)
     assert _rel_err(got, want) < REL
 
 
