@@ -240,61 +240,31 @@ struct Acc {
     double v[N > 0 ? N : 1];
 };
 
-// exp(x) for x in [-690, 0]: 2^n * 2^(j/16) * e^u; 2^(j/16) from a shared-memory table, e^u by a
-// short Taylor polynomial.  Relative error < 1e-15 + the rounding of x*16*log2(e) (<= 1e-14 for
-// |x| < 100).  Branch-free: 13 fp64 ops.
+// exp(x) for x in [-690, 0], argument given pre-scaled: t = x * 16 log2(e).  2^n * 2^(j/16) * e^u
+// with 16 n + j = rint(t); 2^(j/16) from a shared-memory table, e^u by a degree-6 Taylor
+// polynomial in v = t - rint(t) (coefficients (ln2/16)^i / i! folded in; |u| <= ln2/32,
+// truncation 4.5e-16).  Relative error < 1e-15 + the rounding of t (<= 1e-14 for |x| < 100).
+// Branch-free, 11 fp64 operations.  16 entries * 8 bytes = one 128-byte row of shared memory:
+// every entry has its own bank pair, so the divergent table reads of a warp are conflict-free.
+// The caller guarantees t >= -690 * kExpScale (2^n stays normal): soap_layout rejects cutoffs
+// for which gamma * r^2 could exceed 690.
 constexpr int kExpTab = 16;
-#ifndef DSG_SOAP_EXP_TABLE
-#define DSG_SOAP_EXP_TABLE 1
-#endif
-#if DSG_SOAP_EXP_TABLE
-// 16 entries * 8 bytes = one 128-byte row of shared memory: every entry has its own bank pair, so
-// the divergent table reads of a warp are conflict-free.  |u| <= ln2/32, degree-6 Taylor
-// polynomial (truncation 4.5e-16).
-__device__ __forceinline__ double exp_neg(double x, const double* __restrict__ tab) {
-    const double t = fmax(x, -690.0) * 23.083120654223414;       // 16 * log2(e); keeps 2^n normal
+constexpr double kExpScale = 23.083120654223414;  // 16 * log2(e)
+__device__ __forceinline__ double exp_scaled(double t, const double* __restrict__ tab) {
     const double magic = 6755399441055744.0;                     // 1.5 * 2^52
     const double tn = t + magic;
     const int kq = __double2loint(tn);                           // 16 n + j
-    const double u = (t - (tn - magic)) * 0.04332169878499658;   // ln2 / 16
-    double p = 1.38888888888888888889e-03;                       // 1/6!
-    p = fma(p, u, 8.33333333333333333333e-03);
-    p = fma(p, u, 4.16666666666666666667e-02);
-    p = fma(p, u, 1.66666666666666666667e-01);
-    p = fma(p, u, 0.5);
-    p = fma(p, u, 1.0);
-    p = fma(p, u, 1.0);
+    const double v = t - (tn - magic);                           // [-1/2, 1/2]
+    double p = 9.18121957384443806176e-12;
+    p = fma(p, v, 1.27158719505581314889e-09);
+    p = fma(p, v, 1.46761003229194288311e-07);
+    p = fma(p, v, 1.35508077794974568162e-05);
+    p = fma(p, v, 9.38384792808987194639e-04);
+    p = fma(p, v, 4.33216987849965803892e-02);
+    p = fma(p, v, 1.0);
     const double r = tab[kq & (kExpTab - 1)] * p;
     return __hiloint2double(__double2hiint(r) + ((kq >> 4) << 20), __double2loint(r));
 }
-#else
-// table-free variant: 2^n * 2^f, f in [-1/2, 1/2], degree-12 Taylor polynomial of exp(f ln 2)
-// split into even and odd halves (two independent FMA chains).
-__device__ __forceinline__ double exp_neg(double x, const double* __restrict__) {
-    const double t = fmax(x, -690.0) * 1.4426950408889634074;
-    const double magic = 6755399441055744.0;
-    const double tn = t + magic;
-    const int n = __double2loint(tn);
-    const double f = t - (tn - magic);
-    const double u = f * 0.69314718055994530942;
-    const double u2 = u * u;
-    double pe = 2.08767569878680989792e-09;
-    pe = fma(pe, u2, 2.75573192239858906526e-07);
-    pe = fma(pe, u2, 2.48015873015873015873e-05);
-    pe = fma(pe, u2, 1.38888888888888888889e-03);
-    pe = fma(pe, u2, 4.16666666666666666667e-02);
-    pe = fma(pe, u2, 0.5);
-    pe = fma(pe, u2, 1.0);
-    double po = 2.50521083854417187751e-08;
-    po = fma(po, u2, 2.75573192239858906526e-06);
-    po = fma(po, u2, 1.98412698412698412698e-04);
-    po = fma(po, u2, 8.33333333333333333333e-03);
-    po = fma(po, u2, 1.66666666666666666667e-01);
-    po = fma(po, u2, 1.0);
-    const double p = fma(po, u, pe);
-    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
-}
-#endif
 
 // Phase B: un-normalised regular solid harmonics of one displacement, rows padded to even length:
 //   rt[l(l+1) + l + m] = S_l^m(z, r2) * A_m(x, y),   rt[l(l+1) + l - m] = S_l^m * B_m   (m > 0)
@@ -526,9 +496,9 @@ soap_kernel(const SoapArgs a) {
         double gam[kMaxItems];
 #pragma unroll
         for (int t = 0; t < kMaxItems; ++t)
-            gam[t] = (kact && il[t] >= 0) ? -a.gamma[il[t] * n + k] : 0.0;
+            gam[t] = (kact && il[t] >= 0) ? -a.gamma[il[t] * n + k] * kExpScale : 0.0;
         // l = 0: lane (jq, k) sums exp(-gamma_0k r^2) over the neighbours jj = jq (mod 4)
-        const double gam0 = kact ? -a.gamma[k] : 0.0;
+        const double gam0 = kact ? -a.gamma[k] * kExpScale : 0.0;
         double acc00 = 0.0;
         Acc<S0> a0;
         Acc<S1> a1;
@@ -555,15 +525,15 @@ soap_kernel(const SoapArgs a) {
                 for (int jj = 0; jj < nh; ++jj) {   // phase C
                     const double r2 = nbuf[(h0 + jj) * 4 + 3];
                     const double* __restrict__ rt = rbuf + jj * P;
-                    if (S0 > 0) accumulate<S0>(a0, exp_neg(gam[0] * r2, exp_tab), rt + ioff[0]);
-                    if (S1 > 0) accumulate<S1>(a1, exp_neg(gam[1] * r2, exp_tab), rt + ioff[1]);
-                    if (S2 > 0) accumulate<S2>(a2, exp_neg(gam[2] * r2, exp_tab), rt + ioff[2]);
-                    if (S3 > 0) accumulate<S3>(a3, exp_neg(gam[3] * r2, exp_tab), rt + ioff[3]);
+                    if (S0 > 0) accumulate<S0>(a0, exp_scaled(gam[0] * r2, exp_tab), rt + ioff[0]);
+                    if (S1 > 0) accumulate<S1>(a1, exp_scaled(gam[1] * r2, exp_tab), rt + ioff[1]);
+                    if (S2 > 0) accumulate<S2>(a2, exp_scaled(gam[2] * r2, exp_tab), rt + ioff[2]);
+                    if (S3 > 0) accumulate<S3>(a3, exp_scaled(gam[3] * r2, exp_tab), rt + ioff[3]);
                 }
 #pragma unroll
                 for (int q = 0; q < kChunk / 4; ++q) {   // l = 0, a quarter of the chunk per lane
                     const int jj = (lane >> 3) + 4 * q;
-                    if (jj < nh) acc00 += exp_neg(gam0 * nbuf[(h0 + jj) * 4 + 3], exp_tab);
+                    if (jj < nh) acc00 += exp_scaled(gam0 * nbuf[(h0 + jj) * 4 + 3], exp_tab);
                 }
                 __syncwarp();
             }
@@ -870,6 +840,10 @@ static int soap_layout(int n_frames, int n_atoms, int n_cent, int n_species, int
                          kMaxSpecies);
     if (!(r_cut > 1.0))
         return set_error(DSG_ERR_INVALID_ARGUMENT, "r_cut=%g must be > 1 (DScribe GTO basis)",
+                         r_cut);
+    // gamma < eta = 1/2, so gamma r^2 < R^2 / 2 must stay below 690 (see exp_scaled)
+    if (0.5 * soap_radius(r_cut) * soap_radius(r_cut) > 690.0)
+        return set_error(DSG_ERR_UNSUPPORTED, "r_cut=%g: search radius above 37 A is unsupported",
                          r_cut);
     if ((long long)n_frames * n_atoms >= 0x7fffffffLL)
         return set_error(DSG_ERR_OVERFLOW, "n_frames*n_atoms must stay below 2^31 per batch");
