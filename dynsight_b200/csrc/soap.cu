@@ -92,6 +92,7 @@ struct SoapArgs {
     const double* bmat;     // (L+1, n, n)  beta * prefactor
     const double* exp_tab;  // (64) 2^(j/64)
     int bmat_smem_doubles;  // size of bmat if it is staged in shared memory, else 0
+    int epi_smem_doubles;   // fused epilogue tables (swlm, lm_l, decode) in shared memory
     const double* swlm;     // (n_lm)  sqrt of the m-contraction weights
     const int* lm_l;        // (n_lm) -> l
     const int* decode;      // (n_feat)
@@ -339,6 +340,9 @@ __device__ __forceinline__ void store_item(const Acc<S>& a, int l, int k, int n,
 __device__ __forceinline__ void mix_and_spectrum(const SoapArgs& a, const double* __restrict__ gsum,
                                                  double* __restrict__ mix,
                                                  const double* __restrict__ bmat,
+                                                 const double* __restrict__ swlm,
+                                                 const unsigned char* __restrict__ lm_l,
+                                                 const unsigned short* __restrict__ decode,
                                                  double* __restrict__ out, int lane) {
     const SoapPlan& pl = a.plan;
     const int n = pl.n_max, n_lm = pl.n_lm;
@@ -347,8 +351,8 @@ __device__ __forceinline__ void mix_and_spectrum(const SoapArgs& a, const double
         // one column (z, lm) per lane: G[0..8) in registers, 8x8 matrix rows as 128-bit broadcasts
         for (int col = lane; col < pl.n_species * n_lm; col += 32) {
             const int lm = col % n_lm;
-            const int l = a.lm_l[lm];
-            const double w = a.swlm[lm];
+            const int l = lm_l[lm];
+            const double w = swlm[lm];
             const double2* __restrict__ v2 = reinterpret_cast<const double2*>(gsum + (size_t)col * 8);
             const double2 g0 = v2[0], g1 = v2[1], g2 = v2[2], g3 = v2[3];
             const double2* __restrict__ b2 = reinterpret_cast<const double2*>(bmat + (size_t)l * 64);
@@ -374,7 +378,7 @@ __device__ __forceinline__ void mix_and_spectrum(const SoapArgs& a, const double
         int lm = col % n_lm;
         const int dcol = 32 / n, dnp = 32 - dcol * n;
         for (int idx = lane; idx < n_out; idx += 32) {
-            const int l = a.lm_l[lm];
+            const int l = lm_l[lm];
             const double* __restrict__ v = gsum + (size_t)col * n;
             const double* __restrict__ bm = bmat + ((size_t)l * n + np) * n;
             double s0 = 0.0, s1 = 0.0;
@@ -384,7 +388,7 @@ __device__ __forceinline__ void mix_and_spectrum(const SoapArgs& a, const double
                 s1 = fma(bm[k + 1], v[k + 1], s1);
             }
             if (k < n) s0 = fma(bm[k], v[k], s0);
-            mix[idx] = (s0 + s1) * a.swlm[lm];
+            mix[idx] = (s0 + s1) * swlm[lm];
             col += dcol;
             lm += dcol;
             np += dnp;
@@ -395,11 +399,10 @@ __device__ __forceinline__ void mix_and_spectrum(const SoapArgs& a, const double
     __syncwarp();
 
     for (int c = lane; c < pl.n_feat; c += 32) {
-        const int code = a.decode[c];
-        const int zi = code & 15, zj = (code >> 4) & 15, l = (code >> 8) & 15;
-        const int na = (code >> 12) & 31, nb = (code >> 17) & 31;
-        const double* __restrict__ ca = mix + ((size_t)zi * n_lm + l * l) * n + na;
-        const double* __restrict__ cb = mix + ((size_t)zj * n_lm + l * l) * n + nb;
+        const int code = decode[c];   // single species: l | na << 4 | nb << 9
+        const int l = code & 15, na = (code >> 4) & 31, nb = (code >> 9) & 31;
+        const double* __restrict__ ca = mix + (size_t)(l * l) * n + na;
+        const double* __restrict__ cb = mix + (size_t)(l * l) * n + nb;
         // 2l+1 terms: one leading term, then pairs on two independent chains
         double s0 = ca[0] * cb[0], s1 = 0.0;
         for (int mi = 1; mi < 2 * l + 1; mi += 2) {
@@ -428,11 +431,28 @@ soap_kernel(const SoapArgs a) {
     double* exp_tab = smem_all;
     double* bmat_s = smem_all + kExpTab;
     const int bmat_stage = SPLIT ? 0 : a.bmat_smem_doubles;
+    // fused epilogue: m-weights, lm -> l and the feature decode table also sit in shared memory
+    // (their global loads were exposed latency in every centre's epilogue)
+    const int epi_stage = SPLIT ? 0 : a.epi_smem_doubles;
+    double* swlm_s = bmat_s + bmat_stage;
+    unsigned short* decode_s = reinterpret_cast<unsigned short*>(swlm_s + a.plan.n_lm);
+    unsigned char* lm_l_s = reinterpret_cast<unsigned char*>(decode_s + a.plan.n_feat);
     for (int i = threadIdx.x; i < kExpTab; i += blockDim.x) exp_tab[i] = a.exp_tab[i];
     for (int i = threadIdx.x; i < bmat_stage; i += blockDim.x) bmat_s[i] = a.bmat[i];
+    if (!SPLIT) {
+        for (int i = threadIdx.x; i < a.plan.n_lm; i += blockDim.x) {
+            swlm_s[i] = a.swlm[i];
+            lm_l_s[i] = (unsigned char)a.lm_l[i];
+        }
+        for (int i = threadIdx.x; i < a.plan.n_feat; i += blockDim.x) {
+            const int code = a.decode[i];   // zi = zj = 0 in the fused (single-species) kernel
+            decode_s[i] = (unsigned short)(((code >> 8) & 15) | (((code >> 12) & 31) << 4) |
+                                           (((code >> 17) & 31) << 9));
+        }
+    }
     __syncthreads();
     const double* __restrict__ bmat = bmat_stage > 0 ? bmat_s : a.bmat;
-    double* smem = smem_all + kExpTab + bmat_stage;
+    double* smem = smem_all + kExpTab + bmat_stage + epi_stage;
     const int f = blockIdx.y;
     // each warp walks a run of consecutive slots of the frame's (species, cell)-sorted order:
     // consecutive centres share their candidate cells (L1 reuse, cached cell table) and the
@@ -689,7 +709,8 @@ soap_kernel(const SoapArgs a) {
         __syncwarp();
         if (!SPLIT) {
             // the harmonics buffer is free now: G sits at its start, the mixed coefficients follow
-            mix_and_spectrum(a, rbuf, rbuf + ((c_doubles + 1) & ~1), bmat,
+            mix_and_spectrum(a, rbuf, rbuf + ((c_doubles + 1) & ~1), bmat, swlm_s, lm_l_s,
+                             decode_s,
                              a.out + (long long)ci * a.stride_i + (long long)f * a.stride_f, lane);
         }
     }  // slot loop
@@ -1108,7 +1129,11 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
         8 * ((((size_t)kListCap * 4 + (size_t)kCellTab * 4 + (size_t)kBatchDoubles +
                (size_t)a.plan.rbuf_doubles) + 1) & ~(size_t)1);
     // two warps per block keep several blocks resident per SM
-    const size_t shared_tables = 8 * ((size_t)kExpTab + (split ? 0 : (size_t)a.bmat_smem_doubles));
+    // swlm (n_lm doubles) + decode (n_feat u16) + lm_l (n_lm bytes), rounded to 16 bytes
+    a.epi_smem_doubles = split ? 0 : (int)((n_lm + (2 * n_feat + n_lm + 7) / 8 + 1) & ~1);
+    const size_t shared_tables =
+        8 * ((size_t)kExpTab +
+             (split ? 0 : (size_t)a.bmat_smem_doubles + (size_t)a.epi_smem_doubles));
     int warps = 2;
     if (per_warp * warps + shared_tables > 227 * 1024) warps = 1;
     const size_t smem = per_warp * warps + shared_tables;
