@@ -733,9 +733,9 @@ cell_scatter_local_kernel(const T* __restrict__ pos, int n_atoms,
 // reserves space for its 32 rows with ONE atomic and copies them out coalesced.  ~4x fewer issued
 // instructions per centre than one warp per cell when cells hold 2..5 atoms.
 constexpr int kTpcThreads = 128;
-constexpr int kTpcHitCap = 32;
 
-template <typename T>
+// kTpcHitCap = rows that fit the staging tile (32 or 64 hits per centre)
+template <typename T, int kTpcHitCap>
 __global__ void __launch_bounds__(kTpcThreads)
 neigh_rows_thread_kernel(const RowsArgs a, const unsigned* __restrict__ cent_slot_cell) {
     __shared__ int stage[kTpcHitCap][kTpcThreads];
@@ -1173,12 +1173,15 @@ static int neigh_rows_impl(const void* d_pos_env, const void* d_pos_cent, int n_
         if (k_est > k_max) k_max = k_est;
     }
     // sparse cells (few candidates per centre): one thread per centre issues ~4x fewer instructions
-    const bool use_thread_kernel =
-        !(kernel_choice & 1) && !any_rint && packable && cand_sum / n_frames <= 200.0 &&
-        k_max + 6.0 * std::sqrt(k_max) <= (double)kTpcHitCap;  // rows must fit the staging tile
+    const double k_hi = k_max + 6.0 * std::sqrt(k_max);  // rows must fit the staging tile
+    const bool use_thread_kernel = !(kernel_choice & 1) && !any_rint && packable &&
+                                   cand_sum / n_frames <= 200.0 && k_hi <= 64.0;
     if (use_thread_kernel) {
         dim3 tgrid((n_cent + kTpcThreads - 1) / kTpcThreads, n_frames);
-        neigh_rows_thread_kernel<T><<<tgrid, kTpcThreads, 0, st>>>(a, slot_cell_c);
+        if (k_hi <= 32.0)
+            neigh_rows_thread_kernel<T, 32><<<tgrid, kTpcThreads, 0, st>>>(a, slot_cell_c);
+        else
+            neigh_rows_thread_kernel<T, 64><<<tgrid, kTpcThreads, 0, st>>>(a, slot_cell_c);
     } else if (any_rint) neigh_rows_kernel<T, true><<<grid, kWarpsPerBlock * 32, 0, st>>>(a);
     else neigh_rows_kernel<T, false><<<grid, kWarpsPerBlock * 32, 0, st>>>(a);
     DSG_LAUNCH_CHECK("neigh_rows_kernel");

@@ -98,7 +98,8 @@ int dsg_neigh_fill(const void* d_pos_env, const void* d_pos_cent, int pos_dtype,
  * (status[1] = number of regions actually used, a power of two <= 256).
  * respect_pbc: bit 0 = apply the minimum image; bit 1 = force the warp-per-cell kernel.  Without
  * bit 1 sparse grids use one thread per centre; status[0] == 2 then means that some row exceeded
- * that kernel's 32-entry staging tile and the call must be repeated with bit 1 set. */
+ * that kernel's staging tile (32 or 64 entries, chosen from the density) and the call must be
+ * repeated with bit 1 set. */
 int dsg_neigh_rows(const void* d_pos_env, const void* d_pos_cent, int pos_dtype, int n_frames,
                    int n_env, int n_cent, const double* h_box, double r_cut, int respect_pbc,
                    void* d_workspace, size_t workspace_bytes, int32_t* d_counts,
