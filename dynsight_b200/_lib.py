@@ -83,6 +83,20 @@ SIGNATURES: dict[str, tuple] = {
         [_c_ptr, _c_int, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_int, _c_ptr, _c_dbl, _c_int,
          _c_int, _c_ptr, _c_ptr, _c_ptr, _c_size, _c_ptr, _c_i64, _c_i64, _c_ptr],
     ),
+    "dsg_wrap_positions": (_c_int, [_c_ptr, _c_int, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr]),
+    "dsg_spatial_average_rows": (
+        _c_int,
+        [_c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_ptr, _c_i64, _c_i64, _c_ptr, _c_i64,
+         _c_i64, _c_ptr],
+    ),
+    "dsg_xtc_index": (
+        _c_int,
+        [ctypes.c_char_p, ctypes.POINTER(_c_i64), ctypes.POINTER(ctypes.c_int32), _c_ptr, _c_i64],
+    ),
+    "dsg_xtc_read": (
+        _c_int,
+        [ctypes.c_char_p, _c_ptr, _c_i64, ctypes.c_int32, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_int],
+    ),
 }  # fmt: skip
 
 _LIB: ctypes.CDLL | None = None

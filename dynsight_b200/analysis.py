@@ -1,0 +1,97 @@
+"""Drop-in for the pieces of ``dynsight.analysis`` that sit right after the descriptor hot path.
+
+* :func:`spatialaverage` -- ``dynsight.analysis.spatialaverage``
+  (``_internal/analysis/spatial_average.py:66-211``): neighbour search + mean over each particle's
+  neighbourhood, on the device.
+* :func:`self_time_correlation` -- ``dynsight.analysis.self_time_correlation``
+  (``_internal/analysis/time_correlations.py:13-92``), SURVEY.md section 8f row 4.
+"""
+
+from __future__ import annotations
+
+from typing import TYPE_CHECKING, Any
+
+import numpy as np
+import torch
+
+from dynsight_b200 import engine, frames
+
+if TYPE_CHECKING:
+    from numpy.typing import NDArray
+
+_SCALAR_NDIM = 2
+_VECTOR_NDIM = 3
+
+
+def spatialaverage_device(
+    universe: Any,
+    descriptor_array: NDArray[np.float64] | torch.Tensor,
+    selection: str,
+    r_cut: float,
+    trajslice: slice | None = None,
+    batch_frames: int | None = None,
+) -> torch.Tensor:
+    """:func:`spatialaverage` returning a CUDA tensor (no device -> host copy)."""
+    sel = universe.select_atoms(selection)
+    sel_ix = np.asarray(sel.indices)
+    if descriptor_array.ndim not in (_SCALAR_NDIM, _VECTOR_NDIM):
+        msg = "descriptor_array must have ndim == 2 or ndim == 3."
+        raise ValueError(msg)
+    fr_idx = frames.frame_sequence(universe.trajectory.n_frames, trajslice)
+    dev = frames.device()
+    values = torch.as_tensor(descriptor_array).to(device=dev, dtype=torch.float64).contiguous()
+    out = torch.zeros_like(values)  # frames beyond the slice stay zero (np.zeros in the reference)
+    n_all = len(universe.atoms)
+    if values.shape[0] != sel_ix.size or values.shape[1] < len(fr_idx):
+        msg = (
+            f"descriptor_array has shape {tuple(values.shape)}; the selection has {sel_ix.size} "
+            f"atoms and the slice {len(fr_idx)} frames"
+        )
+        raise IndexError(msg)
+    if batch_frames is None:
+        batch_frames = frames.pick_batch_frames(sel_ix.size, 400.0, 1)
+    for fb in frames.iter_batches(universe, fr_idx, batch_frames):
+        if fb.dims is None:
+            msg = "spatialaverage needs a simulation box (ts.dimensions is None)"
+            raise ValueError(msg)
+        if not np.allclose(fb.dims[:, 3:], 90.0, atol=1e-4):
+            msg = "dynsight_b200 spatialaverage supports orthorhombic boxes only"
+            raise NotImplementedError(msg)
+        box = np.ascontiguousarray(fb.dims[:, :3].astype(np.float64))
+        pos = engine.wrap_positions(fb.select(sel_ix, n_all), box)  # FastNS bins wrapped positions
+        capacity = None
+        force_warp = False
+        while True:
+            nr = engine.neighbor_rows(pos, box, float(r_cut), None, True, capacity, force_warp,
+                                      inclusive_cutoff=True)  # fmt: skip
+            engine.spatial_average_rows(nr, values, out, frame0=fb.seq0)
+            if not nr.overflowed():
+                break
+            if nr.needs_warp_kernel():
+                force_warp = True
+            else:
+                capacity = int(nr.needed_capacity() * 1.1) + 2048 * 256
+    return out
+
+
+def spatialaverage(
+    universe: Any,
+    descriptor_array: NDArray[np.float64],
+    selection: str,
+    r_cut: float,
+    trajslice: slice | None = None,
+    n_jobs: int = 1,  # noqa: ARG001  (kept for signature parity; the GPU path ignores it)
+) -> NDArray[np.float64]:
+    """Compute spatially averaged descriptor values over neighboring particles.
+
+    For every particle of ``selection`` and every frame of ``trajslice`` the descriptor is averaged
+    over the particle itself and the particles within ``r_cut`` (periodic minimum image, pairs at
+    exactly ``r_cut`` included like MDAnalysis' FastNS).  ``descriptor_array`` has shape
+    ``(n_atoms, n_frames)`` or ``(n_atoms, n_frames, n_features)``; the result has the same shape.
+
+    Raises:
+        ValueError: if ``descriptor_array`` has neither 2 nor 3 dimensions.
+    """
+    return frames.to_host(
+        spatialaverage_device(universe, descriptor_array, selection, r_cut, trajslice)
+    )

@@ -9,7 +9,8 @@ from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
 CSRC = _PKG / "csrc"
-SOURCES = ["core.cu", "neighbors.cu", "lens.cu", "descriptors.cu", "timesoap.cu", "soap.cu"]
+SOURCES = ["core.cu", "neighbors.cu", "lens.cu", "descriptors.cu", "timesoap.cu", "soap.cu",
+           "spatial.cu", "xtc.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -21,7 +22,7 @@ NVCC_FLAGS = [
 def needs_build(out: Path) -> bool:
     if not out.exists():
         return True
-    newest = max(p.stat().st_mtime for p in [*CSRC.glob("*.cu"), *CSRC.glob("*.cuh"),
+    newest = max(p.stat().st_mtime for p in [*CSRC.glob("*.cu"), *CSRC.glob("*.cuh"), *CSRC.glob("*.cpp"),
                                              _PKG.parent / "include" / "dynsight_b200.h"])
     return out.stat().st_mtime < newest
 

@@ -17,6 +17,7 @@
 // a rigorous guard band around (r_cut-1e-6)^2 (frame_finalize computes the band from the
 // coordinate magnitudes); inside the band the reference's float64 expression is evaluated.
 #include <climits>
+#include <cmath>
 #include <vector>
 
 #include "common.cuh"
@@ -1108,8 +1109,12 @@ static int neigh_rows_impl(const void* d_pos_env, const void* d_pos_cent, int n_
     int* start_c = (int*)(ws + L.off_start_c);
     float4* sorted_c = (float4*)(ws + L.off_sorted_c);
     int* tile_tmp = (int*)(ws + L.off_tile_tmp);
-    const double rc_eff = r_cut - 1e-6;  // lens.py:78
-    const double r2 = rc_eff * rc_eff;
+    // lens.py:78 "dr2 < (r_cut - 1e-6)^2"; the inclusive mode (bit 1 of kernel_choice) is the
+    // FastNS rule "dr2 <= r_cut^2" of analysis/spatial_average.py:39-40, kept as a strict test
+    // against the next float64 above r_cut^2
+    const double rc_eff = r_cut - 1e-6;
+    const double r2 = (kernel_choice & 2) ? std::nextafter(r_cut * r_cut, INFINITY)
+                                          : rc_eff * rc_eff;
 
     DSG_CUDA_CHECK(cudaMemcpyAsync(d_fp, fps.data(), sizeof(FrameParams) * n_frames,
                                    cudaMemcpyHostToDevice, st));

@@ -184,8 +184,12 @@ def neighbor_rows(
     respect_pbc: bool = True,
     capacity: int | None = None,
     force_warp_kernel: bool = False,
+    inclusive_cutoff: bool = False,
 ) -> NeighborRows:
     """Single-traversal neighbour rows (same membership as :func:`neighbor_lists`, rows unsorted).
+
+    ``inclusive_cutoff`` switches the membership rule from the numba kernels'
+    ``dr2 < (r_cut - 1e-6)**2`` to FastNS's ``dr2 <= r_cut**2`` (spatial average).
 
     The library picks one thread per centre for sparse cells and one warp per cell otherwise;
     ``force_warp_kernel`` disables the former.
@@ -225,7 +229,8 @@ def neighbor_rows(
         lib.dsg_neigh_rows(
             pos_env.data_ptr(), pos_cent.data_ptr() if pos_cent is not None else None, code,
             n_frames, n_env, n_cent, h_box.ctypes.data, float(r_cut),
-            int(bool(respect_pbc)) | (2 if force_warp_kernel else 0),
+            int(bool(respect_pbc)) | (2 if force_warp_kernel else 0)
+            | (4 if inclusive_cutoff else 0),
             workspace.data_ptr(), ws_bytes.value, counts.data_ptr(), row_start.data_ptr(),
             rows.data_ptr(), capacity, status.data_ptr(), _stream_ptr(),
         )
@@ -277,6 +282,52 @@ def lens_from_positions(
             force_warp = True  # rows longer than the thread kernel's tile: one warp per cell
         else:
             capacity = int(nr.needed_capacity() * 1.1) + _ROW_PARTS * 2048
+
+
+def wrap_positions(pos: torch.Tensor, box: np.ndarray | torch.Tensor) -> torch.Tensor:
+    """Positions (F, N, 3) folded into ``[0, box)`` per frame, in the input precision."""
+    lib = _lib.load()
+    _require_cuda(pos, "pos")
+    n_frames, n_atoms, _ = pos.shape
+    h_box = _host_box(box, n_frames)
+    d_box = torch.as_tensor(h_box, device=pos.device)
+    out = torch.empty_like(pos)
+    _lib.check(
+        lib.dsg_wrap_positions(
+            pos.data_ptr(), _dtype_code(pos), n_frames, n_atoms, d_box.data_ptr(), out.data_ptr(),
+            _stream_ptr(),
+        )
+    )
+    return out
+
+
+def spatial_average_rows(
+    nr: NeighborRows, values: torch.Tensor, out: torch.Tensor, frame0: int = 0
+) -> torch.Tensor:
+    """Mean of ``values`` over every particle's neighbours and itself for the frames of ``nr``.
+
+    ``values`` / ``out``: (N, F_total) or (N, F_total, C) float64 CUDA tensors (components
+    contiguous); the batch covers the columns ``frame0 .. frame0 + nr.n_frames``.
+    """
+    lib = _lib.load()
+    _require_cuda(values, "values")
+    if values.dtype != torch.float64 or out.dtype != torch.float64:
+        msg = "values and out must be float64"
+        raise TypeError(msg)
+    n_comp = 1 if values.ndim == 2 else values.shape[2]  # noqa: PLR2004
+    if values.ndim == 3 and (values.stride(2) != 1 or out.stride(2) != 1):  # noqa: PLR2004
+        msg = "components must be contiguous"
+        raise ValueError(msg)
+    v = values[:, frame0:]
+    o = out[:, frame0:]
+    _lib.check(
+        lib.dsg_spatial_average_rows(
+            nr.counts.data_ptr(), nr.row_start.data_ptr(), nr.rows.data_ptr(), nr.n_frames,
+            nr.n_cent, int(n_comp), v.data_ptr(), v.stride(0), v.stride(1), o.data_ptr(),
+            o.stride(0), o.stride(1), _stream_ptr(),
+        )
+    )  # fmt: skip
+    return out
 
 
 def lens_pairs(

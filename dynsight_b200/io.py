@@ -4,9 +4,10 @@ They produce exactly what the hot path reads from an ``MDAnalysis.Universe`` (SU
 8b): float32 positions in angstrom ``(F, N, 3)``, per-frame ``dimensions`` ``[lx, ly, lz, 90, 90,
 90]`` float32 (or ``None``), atom names / types / 1-based ids.
 
-Formats: GROMACS ``.gro`` topology, *uncompressed* ``.xtc`` (what GROMACS writes when
-``natoms <= 9`` -- the reference's ``tests/systems/balls_7_nvt.xtc``), and ``.xyz``.
-Compressed XTC is out of scope for this round.
+Formats: GROMACS ``.gro`` topology, ``.xtc`` (compressed frames are decoded by the native
+multi-threaded reader in ``csrc/xtc.cpp`` through the C ABI; ``read_xtc_uncompressed`` is a pure
+numpy reader for the ``natoms <= 9`` layout of the reference's ``tests/systems/balls_7_nvt.xtc``),
+and ``.xyz``.
 """
 
 from __future__ import annotations
@@ -100,6 +101,51 @@ def read_xtc_uncompressed(path: str | Path) -> tuple[np.ndarray, np.ndarray]:
     dims[:, 2] = box[:, 2, 2] * np.float32(10.0)
     dims[:, 3:] = 90.0
     return np.ascontiguousarray(pos), dims
+
+
+def triclinic_dimensions(box: np.ndarray) -> np.ndarray:
+    """Box vectors (F, 3, 3) float32 -> ``[lx, ly, lz, alpha, beta, gamma]`` (F, 6) float32, the
+    way MDAnalysis' ``triclinic_box`` reports them (lengths of the vectors, angles in degrees;
+    an all-zero box stays all-zero)."""
+    box = np.asarray(box, dtype=np.float32)
+    x, y, z = box[:, 0], box[:, 1], box[:, 2]
+    lx = np.linalg.norm(x, axis=1)
+    ly = np.linalg.norm(y, axis=1)
+    lz = np.linalg.norm(z, axis=1)
+    dims = np.zeros((box.shape[0], 6), dtype=np.float32)
+    ok = (lx > 0) & (ly > 0) & (lz > 0)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        alpha = np.rad2deg(np.arccos(np.einsum("ij,ij->i", y, z) / (ly * lz)))
+        beta = np.rad2deg(np.arccos(np.einsum("ij,ij->i", x, z) / (lx * lz)))
+        gamma = np.rad2deg(np.arccos(np.einsum("ij,ij->i", x, y) / (lx * ly)))
+    dims[ok, 0], dims[ok, 1], dims[ok, 2] = lx[ok], ly[ok], lz[ok]
+    dims[ok, 3], dims[ok, 4], dims[ok, 5] = alpha[ok], beta[ok], gamma[ok]
+    return dims
+
+
+def read_xtc(path: str | Path, n_threads: int = 0) -> tuple[np.ndarray, np.ndarray]:
+    """Read any XTC trajectory (compressed or not) with the native reader (``dsg_xtc_read``).
+
+    Returns ``(positions (F,N,3) float32 angstrom, dimensions (F,6) float32)`` -- the arrays an
+    ``MDAnalysis.Universe`` built from the same file holds (``trajectory.py:68-79``).
+    """
+    import ctypes
+
+    from dynsight_b200 import _lib
+
+    lib = _lib.load()
+    cpath = str(path).encode()
+    n_frames = ctypes.c_int64(0)
+    n_atoms = ctypes.c_int32(0)
+    _lib.check(lib.dsg_xtc_index(cpath, ctypes.byref(n_frames), ctypes.byref(n_atoms), None, 0))
+    offsets = np.empty(n_frames.value, dtype=np.int64)
+    _lib.check(lib.dsg_xtc_index(cpath, ctypes.byref(n_frames), ctypes.byref(n_atoms),
+                                 offsets.ctypes.data, offsets.size))  # fmt: skip
+    pos = np.empty((n_frames.value, n_atoms.value, 3), dtype=np.float32)
+    box = np.empty((n_frames.value, 9), dtype=np.float32)
+    _lib.check(lib.dsg_xtc_read(cpath, offsets.ctypes.data, n_frames.value, n_atoms.value,
+                                pos.ctypes.data, box.ctypes.data, None, None, int(n_threads)))  # fmt: skip
+    return pos, triclinic_dimensions(box.reshape(-1, 3, 3))
 
 
 def read_xyz(path: str | Path) -> tuple[Topology, np.ndarray]:

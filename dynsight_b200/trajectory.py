@@ -78,6 +78,31 @@ class Insight:
         logger.log(f"Insight loaded from {file_path}, dataset from {dataset_path}.")
         return cls(dataset=dataset, meta=data.get("meta", {}))
 
+    def spatial_average(
+        self,
+        trj: Trj,
+        r_cut: float,
+        selection: str = "all",
+        n_jobs: int = 1,
+    ) -> Insight:
+        """Average the descriptor over the neighboring particles (insight.py:94-118).
+
+        The returned Insight contains the following meta: sp_av_r_cut, selection.
+        """
+        from dynsight_b200 import analysis
+
+        averaged_dataset = analysis.spatialaverage(
+            universe=trj.universe,
+            descriptor_array=self.dataset,
+            selection=selection,
+            r_cut=r_cut,
+            trajslice=trj.trajslice,
+            n_jobs=n_jobs,
+        )
+        attr_dict = {"sp_av_r_cut": r_cut, "selection": selection}
+        logger.log(f"Computed spatial average with args {attr_dict}.")
+        return Insight(dataset=averaged_dataset, meta=attr_dict)
+
     def get_angular_velocity(self, delay: int = 1) -> Insight:
         """Computes the angular displacement of a vectorial descriptor (insight.py:136-155).
 
@@ -136,7 +161,7 @@ class Trj:
 
     @classmethod
     def init_from_xtc(cls, traj_file: Path, topo_file: Path) -> Trj:
-        """Initialize Trj object from .gro and .xtc files (uncompressed XTC frames only)."""
+        """Initialize Trj object from .gro and .xtc files (native reader, compressed XTC included)."""
         logger.log(f"Created Trj from {traj_file}, {topo_file}.")
         return Trj(ArrayUniverse.from_gro_xtc(topo_file, traj_file))
 

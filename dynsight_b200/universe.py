@@ -206,7 +206,7 @@ class ArrayUniverse:
     @classmethod
     def from_gro_xtc(cls, topo_file: str | Path, traj_file: str | Path) -> ArrayUniverse:
         topo, _, _ = dsg_io.read_gro(topo_file)
-        pos, dims = dsg_io.read_xtc_uncompressed(traj_file)
+        pos, dims = dsg_io.read_xtc(traj_file)  # native reader: compressed frames included
         return cls(pos, dims, topo.names, topo.types, topo.ids, topo.resnames)
 
     @classmethod

@@ -96,7 +96,9 @@ int dsg_neigh_fill(const void* d_pos_env, const void* d_pos_cent, int pos_dtype,
  * 2+256 int64: after the call status[0] != 0 means that at least one reservation did not fit
  * (those rows have row_start = -1): retry with rows_capacity >= status[1]*max(status[2..258)) * 1.05
  * (status[1] = number of regions actually used, a power of two <= 256).
- * respect_pbc: bit 0 = apply the minimum image; bit 1 = force the warp-per-cell kernel.  Without
+ * respect_pbc: bit 0 = apply the minimum image; bit 1 = force the warp-per-cell kernel; bit 2 =
+ * inclusive cutoff "dr2 <= r_cut^2" (the FastNS rule of analysis/spatial_average.py:39-40)
+ * instead of the numba kernels' "dr2 < (r_cut - 1e-6)^2".  Without
  * bit 1 sparse grids use one thread per centre; status[0] == 2 then means that some row exceeded
  * that kernel's staging tile (32 or 64 entries, chosen from the density) and the call must be
  * repeated with bit 1 set. */
@@ -199,6 +201,44 @@ int dsg_soap(const void* d_pos, int pos_dtype, const int32_t* d_species, const i
              double r_cut, int n_max, int l_max, const double* h_alphas, const double* h_betas,
              void* d_workspace, size_t workspace_bytes, double* d_out, int64_t stride_i,
              int64_t stride_f, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Spatial average (replaces analysis/spatial_average.py:31-63, processframe: FastNS pairs, then
+ * np.mean over each particle's neighbours and itself -- SURVEY.md section 8f row 1).
+ *
+ * dsg_wrap_positions: out = pos folded into [0, box) per frame (d_box (n_frames,3) float64 on the
+ *   device), what FastNS does before binning; feed the result to dsg_neigh_rows with
+ *   respect_pbc = 1 | 4 (minimum image, inclusive cutoff).
+ * dsg_spatial_average_rows: out[i, f, c] = (values[i, f, c] + sum_{j in row(f, i)} values[j, f, c])
+ *   / (counts[f, i] + 1); values / out float64 with element strides v_stride_i / v_stride_f
+ *   (components contiguous, n_comp = 1 for a scalar descriptor).
+ * ------------------------------------------------------------------------------------------ */
+int dsg_wrap_positions(const void* d_pos, int pos_dtype, int n_frames, int n_atoms,
+                       const double* d_box, void* d_out, void* stream);
+
+int dsg_spatial_average_rows(const int32_t* d_counts, const int64_t* d_row_start,
+                             const int32_t* d_rows, int n_frames, int n_cent, int n_comp,
+                             const double* d_values, int64_t v_stride_i, int64_t v_stride_f,
+                             double* d_out, int64_t o_stride_i, int64_t o_stride_f, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * XTC ingest (host code; replaces the MDAnalysis XTCReader behind Trj.init_from_xtc,
+ * trajectory/trajectory.py:68-79 -- SURVEY.md section 8f row 3).  Handles uncompressed
+ * (natoms <= 9) and compressed frames.
+ *
+ * dsg_xtc_index: scans the frame headers; writes the number of frames and atoms and, if
+ *   offsets_out != NULL, the byte offset of the first max_frames frames.
+ * dsg_xtc_read: decodes the frames at the given offsets with n_threads host threads
+ *   (<= 0: all cores).  pos_out (n_frames, n_atoms, 3) float32 in angstrom (nm * 10 in float32,
+ *   as MDAnalysis converts), box_out (n_frames, 9) float32 box vectors in angstrom or NULL,
+ *   step_out / time_out (n_frames) or NULL.
+ * ------------------------------------------------------------------------------------------ */
+int dsg_xtc_index(const char* path, int64_t* n_frames_out, int32_t* n_atoms_out,
+                  int64_t* offsets_out, int64_t max_frames);
+
+int dsg_xtc_read(const char* path, const int64_t* offsets, int64_t n_frames, int32_t n_atoms,
+                 float* pos_out, float* box_out, int32_t* step_out, float* time_out,
+                 int n_threads);
 
 #ifdef __cplusplus
 }

@@ -19,6 +19,10 @@ What it writes (all small, committed):
                          tests/trajectory/files/soap.npy) at frames 0::10 (21 of 201 frames, to keep
                          the fixture small) and the timeSOAP goldens in full
                          (tests/tsoap/test_tsoap/c0-c2, tests/trajectory/files/tsoap.npy).
+* ``coex.npz``        -- the "type O" atoms (2048 of 8192) of the reference's compressed
+                         ``tests/systems/coex/test_coex.xtc`` as decoded by the native reader, the
+                         SHA-256 of all decoded coordinates, and the reference's spatial-average
+                         golden ``tests/analysis/spavg/test_spavg.npy``.
 * ``numba_cases.npz`` -- outputs of the reference's numba kernels (imported by path, unmodified)
                          on seeded random inputs: CSR lists for ragged / out-of-box / centres!=env /
                          pbc on-off cases, a 2048-particle fluid LENS block, and timeSOAP on seeded
@@ -137,6 +141,30 @@ def main() -> None:
         d[f"tsoap_d{delay}"] = ref_ts.timesoap(spectra, delay=delay)
     d["tsoap_norm"] = ref_ts.normalize_soap(spectra)
     np.savez_compressed(HERE / "numba_cases.npz", **d)
+    # ---- compressed XTC + spatial average ----
+    import hashlib
+
+    from dynsight_b200.io import read_xtc
+    from oracle import spatial_oracle
+
+    topo_c, _, _ = read_gro(REF_TESTS / "systems/coex/test_coex.gro")
+    pos_c, dims_c = read_xtc(REF_TESTS / "systems/coex/test_coex.xtc")
+    o_index = np.where(topo_c.types == "O")[0]
+    spavg = np.load(REF_TESTS / "analysis/spavg/test_spavg.npy")
+    # tests/analysis/test_spatialaverage.py:41-61: dataset = x coordinate of the "type O" atoms
+    data_c = pos_c[:, o_index, 0].T.astype(np.float64)
+    mine = spatial_oracle.spatial_average(pos_c[:, o_index], dims_c, data_c, 5.0)
+    print("spatial oracle vs reference golden: max abs diff", np.abs(mine - spavg).max())
+    assert np.allclose(mine, spavg, rtol=1e-13, atol=0)
+    np.savez_compressed(
+        HERE / "coex.npz",
+        o_index=o_index.astype(np.int32),
+        o_positions=pos_c[:, o_index],
+        dims=dims_c,
+        spavg=spavg,
+        sha256_all=hashlib.sha256(np.ascontiguousarray(pos_c).tobytes()).hexdigest(),
+        n_atoms=pos_c.shape[1],
+    )
     for f in sorted(HERE.glob("*.npz")):
         print(f.name, f.stat().st_size)
 
