@@ -95,3 +95,33 @@ def spatialaverage(
     return frames.to_host(
         spatialaverage_device(universe, descriptor_array, selection, r_cut, trajslice)
     )
+
+
+def self_time_correlation(
+    data: NDArray[np.float64] | torch.Tensor,
+    max_delay: int | None = None,
+) -> tuple[NDArray[np.float64], NDArray[np.float64]]:
+    """Computes the mean self time correlation function for time-series.
+
+    ``data`` has shape (n_particles, n_frames).  Returns the self-TCF averaged over the particles
+    for the delays ``0 .. max_delay - 1`` (all delays if ``None``), normalised to 1 at delay 0,
+    and its standard error (time_correlations.py:13-92).
+
+    Raises:
+        ValueError: if ``max_delay`` is outside ``1 .. n_frames`` (the reference silently divides
+            by zero there).
+    """
+    dev = frames.device()
+    values = torch.as_tensor(data).to(device=dev, dtype=torch.float64).contiguous()
+    n_part, n_frames = values.shape
+    if max_delay is None:
+        max_delay = n_frames
+    if max_delay < 1 or max_delay > n_frames:
+        msg = f"max_delay={max_delay} must be in 1..{n_frames}"
+        raise ValueError(msg)
+    mean, std = engine.self_time_correlation_device(values, int(max_delay))
+    valid = n_frames - np.arange(max_delay, dtype=np.float64)
+    correlation = frames.to_host(mean) / valid
+    correlation_error = frames.to_host(std) / (valid * np.sqrt(n_part))
+    norm_fact = correlation[0]
+    return correlation / norm_fact, correlation_error / norm_fact

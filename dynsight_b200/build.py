@@ -10,7 +10,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 CSRC = _PKG / "csrc"
 SOURCES = ["core.cu", "neighbors.cu", "lens.cu", "descriptors.cu", "timesoap.cu", "soap.cu",
-           "spatial.cu", "xtc.cpp"]
+           "spatial.cu", "tcf.cu", "xtc.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

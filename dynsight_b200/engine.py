@@ -330,6 +330,31 @@ def spatial_average_rows(
     return out
 
 
+def self_time_correlation_device(
+    data: torch.Tensor, max_delay: int
+) -> tuple[torch.Tensor, torch.Tensor]:
+    """Per-lag mean and standard deviation over the particles of the un-normalised self
+    correlation ``c_i(t') = sum_t x_i(t) x_i(t+t')`` of the mean-subtracted rows of ``data``."""
+    lib = _lib.load()
+    _require_cuda(data, "data")
+    if data.dtype != torch.float64 or data.ndim != 2 or data.stride(1) != 1:  # noqa: PLR2004
+        msg = "data must be a (n_particles, n_frames) float64 tensor with contiguous rows"
+        raise ValueError(msg)
+    n_part, n_frames = data.shape
+    ws_bytes = ctypes.c_size_t(0)
+    _lib.check(lib.dsg_tcf_workspace_bytes(n_part, n_frames, int(max_delay), ctypes.byref(ws_bytes)))
+    workspace = torch.empty(ws_bytes.value, dtype=torch.uint8, device=data.device)
+    mean = torch.empty(int(max_delay), dtype=torch.float64, device=data.device)
+    std = torch.empty_like(mean)
+    _lib.check(
+        lib.dsg_self_time_correlation(
+            data.data_ptr(), data.stride(0), n_part, n_frames, int(max_delay),
+            workspace.data_ptr(), ws_bytes.value, mean.data_ptr(), std.data_ptr(), _stream_ptr(),
+        )
+    )  # fmt: skip
+    return mean, std
+
+
 def lens_pairs(
     batch: NeighborBatch, delay: int = 1, out: torch.Tensor | None = None, col0: int = 0
 ) -> torch.Tensor:

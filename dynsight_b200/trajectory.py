@@ -103,6 +103,17 @@ class Insight:
         logger.log(f"Computed spatial average with args {attr_dict}.")
         return Insight(dataset=averaged_dataset, meta=attr_dict)
 
+    def get_time_correlation(
+        self,
+        max_delay: int | None = None,
+    ) -> tuple[np.ndarray, np.ndarray]:
+        """Self time correlation function of the time-series signal (insight.py:120-134)."""
+        from dynsight_b200 import analysis
+
+        attr_dict = {"max_delay": max_delay}
+        logger.log(f"Computed time corrleation function with args {attr_dict}.")
+        return analysis.self_time_correlation(self.dataset, max_delay)
+
     def get_angular_velocity(self, delay: int = 1) -> Insight:
         """Computes the angular displacement of a vectorial descriptor (insight.py:136-155).
 

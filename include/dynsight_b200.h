@@ -222,6 +222,20 @@ int dsg_spatial_average_rows(const int32_t* d_counts, const int64_t* d_row_start
                              double* d_out, int64_t o_stride_i, int64_t o_stride_f, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Self time-correlation function (replaces analysis/time_correlations.py:60-92 -- SURVEY.md
+ * section 8f row 4).  d_data (n_part, n_frames) float64 with row stride stride_i (time contiguous).
+ * For every lag t' < max_delay (1 <= max_delay <= n_frames):
+ *   c_i(t') = sum_{t < n_frames - t'} x_i(t) x_i(t + t'),  x_i = data_i - mean_t(data_i)
+ *   mean_out[t'] = mean_i c_i(t'),  std_out[t'] = sqrt(mean_i (c_i(t') - mean_out[t'])^2).
+ * The caller divides by (n_frames - t') and normalises by lag 0 (time_correlations.py:78-90).
+ * ------------------------------------------------------------------------------------------ */
+int dsg_tcf_workspace_bytes(int n_part, int n_frames, int max_delay, size_t* bytes_out);
+
+int dsg_self_time_correlation(const double* d_data, int64_t stride_i, int n_part, int n_frames,
+                              int max_delay, void* d_workspace, size_t workspace_bytes,
+                              double* d_mean_out, double* d_std_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * XTC ingest (host code; replaces the MDAnalysis XTCReader behind Trj.init_from_xtc,
  * trajectory/trajectory.py:68-79 -- SURVEY.md section 8f row 3).  Handles uncompressed
  * (natoms <= 9) and compressed frames.

@@ -23,6 +23,8 @@ What it writes (all small, committed):
                          ``tests/systems/coex/test_coex.xtc`` as decoded by the native reader, the
                          SHA-256 of all decoded coordinates, and the reference's spatial-average
                          golden ``tests/analysis/spavg/test_spavg.npy``.
+* ``tcorr.npz``       -- the reference's self-TCF goldens (tests/analysis/tcorr/{t_corr,std_dev}.npy)
+                         and the doctest value of time_correlations.py:57.
 * ``numba_cases.npz`` -- outputs of the reference's numba kernels (imported by path, unmodified)
                          on seeded random inputs: CSR lists for ragged / out-of-box / centres!=env /
                          pbc on-off cases, a 2048-particle fluid LENS block, and timeSOAP on seeded
@@ -165,6 +167,21 @@ def main() -> None:
         sha256_all=hashlib.sha256(np.ascontiguousarray(pos_c).tobytes()).hexdigest(),
         n_atoms=pos_c.shape[1],
     )
+    # ---- self time-correlation function ----
+    from oracle import tcf_oracle
+
+    t_corr = np.load(REF_TESTS / "analysis/tcorr/t_corr.npy")
+    t_std = np.load(REF_TESTS / "analysis/tcorr/std_dev.npy")
+    mine_c, mine_e = tcf_oracle.self_time_correlation(tcf_oracle.reference_walk())
+    print("tcf oracle vs reference golden:", np.abs(mine_c - t_corr).max(),
+          np.abs(mine_e - t_std).max())
+    assert np.allclose(mine_c, t_corr, rtol=1e-12, atol=1e-14)
+    assert np.allclose(mine_e, t_std, rtol=1e-12, atol=1e-14)
+    np.random.seed(1234)  # doctest of time_correlations.py:44-57
+    kat, _ = tcf_oracle.self_time_correlation(np.random.rand(100, 100))
+    assert np.isclose(kat[1], 0.005519088806189553, rtol=1e-12)
+    np.savez_compressed(HERE / "tcorr.npz", t_corr=t_corr, std_dev=t_std,
+                        kat_rand_lag1=0.005519088806189553)
     for f in sorted(HERE.glob("*.npz")):
         print(f.name, f.stat().st_size)
 

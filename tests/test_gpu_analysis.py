@@ -119,3 +119,46 @@ def test_spavg_large_fluid_properties():
     lhs, rhs = (w * out).sum(0), (w * values).sum(0)
     assert torch.allclose(lhs, rhs, rtol=1e-10)
     assert 10.0 < float(nr.counts.double().mean()) < 12.5
+
+
+# ---- self time-correlation function --------------------------------
+def test_tcf_reference_goldens():
+    """tests/analysis/test_time_correlations.py:55-63 and the doctest of time_correlations.py:57."""
+    from conftest import GOLDEN
+    from oracle import tcf_oracle
+
+    from dynsight_b200.trajectory import Insight
+
+    fx = np.load(GOLDEN / "tcorr.npz")
+    corr, std = Insight(tcf_oracle.reference_walk()).get_time_correlation()
+    assert np.allclose(corr, fx["t_corr"])
+    assert np.allclose(std, fx["std_dev"])
+    assert np.allclose(corr, fx["t_corr"], rtol=1e-10, atol=1e-13)
+    np.random.seed(1234)  # noqa: NPY002
+    from dynsight_b200 import analysis
+
+    time_corr, _ = analysis.self_time_correlation(np.random.rand(100, 100))  # noqa: NPY002
+    assert np.isclose(time_corr[1], float(fx["kat_rand_lag1"]))
+
+
+@pytest.mark.parametrize(("n_part", "n_frames", "max_delay"),
+                         [(37, 1000, None), (300, 257, 100), (3, 30000, 64), (50, 9, 9)])  # fmt: skip
+def test_tcf_vs_oracle(n_part, n_frames, max_delay):
+    from oracle import tcf_oracle
+
+    from dynsight_b200 import analysis
+
+    rng = np.random.default_rng(n_frames)
+    data = np.cumsum(rng.normal(size=(n_part, n_frames)), axis=1) + rng.normal(size=(n_part, 1))
+    got_c, got_e = analysis.self_time_correlation(data, max_delay)
+    want_c, want_e = tcf_oracle.self_time_correlation(data, max_delay)
+    assert got_c.shape == want_c.shape
+    assert np.abs(got_c - want_c).max() <= 1e-10
+    assert np.abs(got_e - want_e).max() <= 1e-10 * max(1.0, np.abs(want_e).max())
+
+
+def test_tcf_errors():
+    from dynsight_b200 import analysis
+
+    with pytest.raises(ValueError, match="max_delay"):
+        analysis.self_time_correlation(np.zeros((3, 10)), 11)
