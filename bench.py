@@ -474,8 +474,10 @@ def run_b200(args: argparse.Namespace) -> None:
     }
 
     extra = None
+    widened = None
     if rank == 0 and not args.no_extra:
         extra = lens_cfg3_section(engine, dev, hbm_peak, hbm_src)
+        widened = widened_section(engine, dev, hbm_peak, fp64_peak_tflops)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -523,6 +525,7 @@ def run_b200(args: argparse.Namespace) -> None:
             },
             "cpu_baseline": cpu_baseline,
             "lens_cfg3": extra,
+            "widened_8f": widened,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -576,6 +579,67 @@ def lens_cfg3_section(engine, dev, hbm_peak: float, hbm_src: str) -> dict:
                      "frac": gbs / hbm_peak, "traffic": None,
                      "algorithmic_bytes_per_pf": bytes_pf, "peak_source": hbm_src},
     }  # fmt: skip
+
+
+def widened_section(engine, dev, hbm_peak: float, fp64_peak_tflops: float) -> dict:
+    """Throughput of the rows widened per SURVEY.md section 8f (reported beside the headline)."""
+    import torch
+
+    def timed(fn, reps: int = 4) -> float:
+        fn()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.mean(ts))
+
+    out: dict = {}
+    # spatial average: cfg3-like fluid, scalar descriptor and a 324-component one (SOAP size)
+    gen = torch.Generator(device=dev).manual_seed(11)
+    for n, nf, n_comp in ((1_000_000, 4, 1), (100_000, 4, 324)):
+        box_l = (n / 0.8) ** (1.0 / 3.0)
+        pos = (torch.rand((nf, n, 3), device=dev, generator=gen) * box_l).float()
+        box = np.full((nf, 3), box_l)
+        shape = (n, nf) if n_comp == 1 else (n, nf, n_comp)
+        values = torch.rand(shape, device=dev, generator=gen, dtype=torch.float64)
+        res = torch.empty_like(values)
+        state = {}
+
+        def run(pos=pos, box=box, values=values, res=res, state=state) -> None:
+            nr = engine.neighbor_rows(engine.wrap_positions(pos, box), box, 1.5,
+                                      inclusive_cutoff=True)
+            engine.spatial_average_rows(nr, values, res)
+            state["nr"] = nr
+
+        ms = timed(run)
+        k = float(state["nr"].counts.float().mean().item())
+        bytes_pf = 12 + 4 * (k + 1) + 8 * n_comp * (k + 2)
+        gbs = bytes_pf * n * nf / (ms * 1e-3) / 1e9
+        out[f"spatial_average_c{n_comp}"] = {
+            "workload": f"{n} particles x {nf} frames, rho*=0.8, r_cut=1.5, {n_comp} component(s)",
+            "value": n * nf / (ms * 1e-3), "unit": UNIT, "ms": ms, "mean_neighbours": k,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": gbs / hbm_peak, "algorithmic_bytes_per_pf": bytes_pf},
+        }  # fmt: skip
+        del pos, values, res, state
+    # self time-correlation function, all lags
+    n_part, n_frames = 20_000, 2_000
+    data = torch.randn((n_part, n_frames), device=dev, generator=gen, dtype=torch.float64).cumsum(1)
+    ms = timed(lambda: engine.self_time_correlation_device(data, n_frames), reps=3)
+    flops = 2.0 * n_part * (n_frames * (n_frames + 1) / 2)
+    tfl = flops / (ms * 1e-3) / 1e12
+    out["self_time_correlation"] = {
+        "workload": f"{n_part} particles x {n_frames} frames, all {n_frames} lags",
+        "value": n_part * n_frames / (ms * 1e-3), "unit": UNIT, "ms": ms,
+        "roofline": {"bound": "fp64", "achieved": tfl, "peak": fp64_peak_tflops,
+                     "unit": "TFLOP/s",
+                     "frac": tfl / fp64_peak_tflops if fp64_peak_tflops else None},
+    }  # fmt: skip
+    return out
 
 
 def main() -> None:
