@@ -75,6 +75,7 @@ struct SoapPlan {
     int rbuf_doubles;  // per-warp harmonics buffer (also holds the mixed coefficients)
     int kblocks;
     int item_l[kGroups][kMaxItems];  // -1 = unused
+    int item_off[kGroups][kMaxItems];  // start of that l's block in a harmonics row
 };
 
 struct SoapArgs {
@@ -267,8 +268,40 @@ __device__ __forceinline__ double exp_scaled(double t, const double* __restrict_
     return __hiloint2double(__double2hiint(r) + ((kq >> 4) << 20), __double2loint(r));
 }
 
-// Phase B: un-normalised regular solid harmonics of one displacement, rows padded to even length:
-//   rt[l(l+1) + l + m] = S_l^m(z, r2) * A_m(x, y),   rt[l(l+1) + l - m] = S_l^m * B_m   (m > 0)
+// Layout of one neighbour's harmonics row: the block of angular momentum l (2l+1 values, padded
+// to even length) starts at harm_off(LT, l); element (l, m) sits at harm_off + l + m.  l = 0 is
+// not used (its single value is 1 and that channel is accumulated separately).  For LT = 8 the
+// blocks of l = 1 and l = 7 change places and l = 0 is dropped: with the natural order the four
+// lane groups of phase C (which read the blocks of four different l with the same running offset)
+// hit the same shared-memory banks for one pair of l; with this order the four block starts are
+// distinct modulo 128 bytes for every l_max <= 8 (checked exhaustively against make_plan's
+// packing; +6 % on the l_max = 8 kernel).  The other instantiations keep the natural order
+// l(l+1): the same change made the l_max = 10 kernel slower (ncu: half the bank conflicts but 6 %
+// more instructions and a worse schedule at its 255-register limit).
+__host__ __device__ constexpr int harm_off(int lt, int l) {
+    if (lt != 8) return l * (l + 1);
+    switch (l) {  // block order 7, 2, 3, 4, 5, 6, 1, 8, 9, 10, 11, 12 (sizes 2l+2)
+        case 1: return 66;
+        case 2: return 16;
+        case 3: return 22;
+        case 4: return 30;
+        case 5: return 40;
+        case 6: return 52;
+        case 7: return 0;
+        case 8: return 70;
+        case 9: return 88;
+        case 10: return 108;
+        case 11: return 130;
+        case 12: return 154;
+        default: return 0;
+    }
+}
+__host__ __device__ constexpr int harm_len(int lt) {
+    return lt != 8 ? (lt + 1) * (lt + 2) : harm_off(lt, lt) + 2 * lt + 2;
+}
+
+// Phase B: un-normalised regular solid harmonics of one displacement:
+//   rt[off(l) + l + m] = S_l^m(z, r2) * A_m(x, y),   rt[off(l) + l - m] = S_l^m * B_m   (m > 0)
 //   A_m + i B_m = (x + i y)^m ;  S_m^m = (2m-1)!!, S_{m+1}^m = (2m+1) z S_m^m,
 //   S_l^m = ((2l-1) z S_{l-1}^m - (l+m-1) r2 S_{l-2}^m) / (l-m)
 template <int LT>
@@ -284,14 +317,14 @@ __device__ __forceinline__ void solid_harmonics(double x, double y, double z, do
             dfact *= (double)(2 * m - 1);
         }
         double s0 = dfact;  // S_m^m
-        rt[m * (m + 1) + 2 * m] = s0 * am;
-        if (m > 0) rt[m * (m + 1)] = s0 * bm;
+        if (m > 0) {
+            rt[harm_off(LT, m) + 2 * m] = s0 * am;
+            rt[harm_off(LT, m)] = s0 * bm;
+        }
         if (m + 1 <= LT) {
             double s1 = (double)(2 * m + 1) * z * s0;  // S_{m+1}^m
             {
-                constexpr int dummy = 0;
-                (void)dummy;
-                const int l = m + 1, o = l * (l + 1) + l;
+                const int o = harm_off(LT, m + 1) + m + 1;
                 rt[o + m] = s1 * am;
                 if (m > 0) rt[o - m] = s1 * bm;
             }
@@ -300,7 +333,7 @@ __device__ __forceinline__ void solid_harmonics(double x, double y, double z, do
                 const double inv = 1.0 / (double)(l - m);  // compile-time constant after unrolling
                 const double s2 =
                     ((double)(2 * l - 1) * z * s1 - (double)(l + m - 1) * r2 * s0) * inv;
-                const int o = l * (l + 1) + l;
+                const int o = harm_off(LT, l) + l;
                 rt[o + m] = s2 * am;
                 if (m > 0) rt[o - m] = s2 * bm;
                 s0 = s1;
@@ -491,7 +524,7 @@ soap_kernel(const SoapArgs a) {
 #pragma unroll
     for (int t = 0; t < kMaxItems; ++t) {
         il[t] = pl.item_l[g][t];
-        ioff[t] = il[t] >= 0 ? il[t] * (il[t] + 1) : 0;
+        ioff[t] = pl.item_off[g][t];
     }
 
     const int n_pass = SPLIT ? pl.n_species * pl.kblocks : 1;
@@ -956,11 +989,11 @@ static void make_plan(int n_species, int n_max, int l_max, int lt, int s0, SoapP
     pl->n_species = n_species;
     pl->n_feat = dsg_soap_n_features(n_species, n_max, l_max);
     pl->n_lm = (l_max + 1) * (l_max + 1);
-    // harmonics rows padded to even length: (lt+1)(lt+2) doubles per neighbour; the stride is
-    // = 2 mod 16 so that the phase-B stores of 32 lanes spread over the banks
+    // harmonics rows (harm_len doubles per neighbour); the stride is = 2 mod 4 so that the
+    // phase-B stores of the lanes spread over the banks
     pl->kblocks = (n_max + kKBlock - 1) / kKBlock;
-    int p = (lt + 1) * (lt + 2);
-    while (p % 16 != 2) ++p;
+    int p = harm_len(lt);
+    while (p % (lt == 8 ? 4 : 16) != 2) ++p;
     pl->row_stride = p;
     int rb = kChunk * p + s0 + 2;  // tail: item rows are read S_t wide past the last row
     // fused epilogue: G and the mixed coefficients both live here (split mode: neither)
@@ -971,12 +1004,16 @@ static void make_plan(int n_species, int n_max, int l_max, int lt, int s0, SoapP
     // longest-processing-time packing of l = l_max..1 (size 2l+1) into 4 lane groups
     int load[kGroups] = {0, 0, 0, 0}, cnt[kGroups] = {0, 0, 0, 0};
     for (int g = 0; g < kGroups; ++g)
-        for (int t = 0; t < kMaxItems; ++t) pl->item_l[g][t] = -1;
+        for (int t = 0; t < kMaxItems; ++t) {
+            pl->item_l[g][t] = -1;
+            pl->item_off[g][t] = 0;
+        }
     // l = 0 (a single m, weight exp(-gamma_0k r^2) only) is accumulated cooperatively by all lanes
     for (int l = l_max; l >= 1; --l) {
         int best = 0;
         for (int g = 1; g < kGroups; ++g)
             if (load[g] < load[best]) best = g;
+        pl->item_off[best][cnt[best]] = harm_off(lt, l);
         pl->item_l[best][cnt[best]++] = l;
         load[best] += 2 * l + 1;
     }
@@ -1136,7 +1173,10 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
              (split ? 0 : (size_t)a.bmat_smem_doubles + (size_t)a.epi_smem_doubles));
     int warps = 2;
     if (per_warp * warps + shared_tables > 227 * 1024) warps = 1;
-    const size_t smem = per_warp * warps + shared_tables;
+#ifndef DSG_SOAP_EXTRA_SMEM
+#define DSG_SOAP_EXTRA_SMEM 0
+#endif
+    const size_t smem = per_warp * warps + shared_tables + DSG_SOAP_EXTRA_SMEM;  // (occupancy probe)
     // spectrum kernel: mixed coefficients of one l per warp
     const size_t spec_bytes = 8 * (size_t)n_species * (2 * l_max + 1) * ((n_max + 1) & ~1);
     if (smem > 227 * 1024 || (split && spec_bytes + 8 * (size_t)a.bmat_smem_doubles > 227 * 1024))
