@@ -769,18 +769,19 @@ neigh_rows_thread_kernel(const RowsArgs a, const unsigned* __restrict__ cent_slo
                     cd[u] = a.env_sorted[min(q0 + u, qe - 1)];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    if (q0 + u >= qe) break;
                     const int j = __float_as_int(cd[u].w);
                     const float dx = cd[u].x + ox, dy = cd[u].y + oy, dz = cd[u].z + oz;
                     const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                    const bool valid = q0 + u < qe;
                     bool hit = d2 < r2_lo;
-                    if (!hit && !(d2 > r2_hi))
+                    if (valid && !hit && !(d2 > r2_hi))   // inside the guard band: rare
                         hit = exact_test<T>(pos_env_f + (size_t)j * 3,
                                             pos_cent_f + (size_t)my_id * 3, p->box, pbc, a.r2);
-                    if (hit && j != my_id) {  // lens.py:104 "j != i"
-                        if (cnt < kTpcHitCap) stage[cnt][tid] = j;
-                        ++cnt;
-                    }
+                    hit = hit && valid && j != my_id;  // lens.py:104 "j != i"
+                    // branch-free staging: an overflowing row keeps rewriting the last slot (the
+                    // batch is redone by the warp kernel then, status 2)
+                    if (hit) stage[min(cnt, kTpcHitCap - 1)][tid] = j;
+                    cnt += hit ? 1 : 0;
                 }
             }
         };
