@@ -190,6 +190,23 @@ class Trj:
         logger.log(f"Created a sliced Trj with args {attr_dict}.")
         return Trj(self.universe, trajslice=trajslice)
 
+    def get_slice(self, start: int, stop: int, step: int) -> Trj:
+        """Returns a Trj with a subset of frames (trajectory.py:115-137; deprecated upstream in
+        favour of ``with_slice``).  Like the reference's ``MemoryReader`` copy, the new trajectory
+        keeps the coordinates only: it has no simulation box."""
+        coords = np.array(
+            [ts.positions.copy() for ts in self.universe.trajectory[start:stop:step]],
+            dtype=np.float32,
+        ).reshape(-1, self.universe.atoms.n_atoms, 3)
+        atoms = self.universe.atoms
+        u_new = ArrayUniverse(
+            coords, None, names=getattr(atoms, "names", None), types=getattr(atoms, "types", None),
+            ids=getattr(atoms, "ids", None), resnames=getattr(atoms, "resnames", None),
+        )  # fmt: skip
+        attr_dict = {"start": start, "stop": stop, "step": step}
+        logger.log(f"Created a sliced Trj with args {attr_dict}.")
+        return Trj(u_new)
+
     def get_coord_number(
         self,
         r_cut: float,

@@ -221,3 +221,17 @@ def test_no_cuda_means_loud_failure(balls7):
         trj.get_lens(r_cut=15.0)
     with pytest.raises(RuntimeError, match="CUDA device"):
         trj.get_soap(r_cut=8.0, n_max=4, l_max=4)
+
+
+def test_trj_get_slice_keeps_coordinates_only(balls7):
+    """trajectory.py:115-137: a MemoryReader copy of the chosen frames, without a box."""
+    from dynsight_b200.trajectory import Trj
+    from dynsight_b200.universe import ArrayUniverse
+
+    trj = Trj(ArrayUniverse(balls7["positions"], balls7["dims"], balls7["names"], balls7["types"],
+                            balls7["ids"]))  # fmt: skip
+    sub = trj.get_slice(3, 40, 7)
+    assert sub.universe.trajectory.n_frames == len(range(3, 40, 7))
+    assert np.array_equal(sub.get_coordinates("all"), balls7["positions"][3:40:7])
+    assert sub.universe.trajectory.ts.dimensions is None
+    assert sub.universe.select_atoms("name C3").n_atoms == 1
