@@ -245,8 +245,16 @@ __global__ void frame_finalize_kernel(FrameParams* __restrict__ fp, int n_frames
     for (int k = 0; k < 3; ++k) {
         const double a = (double)__uint_as_float(p->amax_bits[k]);
         const double b = p->box[k] > 0.0 ? p->box[k] : 0.0;
-        const double e = 8.0 * u * (a + b);
-        const double delta = 4.0 * e;
+        double delta = 32.0 * u * (a + b);
+        if (p->shift_mode[k]) {
+            // rows path, shift mode: the staged value is the image next to the atom's cell,
+            // |x'| <= A = b + edge <= 1.2 b (ncell >= 6), computed in float64 (error
+            // <= 2^-52 (a + b)) and rounded once (u A).  The difference is formed as
+            // (x'_j + (+-b_f32 - x'_i)) or ((x'_j +- b_f32) - x'_i): roundings u A (x'_j), u A
+            // (x'_i), u b (b_f32), u (b + A) (inner sum), u * 0.75 b (outer sum, |d| <= 4.5
+            // edges) -- 6.35 u b in total; 8 u b is used.
+            delta = 8.0 * u * b + 8.8817841970012523e-16 * (a + b);
+        }
         tol += delta * (3.0 * r_cut + delta);
         if (b > 0.0) {
             const double dq = 4.0 * u * (2.0 * a / b + 1.0);  // error of the f32 image quotient

@@ -362,3 +362,35 @@ def test_rows_path_lens_goldens(balls7, ref_lens, numba_cases):
         p2, d2 = lens_2d_inputs()
         lens, _ = engine.lens_from_positions(_dev(p2), d2[:, :3], 0.1, 1, respect_pbc=pbc)
         assert np.array_equal(lens.cpu().numpy(), ref_lens["lens_2d_pbc" if pbc else "lens_2d_fbc"])
+
+
+@pytest.mark.parametrize("force_warp", [False, True])
+def test_rows_path_near_threshold_pairs_in_a_large_box(force_warp):
+    """Adversarial for the float32 guard band of the shift-mode rows kernels: thousands of pairs
+    whose distance is within a few float32 ulps of the cutoff, at coordinates ~100 (float32
+    spacing 8e-6), many of them across the periodic boundary.  Membership must follow the
+    reference's float64 rule bit for bit."""
+    from dynsight_b200 import engine
+
+    rng = np.random.default_rng(99)
+    r_cut = 1.5
+    rc = r_cut - 1e-6
+    box = np.array([107.7, 96.3, 121.1], dtype=np.float32)
+    n_pairs = 6000
+    base = rng.random((n_pairs, 3)) * box
+    # a third of the pairs hug a face of the box so that the partner lands in the periodic image
+    face = rng.integers(0, 3, n_pairs)
+    hug = rng.random(n_pairs) < 0.33
+    base[hug, face[hug]] = rng.random(hug.sum()) * 0.4
+    d = rng.normal(size=(n_pairs, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r = rc * (1.0 + rng.uniform(-4e-6, 4e-6, n_pairs))
+    partner = base - d * r[:, None]
+    pts = np.concatenate([base, partner]).astype(np.float32)
+    pts = np.mod(pts, box).astype(np.float32)
+    frames = np.stack([pts, np.roll(pts, 1, axis=0)])
+    nr = engine.neighbor_rows(_dev(frames), box, r_cut, None, True, force_warp_kernel=force_warp)
+    assert not nr.overflowed()
+    _check_rows_vs_oracle(nr, frames, None, box, r_cut, True)
+    counts = nr.counts.cpu().numpy()
+    assert 0.2 < (counts[0, :n_pairs] > 0).mean() < 0.8  # both outcomes occur
