@@ -50,6 +50,7 @@ def spatialaverage_device(
         raise IndexError(msg)
     if batch_frames is None:
         batch_frames = frames.pick_batch_frames(sel_ix.size, 400.0, 1)
+    sel_all = frames.Selection(sel_ix, n_all)
     for fb in frames.iter_batches(universe, fr_idx, batch_frames):
         if fb.dims is None:
             msg = "spatialaverage needs a simulation box (ts.dimensions is None)"
@@ -58,7 +59,7 @@ def spatialaverage_device(
             msg = "dynsight_b200 spatialaverage supports orthorhombic boxes only"
             raise NotImplementedError(msg)
         box = np.ascontiguousarray(fb.dims[:, :3].astype(np.float64))
-        pos = engine.wrap_positions(fb.select(sel_ix, n_all), box)  # FastNS bins wrapped positions
+        pos = engine.wrap_positions(fb.select(sel_all, n_all), box)  # FastNS bins wrapped positions
         capacity = None
         force_warp = False
         while True:

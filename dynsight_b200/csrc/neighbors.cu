@@ -1192,7 +1192,9 @@ static int neigh_rows_impl(const void* d_pos_env, const void* d_pos_cent, int n_
                                    cand_sum / n_frames <= 200.0 && k_hi <= 64.0;
     if (use_thread_kernel) {
         dim3 tgrid((n_cent + kTpcThreads - 1) / kTpcThreads, n_frames);
-        if (k_hi <= 32.0)
+        // an ideal-gas-like (Poisson) neighbour count must not overflow the tile anywhere in a
+        // batch of 1e7 centres, or the whole batch is redone by the warp kernel: 10 sigma
+        if (k_max + 10.0 * std::sqrt(k_max) <= 32.0)
             neigh_rows_thread_kernel<T, 32><<<tgrid, kTpcThreads, 0, st>>>(a, slot_cell_c);
         else
             neigh_rows_thread_kernel<T, 64><<<tgrid, kTpcThreads, 0, st>>>(a, slot_cell_c);

@@ -25,7 +25,8 @@ __all__ = ["compute_mean_alignment", "orientational_order_param", "velocity_alig
 def _all_positions(universe: Any) -> torch.Tensor:
     """Positions of all atoms for every frame of the trajectory -> (F, N, 3) on the device."""
     n_frames = len(universe.trajectory)
-    chunks = [fb.pos_all for fb in frames.iter_batches(universe, list(range(n_frames)), 4096)]
+    # iter_batches reuses two device buffers: keep copies, not views
+    chunks = [fb.pos_all.clone() for fb in frames.iter_batches(universe, list(range(n_frames)), 4096)]
     return chunks[0] if len(chunks) == 1 else torch.cat(chunks, dim=0)
 
 

@@ -25,12 +25,32 @@ class FrameBatch:
     pos_all: torch.Tensor  # (F, N_all, 3) float32 / float64, CUDA
     dims: np.ndarray | None  # (F, 6) float32 box [lx, ly, lz, alpha, beta, gamma] or None
 
-    def select(self, ix: np.ndarray, n_all: int) -> torch.Tensor:
+    def select(self, ix: np.ndarray | Selection, n_all: int) -> torch.Tensor:
         """Positions of the atoms ``ix`` (universe indices) -> (F, n, 3) contiguous."""
-        if ix.size == n_all and np.array_equal(ix, np.arange(n_all)):
+        sel = ix if isinstance(ix, Selection) else Selection(ix, n_all)
+        if sel.identity:
             return self.pos_all
-        idx = torch.as_tensor(ix, dtype=torch.long, device=self.pos_all.device)
-        return self.pos_all.index_select(1, idx).contiguous()
+        return self.pos_all.index_select(1, sel.device_index(self.pos_all.device)).contiguous()
+
+
+class Selection:
+    """Atom indices of a selection, analysed once per API call (not once per batch): whether it
+    is the whole universe in order (then batches are used as they are) and, if not, the index
+    tensor on the device."""
+
+    def __init__(self, ix: np.ndarray, n_all: int) -> None:
+        self.ix = np.asarray(ix)
+        self.identity = bool(
+            self.ix.size == n_all
+            and (n_all == 0 or (self.ix[0] == 0 and self.ix[-1] == n_all - 1
+                                and np.array_equal(self.ix, np.arange(n_all))))
+        )  # fmt: skip
+        self._dev_index: torch.Tensor | None = None
+
+    def device_index(self, dev: torch.device) -> torch.Tensor:
+        if self._dev_index is None or self._dev_index.device != dev:
+            self._dev_index = torch.as_tensor(self.ix, dtype=torch.long, device=dev)
+        return self._dev_index
 
 
 def device() -> torch.device:
@@ -49,31 +69,73 @@ def frame_sequence(n_frames: int, trajslice: slice | None) -> list[int]:
     return idx if trajslice is None else idx[trajslice]
 
 
+_COPY_STREAMS: dict[int, torch.cuda.Stream] = {}
+
+
+def _copy_stream(dev: torch.device) -> torch.cuda.Stream:
+    """One side stream per device for host -> device copies."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _COPY_STREAMS[key]
+
+
 def iter_batches(universe: Any, frames: list[int], batch_frames: int, overlap: int = 0
                  ) -> Iterator[FrameBatch]:  # fmt: skip
-    """Yield device batches covering ``frames``; consecutive batches share ``overlap`` frames."""
+    """Yield device batches covering ``frames``; consecutive batches share ``overlap`` frames.
+
+    Double-buffered: two device buffers are reused alternately, and the host -> device copy of a
+    batch runs on a side stream.  The copy is issued when the consumer asks for the next batch,
+    i.e. after the kernels of the previous batch were enqueued on the compute stream, so it
+    overlaps that compute instead of queueing behind it; the compute stream waits on the copy's
+    event before the batch is handed out, and a buffer is overwritten only after the kernels
+    that read it (recorded when the consumer came back for more) have finished.  A consumer may
+    therefore keep using a batch until it has asked for the batch after the next one.
+    """
     dev = device()
     n = len(frames)
     batch_frames = max(int(batch_frames), overlap + 1)
+    side = _copy_stream(dev)
+    compute = torch.cuda.current_stream(dev)
+    bufs: list[torch.Tensor | None] = [None, None]
+    released: list[torch.cuda.Event | None] = [None, None]
     start = 0
+    k = 0
     while True:
         stop = min(n, start + batch_frames)
         chunk = frames[start:stop]
-        yield _load(universe, chunk, start, dev)
+        host, dims = _load_host(universe, chunk)
+        slot = k & 1
+        if bufs[slot] is None or bufs[slot].dtype != host.dtype or bufs[slot].shape[0] < len(chunk):
+            bufs[slot] = torch.empty((min(batch_frames, n), *host.shape[1:]), dtype=host.dtype,
+                                     device=dev)  # fmt: skip
+            released[slot] = torch.cuda.Event()
+            released[slot].record(compute)  # the allocator may hand out memory still in use there
+        dst = bufs[slot][: len(chunk)]
+        with torch.cuda.stream(side):
+            side.wait_event(released[slot])
+            dst.copy_(host, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(side)
+        compute.wait_event(ready)
+        yield FrameBatch(start, chunk, dst, dims)
+        released[slot] = torch.cuda.Event()
+        released[slot].record(compute)
         if stop >= n:
             return
         start = stop - overlap
+        k += 1
 
 
-def _load(universe: Any, chunk: list[int], seq0: int, dev: torch.device) -> FrameBatch:
+def _load_host(universe: Any, chunk: list[int]) -> tuple[torch.Tensor, np.ndarray | None]:
+    """Positions of all atoms for the frames ``chunk`` as one host tensor (+ per-frame boxes)."""
     if isinstance(universe, ArrayUniverse):
         reader = universe.trajectory
         coords = reader.coordinates
         contiguous_run = len(chunk) > 0 and chunk == list(range(chunk[0], chunk[0] + len(chunk)))
         host = coords[chunk[0] : chunk[0] + len(chunk)] if contiguous_run else coords[chunk]
         dims = None if reader.dimensions_array is None else reader.dimensions_array[chunk]
-        t = torch.from_numpy(np.ascontiguousarray(host))
-        return FrameBatch(seq0, chunk, t.to(dev, non_blocking=True), dims)
+        return torch.from_numpy(np.ascontiguousarray(host)), dims
     # generic duck-typed Universe (e.g. MDAnalysis): seek + copy frame by frame into pinned memory
     n_all = len(universe.atoms)
     first = np.asarray(universe.atoms.positions)
@@ -93,7 +155,7 @@ def _load(universe: Any, chunk: list[int], seq0: int, dev: torch.device) -> Fram
         raise ValueError(msg)
     else:
         dims = np.stack(dims_list)  # type: ignore[arg-type]
-    return FrameBatch(seq0, chunk, stage.to(dev, non_blocking=True), dims)
+    return stage, dims
 
 
 def lens_boxes(batch: FrameBatch, scale: float | None) -> np.ndarray:

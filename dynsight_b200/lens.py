@@ -54,13 +54,32 @@ def compute_lens_device(
     if batch_frames is None:
         batch_frames = frames.pick_batch_frames(max(ix_env.size, ix_cent.size), 160.0, delay + 1)
     batch_frames = max(batch_frames, delay + 1)
+
+    def settle(job: tuple | None) -> None:
+        """The one host sync per batch: a reservation overflow (rare) reruns that batch."""
+        if job is None:
+            return
+        fb, box, pos_env, pos_cent, nr = job
+        if nr.overflowed():
+            engine.lens_from_positions(
+                pos_env, box, r_cut, delay, pos_cent, respect_pbc, out=out, col0=fb.seq0,
+                capacity=None if nr.needs_warp_kernel() else int(nr.needed_capacity() * 1.1),
+            )
+
+    # Software pipeline over batches: asking the iterator for batch k issues its host -> device
+    # copy on the side stream while the kernels of batch k-1 (already enqueued) run; the status
+    # of batch k-1 is read only after the kernels of batch k are enqueued.
+    pending = None
+    sel_env, sel_cent = frames.Selection(ix_env, n_all), frames.Selection(ix_cent, n_all)
     for fb in frames.iter_batches(universe, fr_idx, batch_frames, overlap=delay):
         box = frames.lens_boxes(fb, 1.01)
-        pos_env = fb.select(ix_env, n_all)
-        pos_cent = None if same else fb.select(ix_cent, n_all)
-        engine.lens_from_positions(
-            pos_env, box, r_cut, delay, pos_cent, respect_pbc, out=out, col0=fb.seq0
-        )
+        pos_env = fb.select(sel_env, n_all)
+        pos_cent = None if same else fb.select(sel_cent, n_all)
+        nr = engine.neighbor_rows(pos_env, box, r_cut, pos_cent, respect_pbc)
+        engine.lens_pairs_rows(nr, delay, out=out, col0=fb.seq0)
+        settle(pending)
+        pending = (fb, box, pos_env, pos_cent, nr)
+    settle(pending)
     return out
 
 

@@ -89,9 +89,10 @@ def saponify_trajectory_device(
         # workspace per atom-frame: sorted copies + (several species / n_max > 8) primitive sums
         scratch = soap_basis.scratch_doubles(n_species, soapnmax, soaplmax) * 8.0
         batch_frames = frames.pick_batch_frames(sel_ix.size, 80.0 + scratch, 1, maximum=1024)
+    sel_all = frames.Selection(sel_ix, n_all)
     for fb in frames.iter_batches(universe, fr_idx, batch_frames):
         box = frames.soap_boxes(fb, bool(soap_respectpbc))
-        pos = fb.select(sel_ix, n_all)
+        pos = fb.select(sel_all, n_all)
         engine.soap_power_spectrum(
             pos, species_t, centres_t, box, float(soaprcut), int(soapnmax), int(soaplmax),
             n_species=n_species, out=out, frame0=fb.seq0,
@@ -244,9 +245,10 @@ def timesoap_from_trajectory(
         per_frame = max(1, n_cent) * (n_feat + scratch) * 8.0
         batch_frames = int(max(delay + 1, min(512, 16e9 // per_frame)))
     batch_frames = max(batch_frames, delay + 1)
+    sel_all = frames.Selection(sel_ix, n_all)
     for fb in frames.iter_batches(universe, fr_idx, batch_frames, overlap=delay):
         box = frames.soap_boxes(fb, bool(soap_respectpbc))
-        pos = fb.select(sel_ix, n_all)
+        pos = fb.select(sel_all, n_all)
         spectra = engine.soap_power_spectrum(
             pos, species_t, centres_t, box, float(soaprcut), int(soapnmax), int(soaplmax),
             n_species=n_species,

@@ -145,6 +145,8 @@ class ArrayAtomGroup:
             yield ArrayAtomGroup(self.universe, np.array([i]))
 
     def select_atoms(self, selection: str) -> ArrayAtomGroup:
+        if selection.strip() == "all":  # the common case, no mask arithmetic on 1e6 atoms
+            return self
         mask = _Selector(self.universe).evaluate(selection)
         return ArrayAtomGroup(self.universe, self.ix[mask[self.ix]])
 
