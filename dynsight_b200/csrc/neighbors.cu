@@ -762,12 +762,18 @@ neigh_rows_thread_kernel(const RowsArgs a, const unsigned* __restrict__ cent_slo
     const T* __restrict__ pos_cent_f = (const T*)a.pos_cent + (size_t)f * a.n_cent * 3;
 
     int cnt = 0, my_id = 0;
+    float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cx = 0, cy = 0, cz = 0;
     if (active) {
         const size_t slot = (size_t)f * a.n_cent + slot_local;
-        const float4 me = a.cent_sorted[slot];
+        me = a.cent_sorted[slot];
         my_id = __float_as_int(me.w);
         const unsigned pc = cent_slot_cell[slot];
-        const int cx = (int)(pc >> 20), cy = (int)((pc >> 10) & 1023u), cz = (int)(pc & 1023u);
+        cx = (int)(pc >> 20), cy = (int)((pc >> 10) & 1023u), cz = (int)(pc & 1023u);
+    }
+    // The 27 cells of the centre; hits go to the shared staging tile (gdst == nullptr) or, in the
+    // rare second pass of a row longer than the tile, straight to the row's place in global memory.
+    auto walk = [&](int* __restrict__ gdst) {
         // candidates of a contiguous run of cells, four loads in flight per step
         auto scan_run = [&](int qb, int qe, float ox, float oy, float oz) {
             for (int q0 = qb; q0 < qe; q0 += 4) {
@@ -786,9 +792,11 @@ neigh_rows_thread_kernel(const RowsArgs a, const unsigned* __restrict__ cent_slo
                         hit = exact_test<T>(pos_env_f + (size_t)j * 3,
                                             pos_cent_f + (size_t)my_id * 3, p->box, pbc, a.r2);
                     hit = hit && valid && j != my_id;  // lens.py:104 "j != i"
-                    // branch-free staging: an overflowing row keeps rewriting the last slot (the
-                    // batch is redone by the warp kernel then, status 2)
-                    if (hit) stage[min(cnt, kTpcHitCap - 1)][tid] = j;
+                    if (hit) {
+                        // branch-free staging: an overflowing row keeps rewriting the last slot
+                        if (gdst == nullptr) stage[min(cnt, kTpcHitCap - 1)][tid] = j;
+                        else gdst[cnt] = j;
+                    }
                     cnt += hit ? 1 : 0;
                 }
             }
@@ -815,32 +823,44 @@ neigh_rows_thread_kernel(const RowsArgs a, const unsigned* __restrict__ cent_slo
                 }
             }
         }
-    }
-    // one reservation per warp
-    const int incl = warp_incl_scan(cnt, lane);
+    };
+    if (active) walk(nullptr);
+    // one reservation per warp for the rows that fit the tile; a longer row (rare) reserves its
+    // own place and is written by a second walk of its thread
+    const bool long_row = cnt > kTpcHitCap;
+    const int cnt_t = long_row ? 0 : cnt;
+    const int incl = warp_incl_scan(cnt_t, lane);
     const int total = __shfl_sync(kFull, incl, 31);
-    const bool too_many = __any_sync(kFull, cnt > kTpcHitCap);
+    const int part = (blockIdx.x * (kTpcThreads / 32) + warp + f * 131) & (a.n_parts - 1);
     long long base = 0;
-    if (lane == 0) {
-        if (too_many) {
-            a.status[0] = 2;  // a row does not fit the staging tile: caller switches kernels
+    if (lane == 0 && total > 0) {
+        const unsigned long long off = atomicAdd(&a.cursors[part], (unsigned long long)total);
+        if ((long long)(off + total) > a.part_cap) {
+            if (a.status[0] == 0) a.status[0] = 1;
             base = -1;
-        } else if (total > 0) {
-            const int part = (blockIdx.x * (kTpcThreads / 32) + warp + f * 131) & (a.n_parts - 1);
-            const unsigned long long off = atomicAdd(&a.cursors[part], (unsigned long long)total);
-            if ((long long)(off + total) > a.part_cap) {
-                if (a.status[0] == 0) a.status[0] = 1;
-                base = -1;
-            } else {
-                base = (long long)part * a.part_cap + (long long)off;
-            }
+        } else {
+            base = (long long)part * a.part_cap + (long long)off;
         }
     }
     if (blockIdx.x == 0 && f == 0 && tid == 0) a.status[1] = a.n_parts;
     base = __shfl_sync(kFull, base, 0);
+    long long my_start = base < 0 ? -1 : base + (long long)(incl - cnt_t);
+    if (long_row) {
+        const int n_row = cnt;
+        const unsigned long long off = atomicAdd(&a.cursors[part], (unsigned long long)n_row);
+        if ((long long)(off + n_row) > a.part_cap) {
+            if (a.status[0] == 0) a.status[0] = 1;
+            my_start = -1;
+        } else {
+            my_start = (long long)part * a.part_cap + (long long)off;
+            cnt = 0;
+            walk(a.rows + my_start);
+        }
+        cnt = n_row;
+    }
     if (active) {
         a.counts[(size_t)f * a.n_cent + my_id] = cnt;
-        a.row_start[(size_t)f * a.n_cent + my_id] = base < 0 ? -1 : base + (long long)(incl - cnt);
+        a.row_start[(size_t)f * a.n_cent + my_id] = my_start;
     }
     if (base < 0 || total == 0) return;
     __syncwarp();
@@ -855,7 +875,7 @@ neigh_rows_thread_kernel(const RowsArgs a, const unsigned* __restrict__ cent_slo
             if (v <= pp) t += s;
         }
         t &= 31;
-        const int excl_t = __shfl_sync(kFull, incl - cnt, t);
+        const int excl_t = __shfl_sync(kFull, incl - cnt_t, t);
         if (pp < total) dst[pp] = stage[pp - excl_t][warp * 32 + t];
     }
 }
@@ -1187,14 +1207,14 @@ static int neigh_rows_impl(const void* d_pos_env, const void* d_pos_cent, int n_
         if (k_est > k_max) k_max = k_est;
     }
     // sparse cells (few candidates per centre): one thread per centre issues ~4x fewer instructions
-    const double k_hi = k_max + 6.0 * std::sqrt(k_max);  // rows must fit the staging tile
+    // rows longer than the staging tile are written by a second walk of their thread, so the
+    // tile only has to hold the typical row: mean + 3 sigma of a Poisson count
+    const double k_hi = k_max + 3.0 * std::sqrt(k_max);
     const bool use_thread_kernel = !(kernel_choice & 1) && !any_rint && packable &&
                                    cand_sum / n_frames <= 200.0 && k_hi <= 64.0;
     if (use_thread_kernel) {
         dim3 tgrid((n_cent + kTpcThreads - 1) / kTpcThreads, n_frames);
-        // an ideal-gas-like (Poisson) neighbour count must not overflow the tile anywhere in a
-        // batch of 1e7 centres, or the whole batch is redone by the warp kernel: 10 sigma
-        if (k_max + 10.0 * std::sqrt(k_max) <= 32.0)
+        if (k_hi <= 32.0)
             neigh_rows_thread_kernel<T, 32><<<tgrid, kTpcThreads, 0, st>>>(a, slot_cell_c);
         else
             neigh_rows_thread_kernel<T, 64><<<tgrid, kTpcThreads, 0, st>>>(a, slot_cell_c);

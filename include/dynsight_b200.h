@@ -98,10 +98,9 @@ int dsg_neigh_fill(const void* d_pos_env, const void* d_pos_cent, int pos_dtype,
  * (status[1] = number of regions actually used, a power of two <= 256).
  * respect_pbc: bit 0 = apply the minimum image; bit 1 = force the warp-per-cell kernel; bit 2 =
  * inclusive cutoff "dr2 <= r_cut^2" (the FastNS rule of analysis/spatial_average.py:39-40)
- * instead of the numba kernels' "dr2 < (r_cut - 1e-6)^2".  Without
- * bit 1 sparse grids use one thread per centre; status[0] == 2 then means that some row exceeded
- * that kernel's staging tile (32 or 64 entries, chosen from the density) and the call must be
- * repeated with bit 1 set. */
+ * instead of the numba kernels' "dr2 < (r_cut - 1e-6)^2".  Without bit 1 sparse grids use one
+ * thread per centre (rows longer than its staging tile are written by a second walk of the same
+ * thread).  status[0] == 2 is reserved: a caller seeing it must repeat the call with bit 1 set. */
 int dsg_neigh_rows(const void* d_pos_env, const void* d_pos_cent, int pos_dtype, int n_frames,
                    int n_env, int n_cent, const double* h_box, double r_cut, int respect_pbc,
                    void* d_workspace, size_t workspace_bytes, int32_t* d_counts,
