@@ -61,7 +61,7 @@ spatial_mean_scalar_kernel(const int* __restrict__ counts, const long long* __re
 }
 
 // Vector descriptor (components contiguous): one warp per (particle, frame); lanes own components
-// (coalesced reads of each neighbour's vector), neighbours are summed in row order.
+// (coalesced reads of each neighbour's vector), neighbours are summed in row order, four at a time.
 __global__ void __launch_bounds__(kSpWarps * 32)
 spatial_mean_vector_kernel(const int* __restrict__ counts, const long long* __restrict__ row_start,
                            const int* __restrict__ rows, int n_frames, int n_cent, int n_comp,
@@ -80,19 +80,44 @@ spatial_mean_vector_kernel(const int* __restrict__ counts, const long long* __re
     const double inv = 1.0 / (double)(n + 1);
     const int* __restrict__ row = rs >= 0 ? rows + rs : nullptr;
     for (int c0 = 0; c0 < n_comp; c0 += 128) {
-        // four components per lane per pass keep four independent gathers in flight
+        // four components per lane and four neighbours per step: 16 independent gathers in flight;
+        // the row's indices are loaded coalesced (lane t holds row[t0 + t]) and broadcast
         double s[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int c = c0 + lane + 32 * u;
             s[u] = c < n_comp ? vf[(long long)i * v_stride_i + c] : 0.0;
         }
-        for (int t = 0; t < (row ? n : 0); ++t) {
-            const double* __restrict__ vj = vf + (long long)row[t] * v_stride_i;
+        const int n_row = row ? n : 0;
+        for (int t0 = 0; t0 < n_row; t0 += 32) {
+            const int mine = t0 + lane < n_row ? row[t0 + lane] : 0;
+            const int m = min(32, n_row - t0);
+            int t = 0;
+            for (; t + 4 <= m; t += 4) {
+                const double* __restrict__ v0 = vf + (long long)__shfl_sync(kFullSp, mine, t) * v_stride_i;
+                const double* __restrict__ v1 = vf + (long long)__shfl_sync(kFullSp, mine, t + 1) * v_stride_i;
+                const double* __restrict__ v2 = vf + (long long)__shfl_sync(kFullSp, mine, t + 2) * v_stride_i;
+                const double* __restrict__ v3 = vf + (long long)__shfl_sync(kFullSp, mine, t + 3) * v_stride_i;
+                double x[4][4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int c = c0 + lane + 32 * u;
-                if (c < n_comp) s[u] += vj[c];
+                for (int u = 0; u < 4; ++u) {
+                    const int c = c0 + lane + 32 * u;
+                    const bool ok = c < n_comp;
+                    x[0][u] = ok ? v0[c] : 0.0;
+                    x[1][u] = ok ? v1[c] : 0.0;
+                    x[2][u] = ok ? v2[c] : 0.0;
+                    x[3][u] = ok ? v3[c] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) s[u] += x[0][u], s[u] += x[1][u], s[u] += x[2][u], s[u] += x[3][u];
+            }
+            for (; t < m; ++t) {
+                const double* __restrict__ vj = vf + (long long)__shfl_sync(kFullSp, mine, t) * v_stride_i;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c = c0 + lane + 32 * u;
+                    if (c < n_comp) s[u] += vj[c];
+                }
             }
         }
 #pragma unroll

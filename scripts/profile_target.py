@@ -1,6 +1,6 @@
 """Small single-purpose launcher for ncu: runs one hot-path stage a few times.
 
-usage: python scripts/profile_target.py soap|neigh|tsoap [atoms] [frames]
+usage: python scripts/profile_target.py soap|soap3|neigh|neigh_fluid|tsoap|tcf|spavg|spavg324 [atoms] [frames]
 """
 import sys
 from pathlib import Path
@@ -19,7 +19,7 @@ g = torch.Generator(device=dev).manual_seed(0)
 if what == "soap3":  # cfg4-like: 3 species, l_max = 10, metal density
     box_l = (n / 0.0857) ** (1 / 3)
     r_cut = 5.0
-elif what == "neigh_fluid":
+elif what in ("neigh_fluid", "spavg", "spavg324"):
     box_l = (n / 0.8) ** (1 / 3)
     r_cut = 1.5
 else:
@@ -44,6 +44,15 @@ for it in range(3):
             out = engine.lens_pairs(nb, 1)
         else:
             out, _ = engine.lens_from_positions(pos, box, r_cut, 1)
+    elif what == "tcf":  # n particles x nf frames, all lags
+        data = torch.randn((n, nf), device=dev, dtype=torch.float64).cumsum(1)
+        out = engine.self_time_correlation_device(data, nf)
+    elif what in ("spavg", "spavg324"):
+        n_comp = 324 if what == "spavg324" else 1
+        vals = torch.rand((n, nf) if n_comp == 1 else (n, nf, n_comp), device=dev, dtype=torch.float64)
+        boxes = np.tile(box.astype(np.float64), (nf, 1))
+        nr = engine.neighbor_rows(engine.wrap_positions(pos, boxes), boxes, r_cut, inclusive_cutoff=True)
+        out = engine.spatial_average_rows(nr, vals, torch.empty_like(vals))
     else:
         soap = torch.rand((n, nf, 324), device=dev, dtype=torch.float64)
         out = engine.timesoap_device(soap, 1)
