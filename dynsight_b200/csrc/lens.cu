@@ -162,6 +162,99 @@ lens_rows_run_kernel(const int* __restrict__ counts, const long long* __restrict
     if (lane < np) out[(long long)i * ld_out + col0 + k0 + lane] = res;
 }
 
+// rows path, delay == 1, short rows: ONE THREAD per centre and a run of kRunPairs consecutive pairs.
+// Both rows of a pair sit in registers (32 values each, loaded in chunks of 8 up to the longest
+// row of the warp, every row is read once and then moves from the "later" to the "earlier" role);
+// every element of the earlier row is compared with the registers of the later one -- a few
+// hundred thread-level instructions per pair instead of a warp-wide shuffle loop that leaves two
+// thirds of the lanes idle on rows of ~10 entries.  A warp that meets a row longer than 32
+// handles its 32 centres with the warp-cooperative intersection.
+constexpr int kLtThreads = 128;
+constexpr int kLtCap = 32;
+
+__device__ __forceinline__ void lt_load_row(int (&r)[kLtCap], const int* __restrict__ rows,
+                                            long long start, int cnt, int warp_max, int fill) {
+#pragma unroll
+    for (int c8 = 0; c8 < kLtCap / 8; ++c8) {
+        const bool need = c8 * 8 < warp_max && warp_max <= kLtCap;   // warp-uniform
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            r[c8 * 8 + j] = (need && c8 * 8 + j < cnt) ? rows[start + c8 * 8 + j] : fill;
+    }
+}
+
+__global__ void __launch_bounds__(kLtThreads)
+lens_rows_thread_kernel(const int* __restrict__ counts, const long long* __restrict__ row_start,
+                        const int* __restrict__ rows, int n_pairs, int n_cent,
+                        double* __restrict__ out, long long ld_out, long long col0) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.y * kLtThreads + threadIdx.x;
+    const int k0 = blockIdx.x * kRunPairs;
+    if (k0 >= n_pairs) return;
+    const bool active = i < n_cent;   // inactive threads stay for the warp-wide operations
+    const int np = min(kRunPairs, n_pairs - k0);
+    int ca = 0;
+    long long sa = -1;
+    if (active) {
+        const size_t idx = (size_t)k0 * n_cent + i;
+        ca = counts[idx];
+        sa = row_start[idx];
+        if (sa < 0) ca = 0;
+    }
+    int maxa = __reduce_max_sync(kFullMask, ca);
+    int a[kLtCap], b[kLtCap];
+    lt_load_row(a, rows, sa, ca, maxa, -2);
+    for (int k = 0; k < np; ++k) {
+        int cb = 0;
+        long long sb = -1;
+        if (active) {
+            const size_t idx = (size_t)(k0 + k + 1) * n_cent + i;
+            cb = counts[idx];
+            sb = row_start[idx];
+            if (sb < 0) cb = 0;
+        }
+        const int maxb = __reduce_max_sync(kFullMask, cb);
+        lt_load_row(b, rows, sb, cb, maxb, -1);
+        int inter = 0;
+        if (maxa <= kLtCap && maxb <= kLtCap) {
+#pragma unroll
+            for (int ca8 = 0; ca8 < kLtCap / 8; ++ca8) {
+                if (ca8 * 8 < maxa) {
+#pragma unroll
+                    for (int ia = 0; ia < 8; ++ia) {
+                        const int av = a[ca8 * 8 + ia];
+                        bool hit = false;
+#pragma unroll
+                        for (int cb8 = 0; cb8 < kLtCap / 8; ++cb8) {
+                            if (cb8 * 8 < maxb) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) hit |= (av == b[cb8 * 8 + j]);
+                            }
+                        }
+                        inter += hit ? 1 : 0;
+                    }
+                }
+            }
+        } else {
+            for (int src = 0; src < 32; ++src) {
+                const int ca_s = __shfl_sync(kFullMask, ca, src), cb_s = __shfl_sync(kFullMask, cb, src);
+                const long long sa_s = __shfl_sync(kFullMask, sa, src);
+                const long long sb_s = __shfl_sync(kFullMask, sb, src);
+                int v = 0;
+                if (ca_s > 0 && cb_s > 0)
+                    v = warp_intersect_unsorted(rows + sa_s, ca_s, rows + sb_s, cb_s, lane);
+                if (lane == src) inter = v;
+            }
+        }
+        if (active) out[(long long)i * ld_out + col0 + k0 + k] = lens_value(ca, cb, inter);
+#pragma unroll
+        for (int j = 0; j < kLtCap; ++j) a[j] = b[j] == -1 ? -2 : b[j];
+        ca = cb;
+        sa = sb;
+        maxa = maxb;
+    }
+}
+
 __global__ void __launch_bounds__(kLensWarps * 32)
 lens_two_csr_kernel(const int* __restrict__ indptr1, const int* __restrict__ indices1,
                     const int* __restrict__ indptr2, const int* __restrict__ indices2, int n_cent,
@@ -256,10 +349,25 @@ extern "C" int dsg_lens_pairs_rows(const int32_t* d_counts, const int64_t* d_row
     if (!d_counts || !d_row_start || !d_rows || !d_out)
         return set_error(DSG_ERR_INVALID_ARGUMENT, "NULL device pointer argument");
     if (n_cent < 1) return set_error(DSG_ERR_INVALID_ARGUMENT, "n_cent=%d out of range", n_cent);
+    // bit 30 of delay: dense rows expected -> warp-per-centre kernel also for delay 1
+    const int delay_flags = (delay >> 30) & 1;
+    delay &= ~(1 << 30);
     if (delay < 1 || delay >= n_frames)
         return set_error(DSG_ERR_INVALID_ARGUMENT, "delay=%d must be in [1, n_frames=%d)", delay,
                          n_frames);
     const int n_pairs = n_frames - delay;
+    if (delay == 1 && (delay_flags & 1) == 0) {
+        const int per_launch = 65535 * kLtThreads;
+        for (int i0 = 0; i0 < n_cent; i0 += per_launch) {
+            const int ni = n_cent - i0 < per_launch ? n_cent - i0 : per_launch;
+            dim3 grid((n_pairs + kRunPairs - 1) / kRunPairs, (ni + kLtThreads - 1) / kLtThreads);
+            lens_rows_thread_kernel<<<grid, kLtThreads, 0, (cudaStream_t)stream>>>(
+                d_counts + i0, (const long long*)d_row_start + i0, d_rows, n_pairs, n_cent,
+                d_out + (long long)i0 * ld_out, ld_out, col0);
+            DSG_LAUNCH_CHECK("lens_rows_thread_kernel");
+        }
+        return DSG_OK;
+    }
     if (delay == 1) {
         const int rows_per_launch = 65535 * kLensWarps;
         for (int i0 = 0; i0 < n_cent; i0 += rows_per_launch) {

@@ -161,6 +161,7 @@ class NeighborRows:
     status: torch.Tensor  # (2 + 256,) int64: [0] overflow flag, [2:] region cursors
     n_frames: int
     n_cent: int
+    k_est: float = 0.0  # expected row length from the density (host estimate)
 
     def overflowed(self) -> bool:
         return bool(self.status[0].item() != 0)
@@ -174,6 +175,8 @@ class NeighborRows:
 
 
 _ROW_PARTS = 256
+_LENS_DENSE_ROWS = 1 << 30  # bit 30 of dsg_lens_pairs_rows' delay: warp-per-centre kernel
+_LENS_THREAD_MAX_K = 24.0  # above this expected row length one warp per centre is faster
 
 
 def neighbor_rows(
@@ -208,9 +211,9 @@ def neighbor_rows(
         n_cent = n_env
     h_box = _host_box(box, n_frames)
     dev = pos_env.device
+    vol = np.prod(np.maximum(h_box, 1e-30), axis=1)
+    k_est = np.minimum(n_env, n_env / vol * 4.18879 * float(r_cut) ** 3)
     if capacity is None:
-        vol = np.prod(np.maximum(h_box, 1e-30), axis=1)
-        k_est = np.minimum(n_env, n_env / vol * 4.18879 * float(r_cut) ** 3)
         capacity = int(1.3 * float(np.sum(k_est)) * n_cent) + _ROW_PARTS * 2048
     capacity = max(int(capacity), _ROW_PARTS) // _ROW_PARTS * _ROW_PARTS
     ws_bytes = ctypes.c_size_t(0)
@@ -235,7 +238,7 @@ def neighbor_rows(
             rows.data_ptr(), capacity, status.data_ptr(), _stream_ptr(),
         )
     )  # fmt: skip
-    return NeighborRows(counts, row_start, rows, status, n_frames, n_cent)
+    return NeighborRows(counts, row_start, rows, status, n_frames, n_cent, float(np.max(k_est)))
 
 
 def lens_pairs_rows(
@@ -253,7 +256,8 @@ def lens_pairs_rows(
     _lib.check(
         lib.dsg_lens_pairs_rows(
             nr.counts.data_ptr(), nr.row_start.data_ptr(), nr.rows.data_ptr(), nr.n_frames,
-            nr.n_cent, int(delay), out.data_ptr(), out.stride(0), int(col0), _stream_ptr(),
+            nr.n_cent, int(delay) | (_LENS_DENSE_ROWS if nr.k_est > _LENS_THREAD_MAX_K else 0),
+            out.data_ptr(), out.stride(0), int(col0), _stream_ptr(),
         )
     )  # fmt: skip
     return out

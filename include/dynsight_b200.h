@@ -107,7 +107,10 @@ int dsg_neigh_rows(const void* d_pos_env, const void* d_pos_cent, int pos_dtype,
                    int64_t* d_row_start, int32_t* d_rows, int64_t rows_capacity,
                    int64_t* d_status, void* stream);
 
-/* LENS over the rows of dsg_neigh_rows (same output contract as dsg_lens_pairs). */
+/* LENS over the rows of dsg_neigh_rows (same output contract as dsg_lens_pairs).  For delay 1 one
+ * thread owns one centre and a run of pairs (both rows of a pair in registers; warps that meet a
+ * row longer than 32 switch to the warp-cooperative intersection).  Bit 30 of `delay` = rows are
+ * expected to be long (more than ~24 entries): one warp per centre from the start. */
 int dsg_lens_pairs_rows(const int32_t* d_counts, const int64_t* d_row_start,
                         const int32_t* d_rows, int n_frames, int n_cent, int delay, double* d_out,
                         int64_t ld_out, int64_t col0, void* stream);

@@ -396,3 +396,23 @@ def test_rows_path_near_threshold_pairs_in_a_large_box(force_warp):
     _check_rows_vs_oracle(nr, frames, None, box, r_cut, True)
     counts = nr.counts.cpu().numpy()
     assert 0.2 < (counts[0, :n_pairs] > 0).mean() < 0.8  # both outcomes occur
+
+
+def test_lens_rows_thread_and_warp_kernels_agree_on_mixed_rows():
+    """delay 1: thread-per-centre LENS kernel (short rows), its in-kernel switch for warps that
+    hold a row longer than 32, and the warp-per-centre kernel (bit 30) give identical results."""
+    from dynsight_b200 import _lib, engine
+
+    pos, box, r_cut = fluid_case(n_side=16, n_frames=5)
+    dense = pos.copy()
+    dense[:, :80] = (dense[:, :80] % 1.0) * 0.9 + 0.05   # rows of > 32 entries for some centres
+    dims = np.tile(np.concatenate([box, [90, 90, 90]]).astype(np.float32), (5, 1))
+    want = lo.compute_lens_arrays(dense, dims, r_cut)
+    nr = engine.neighbor_rows(_dev(dense), box, r_cut, None, True)
+    assert not nr.overflowed() and int(nr.counts.max()) > 32
+    got_thread = engine.lens_pairs_rows(nr, 1)
+    nr.k_est = 1e9  # force the dense-rows flag
+    got_warp = engine.lens_pairs_rows(nr, 1)
+    assert np.array_equal(got_thread.cpu().numpy(), want)
+    assert np.array_equal(got_warp.cpu().numpy(), want)
+    del _lib
