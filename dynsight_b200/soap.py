@@ -127,12 +127,18 @@ def fill_soap_vector_from_dscribe(
     soapfromdscribe: NDArray[np.float64],
     lmax: int = 8,
     nmax: int = 8,
+    n_species: int = 1,
 ) -> NDArray[np.float64]:
-    """Return the full SOAP spectrum with the symmetric part explicitly stored (single species).
+    """Return the full SOAP spectrum with the symmetric part explicitly stored.
 
     Expands the ``(l+1, n(n+1)/2)`` upper triangles to ``(l+1, n, n)`` symmetric blocks; accepts
     1-D, 2-D or 3-D input like the reference (saponify.py:176-202).  Pure data movement on the
     host: it is not on the timed hot path.
+
+    ``n_species > 1`` (extension; the reference handles one species
+    only): the input is DScribe's multi-species layout -- species pairs ``Z <= Z'``, then ``l``,
+    then ``(n, n')`` (upper triangle for ``Z == Z'``, full ``n x n`` otherwise) -- and the output
+    holds, per ``l``, the symmetric ``(S n) x (S n)`` matrix with row index ``Z n_max + n``.
     """
     input_shape = soapfromdscribe.shape
     arr = np.asarray(soapfromdscribe)
@@ -142,10 +148,38 @@ def fill_soap_vector_from_dscribe(
         arr = arr[:, np.newaxis, :]
     n_particles, n_frames, _ = arr.shape
     upper = np.triu_indices(nmax)
-    tri = arr.reshape(n_particles, n_frames, lmax + 1, -1)
-    full = np.zeros((n_particles, n_frames, lmax + 1, nmax, nmax))
-    full[:, :, :, upper[0], upper[1]] = tri
-    full[:, :, :, upper[1], upper[0]] = tri
+    if n_species == 1:
+        tri = arr.reshape(n_particles, n_frames, lmax + 1, -1)
+        full = np.zeros((n_particles, n_frames, lmax + 1, nmax, nmax))
+        full[:, :, :, upper[0], upper[1]] = tri
+        full[:, :, :, upper[1], upper[0]] = tri
+    else:
+        sn = n_species * nmax
+        expected = sn * (sn + 1) // 2 * (lmax + 1)
+        if arr.shape[2] != expected:
+            msg = f"{arr.shape[2]} components, expected {expected} for {n_species} species"
+            raise ValueError(msg)
+        full = np.zeros((n_particles, n_frames, lmax + 1, sn, sn))
+        pos = 0
+        for zi in range(n_species):
+            for zj in range(zi, n_species):
+                rows = slice(zi * nmax, (zi + 1) * nmax)
+                cols = slice(zj * nmax, (zj + 1) * nmax)
+                if zi == zj:
+                    size = (lmax + 1) * upper[0].size
+                    tri = arr[:, :, pos : pos + size].reshape(n_particles, n_frames, lmax + 1, -1)
+                    block = np.zeros((n_particles, n_frames, lmax + 1, nmax, nmax))
+                    block[:, :, :, upper[0], upper[1]] = tri
+                    block[:, :, :, upper[1], upper[0]] = tri
+                    full[:, :, :, rows, cols] = block
+                else:
+                    size = (lmax + 1) * nmax * nmax
+                    block = arr[:, :, pos : pos + size].reshape(
+                        n_particles, n_frames, lmax + 1, nmax, nmax
+                    )
+                    full[:, :, :, rows, cols] = block
+                    full[:, :, :, cols, rows] = np.swapaxes(block, -1, -2)
+                pos += size
     output = full.reshape(n_particles, n_frames, -1)
     if len(input_shape) == 1:
         return output.squeeze()

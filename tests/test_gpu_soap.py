@@ -172,3 +172,34 @@ def test_invariances_at_bench_scale():
     two = torch.cat([base, base], dim=1)
     assert float(engine.timesoap_device(two, 1).abs().max()) <= 1e-7
     _ = to
+
+
+def test_multi_species_invariances_at_cfg4_parameters():
+    """BASELINE cfg4 parameters (3 species by index hash, l_max = 10, metal density) on 8000 atoms:
+    split mode (accumulate kernel + spectrum kernel).  Permutation + translation + axis rotation
+    leave the spectra unchanged and a few centres agree with the oracle."""
+    from dynsight_b200 import engine
+
+    rng = np.random.default_rng(4)
+    n = 8_000
+    box_l = (n / 0.0857) ** (1 / 3)
+    pos = (rng.random((1, n, 3)) * box_l).astype(np.float64)
+    box = np.full(3, box_l)
+    sp_idx = (np.arange(n) * 7919) % 3
+    cen = torch.arange(n, dtype=torch.int32, device="cuda")
+    base = engine.soap_power_spectrum(
+        torch.as_tensor(pos).cuda(), torch.as_tensor(sp_idx, dtype=torch.int32).cuda(), cen, box,
+        5.0, 8, 10, n_species=3,
+    )  # fmt: skip
+    assert base.shape == (n, 1, 3300)
+    perm = rng.permutation(n)
+    pos2 = (pos[:, :, [2, 0, 1]] + np.array([-4.2, 9.9, 1.7]))[:, perm]
+    other = engine.soap_power_spectrum(
+        torch.as_tensor(pos2).cuda(), torch.as_tensor(sp_idx[perm], dtype=torch.int32).cuda(), cen,
+        box, 5.0, 8, 10, n_species=3,
+    )  # fmt: skip
+    assert _rel_err(other.cpu().numpy()[:, 0], base.cpu().numpy()[perm, 0]) < 1e-9
+    pick = np.arange(0, n, n // 6)[:6]
+    zs = np.array([13, 28, 29])
+    want = so.soap_trajectory(pos, zs[sp_idx], pick, np.tile(box, (1, 1)), 5.0, 8, 10)
+    assert _rel_err(base.cpu().numpy()[pick], want) < REL

@@ -142,6 +142,31 @@ def test_fill_soap_vector_shapes():
     assert np.array_equal(full, soap_oracle.fill_soap_vector(x))
 
 
+def test_fill_soap_vector_multi_species_extension():
+    """Extension of saponify.py:127-202 to DScribe's multi-species layout: per l the symmetric
+    (S n) x (S n) matrix; the power spectrum p^{ZZ'}_{nn'} = p^{Z'Z}_{n'n} fixes the transpose."""
+    from dynsight_b200 import soap
+
+    rng = np.random.default_rng(0)
+    s_, n, lm = 3, 4, 2
+    c = rng.normal(size=(lm + 1, s_ * n, 5))          # fake coefficients c[l][Zn][m]
+    p = np.einsum("lam,lbm->lab", c, c)                # symmetric (S n) x (S n) per l
+    flat = []
+    for zi in range(s_):
+        for zj in range(zi, s_):
+            for l in range(lm + 1):
+                blk = p[l, zi * n:(zi + 1) * n, zj * n:(zj + 1) * n]
+                flat.append(blk[np.triu_indices(n)] if zi == zj else blk.ravel())
+    vec = np.concatenate(flat)
+    full = soap.fill_soap_vector_from_dscribe(vec, lmax=lm, nmax=n, n_species=s_)
+    assert full.shape == ((lm + 1) * (s_ * n) ** 2,)
+    assert np.allclose(full.reshape(lm + 1, s_ * n, s_ * n), p)
+    assert soap.fill_soap_vector_from_dscribe(np.tile(vec, (2, 3, 1)), lm, n, s_).shape == (
+        2, 3, full.size)  # fmt: skip
+    with pytest.raises(ValueError, match="expected"):
+        soap.fill_soap_vector_from_dscribe(vec[:-1], lm, n, s_)
+
+
 def test_api_errors_without_gpu(balls7):
     """Errors the reference raises before any compute must not need a GPU either."""
     from dynsight_b200.trajectory import Insight, Trj

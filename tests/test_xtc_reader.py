@@ -44,7 +44,8 @@ def _synthetic(rng: np.random.Generator, n_groups: int, spread: int, smallidx: i
 
 
 @pytest.mark.parametrize(("spread", "smallidx", "precision"),
-                         [(3000, 21, 1000.0), (200, 12, 100.0), (2_000_000, 30, 1000.0)])  # fmt: skip
+                         [(3000, 21, 1000.0), (200, 12, 100.0), (2_000_000, 30, 1000.0),
+                          (40_000_000, 33, 1000.0)])  # fmt: skip  (last: sizes above 2^24)
 def test_reader_decodes_written_frames(tmp_path, spread, smallidx, precision):
     rng = np.random.default_rng(spread + smallidx)
     frames, expect = [], []

@@ -72,15 +72,24 @@ def write_frame(coords: np.ndarray, box_nm: np.ndarray, step: int, time: float, 
     minint = coords.min(axis=0)
     maxint = coords.max(axis=0)
     sizes = tuple(int(v) for v in (maxint - minint + 1))
-    assert max(sizes) <= 0xFFFFFF  # noqa: PLR2004
-    bitsize = bits_for_product(sizes)
+    wide = max(sizes) > 0xFFFFFF  # noqa: PLR2004  -> three fixed-width fields per full triple
+    bitsize = 0 if wide else bits_for_product(sizes)
+    field_bits = [int(v).bit_length() for v in sizes]  # bits for one value in [0, size]
     bw = BitWriter()
+
+    def put_full(vals: tuple[int, int, int]) -> None:
+        if wide:
+            for v, nb in zip(vals, field_bits):
+                bw.put(v, nb)
+        else:
+            bw.put_triple(vals, sizes, bitsize)
+
     idx = smallidx
     a = 0
     run = 0  # the decoder keeps the last run length until a flag bit changes it
     for kind, adapt in layout:
         if kind == "single":
-            bw.put_triple(tuple(int(v) for v in coords[a] - minint), sizes, bitsize)
+            put_full(tuple(int(v) for v in coords[a] - minint))
             if run == 0:
                 bw.put(0, 1)  # no run information: the previous run length (0) stays
             else:
@@ -94,7 +103,7 @@ def write_frame(coords: np.ndarray, box_nm: np.ndarray, step: int, time: float, 
         small = MAGICINTS[idx]
         smallnum = small // 2
         p0, p1, p2 = (coords[a + k].astype(np.int64) for k in range(3))
-        bw.put_triple(tuple(int(v) for v in p1 - minint), sizes, bitsize)
+        put_full(tuple(int(v) for v in p1 - minint))
         if run == 6 and adapt == 0:  # noqa: PLR2004
             bw.put(0, 1)  # same run length as the previous group, no adaptation
         else:
