@@ -132,24 +132,44 @@ class FrameNeighbours(Sequence):
 
 
 class NeighbourList(Sequence):
-    """``list[list[AtomGroup]]`` of the reference, materialised lazily.
+    """``list[list[AtomGroup]]`` of the reference, materialised lazily -- twice over.
 
     The reference builds one AtomGroup per centre and frame in a Python loop (lens.py:383-388),
-    which dominates its run time; here the CSR arrays are kept and an AtomGroup is only created
-    when an element is accessed.  ``counts`` (n_frames, n_centers) gives the coordination numbers
-    without touching any AtomGroup.
+    which dominates its run time.  Here only the coordination numbers ``counts_device``
+    (n_frames, n_centers) are computed up front (single-traversal rows path, nothing sorted, nothing
+    copied to the host): that is all ``Trj.get_coord_number`` needs.  The canonical CSR (rows
+    ascending, numba-identical ``indptr``) is built on the first access to ``indptr`` /
+    ``frame_off`` / ``indices`` or to any element, and an AtomGroup is only created when an element
+    is accessed.
     """
 
-    def __init__(self, ag_env: Any, counts: torch.Tensor, indptr: np.ndarray,
-                 frame_off: np.ndarray, indices: np.ndarray) -> None:  # fmt: skip
+    def __init__(self, ag_env: Any, counts: torch.Tensor,
+                 build_csr: Any) -> None:  # fmt: skip
         self._ag_env = ag_env
         self.counts_device = counts  # (F, M) int32 CUDA
-        self.indptr = indptr  # (F, M+1) int32 host
-        self.frame_off = frame_off
-        self.indices = indices
+        self._build_csr = build_csr  # () -> (indptr (F, M+1) i32, frame_off (F+1) i64, indices)
+        self._csr: tuple[np.ndarray, np.ndarray, np.ndarray] | None = None
+
+    def _ensure(self) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+        if self._csr is None:
+            self._csr = self._build_csr()
+            self._build_csr = None
+        return self._csr
+
+    @property
+    def indptr(self) -> np.ndarray:
+        return self._ensure()[0]
+
+    @property
+    def frame_off(self) -> np.ndarray:
+        return self._ensure()[1]
+
+    @property
+    def indices(self) -> np.ndarray:
+        return self._ensure()[2]
 
     def __len__(self) -> int:
-        return self.indptr.shape[0]
+        return int(self.counts_device.shape[0])
 
     def __getitem__(self, f: int) -> FrameNeighbours:  # type: ignore[override]
         if isinstance(f, slice):
@@ -187,27 +207,45 @@ def list_neighbours_along_trajectory(
     ix_env = np.asarray(ag_env.indices)
     ix_cent = np.asarray(ag_centers.indices)
     same = ix_env.shape == ix_cent.shape and bool(np.array_equal(ix_env, ix_cent))
-    counts, indptrs, offs, idxs = [], [], [0], []
-    if fr_idx:
-        batch_frames = frames.pick_batch_frames(max(ix_env.size, ix_cent.size), 160.0, 1)
+    sel_env, sel_cent = frames.Selection(ix_env, n_all), frames.Selection(ix_cent, n_all)
+    batch_frames = frames.pick_batch_frames(max(ix_env.size, ix_cent.size, 1), 160.0, 1)
+
+    def batches() -> Iterator[tuple]:
         for fb in frames.iter_batches(universe, fr_idx, batch_frames):
             box = frames.lens_boxes(fb, None)  # no 1.01 factor here (lens.py:368-371)
-            pos_env = fb.select(ix_env, n_all)
-            pos_cent = None if same else fb.select(ix_cent, n_all)
+            pos_env = fb.select(sel_env, n_all)
+            pos_cent = None if same else fb.select(sel_cent, n_all)
+            yield pos_env, pos_cent, box
+
+    def build_csr() -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+        indptrs, offs, idxs = [], [0], []
+        for pos_env, pos_cent, box in batches():
             nb = engine.neighbor_lists(pos_env, box, r_cut, pos_cent, respect_pbc)
-            counts.append(nb.counts)
             indptrs.append(nb.indptr.cpu().numpy())
             fo = nb.frame_off.cpu().numpy()
             offs.extend((fo[1:] + offs[-1]).tolist())
             idxs.append(nb.indices.cpu().numpy())
-    if not counts:
-        dev_counts = torch.empty((0, ix_cent.size), dtype=torch.int32, device=frames.device())
-        return NeighbourList(ag_env, dev_counts, np.zeros((0, ix_cent.size + 1), np.int32),
-                             np.zeros(1, np.int64), np.zeros(0, np.int32))  # fmt: skip
-    return NeighbourList(
-        ag_env,
-        torch.cat(counts, dim=0),
-        np.concatenate(indptrs, axis=0),
-        np.asarray(offs, dtype=np.int64),
-        np.concatenate(idxs),
-    )
+        if not indptrs:
+            return (np.zeros((0, ix_cent.size + 1), np.int32), np.zeros(1, np.int64),
+                    np.zeros(0, np.int32))  # fmt: skip
+        return (np.concatenate(indptrs, axis=0), np.asarray(offs, dtype=np.int64),
+                np.concatenate(idxs))  # fmt: skip
+
+    counts = []
+    if fr_idx:
+        for pos_env, pos_cent, box in batches():
+            capacity = None
+            force_warp = False
+            while True:  # counts only: rows are written to a scratch buffer and dropped
+                nr = engine.neighbor_rows(pos_env, box, r_cut, pos_cent, respect_pbc, capacity,
+                                          force_warp)  # fmt: skip
+                if not nr.overflowed():
+                    break
+                if nr.needs_warp_kernel():
+                    force_warp = True
+                else:
+                    capacity = int(nr.needed_capacity() * 1.1) + 2048 * 256
+            counts.append(nr.counts)
+    dev_counts = (torch.cat(counts, dim=0) if counts else
+                  torch.empty((0, ix_cent.size), dtype=torch.int32, device=frames.device()))  # fmt: skip
+    return NeighbourList(ag_env, dev_counts, build_csr)

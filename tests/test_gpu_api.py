@@ -252,3 +252,15 @@ def test_psi_phi_doctest_and_random_vs_oracle(xyz60, ref_lens):
                                    atol=1e-6)  # fmt: skip
     np.testing.assert_allclose(descriptors.velocity_alignment(u, neig),
                                do.velocity_alignment(pos, csr), rtol=1e-5, atol=1e-6)  # fmt: skip
+
+
+def test_coord_number_does_not_materialise_the_lists(trj, ref_lens):
+    """Trj.get_coord_number needs the counts only: the canonical CSR (two traversals, row sorts,
+    device -> host copy of all indices) is built on the first access to an element."""
+    neigh, got = trj.get_coord_number(r_cut=4, centers="all", selection="all")
+    assert neigh._csr is None  # noqa: SLF001
+    assert np.array_equal(ref_lens["nn_c1"], got.dataset)
+    first = neigh[0][0]
+    assert neigh._csr is not None  # noqa: SLF001
+    assert len(first) == int(got.dataset[0, 0])
+    assert [len(ag) for ag in neigh[5]] == [int(v) for v in got.dataset[:, 5]]
