@@ -31,24 +31,29 @@ def _all_positions(universe: Any) -> torch.Tensor:
 
 
 def _device_csr(neigh_list_per_frame: Any, n_atoms: int) -> engine.NeighborBatch:
-    """CSR of a neighbour list on the device: the lazy NeighbourList keeps host arrays; a plain
-    ``list[list[AtomGroup]]`` is flattened through ``.indices``."""
+    """CSR of a neighbour list on the device: the lazy NeighbourList hands out its device-resident
+    canonical CSR; a plain ``list[list[AtomGroup]]`` is flattened through ``.indices``."""
     dev = frames.device()
     if isinstance(neigh_list_per_frame, NeighbourList):
-        indptr, frame_off, indices = (neigh_list_per_frame.indptr, neigh_list_per_frame.frame_off,
-                                      neigh_list_per_frame.indices)  # fmt: skip
-        counts = neigh_list_per_frame.counts_device
-    else:
-        rows = [[np.asarray(ag.indices, dtype=np.int32) for ag in fr] for fr in neigh_list_per_frame]
-        indptr = np.zeros((len(rows), n_atoms + 1), dtype=np.int32)
-        flat, offs = [], [0]
-        for f, fr in enumerate(rows):
-            indptr[f, 1:] = np.cumsum([len(r) for r in fr])
-            flat.extend(fr)
-            offs.append(offs[-1] + int(indptr[f, -1]))
-        indices = np.concatenate(flat) if flat else np.zeros(0, np.int32)
-        frame_off = np.asarray(offs, dtype=np.int64)
-        counts = torch.as_tensor(np.diff(indptr, axis=1), device=dev)
+        nb = neigh_list_per_frame.device_batch()  # stays on the device: no host round trip
+        if nb.n_cent != n_atoms:
+            msg = "the neighbour list must hold one entry per atom of the universe (centers='all')"
+            raise ValueError(msg)
+        if nb.indices.numel() == 0:
+            nb = engine.NeighborBatch(nb.counts, nb.indptr, nb.frame_off,
+                                      torch.zeros(1, dtype=torch.int32, device=dev), nb.n_frames,
+                                      nb.n_cent)  # fmt: skip
+        return nb
+    rows = [[np.asarray(ag.indices, dtype=np.int32) for ag in fr] for fr in neigh_list_per_frame]
+    indptr = np.zeros((len(rows), n_atoms + 1), dtype=np.int32)
+    flat, offs = [], [0]
+    for f, fr in enumerate(rows):
+        indptr[f, 1:] = np.cumsum([len(r) for r in fr])
+        flat.extend(fr)
+        offs.append(offs[-1] + int(indptr[f, -1]))
+    indices = np.concatenate(flat) if flat else np.zeros(0, np.int32)
+    frame_off = np.asarray(offs, dtype=np.int64)
+    counts = torch.as_tensor(np.diff(indptr, axis=1), device=dev)
     if indptr.shape[1] != n_atoms + 1:
         msg = "the neighbour list must hold one entry per atom of the universe (centers='all')"
         raise ValueError(msg)

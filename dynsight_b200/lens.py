@@ -147,13 +147,22 @@ class NeighbourList(Sequence):
                  build_csr: Any) -> None:  # fmt: skip
         self._ag_env = ag_env
         self.counts_device = counts  # (F, M) int32 CUDA
-        self._build_csr = build_csr  # () -> (indptr (F, M+1) i32, frame_off (F+1) i64, indices)
+        self._build_csr = build_csr  # () -> engine.NeighborBatch covering all frames (device)
+        self._batch: engine.NeighborBatch | None = None
         self._csr: tuple[np.ndarray, np.ndarray, np.ndarray] | None = None
+
+    def device_batch(self) -> engine.NeighborBatch:
+        """Canonical CSR of all frames on the device (built once; what the psi / phi kernels read)."""
+        if self._batch is None:
+            self._batch = self._build_csr()
+            self._build_csr = None
+        return self._batch
 
     def _ensure(self) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
         if self._csr is None:
-            self._csr = self._build_csr()
-            self._build_csr = None
+            nb = self.device_batch()
+            self._csr = (nb.indptr.cpu().numpy(), nb.frame_off.cpu().numpy(),
+                         nb.indices.cpu().numpy())  # fmt: skip
         return self._csr
 
     @property
@@ -217,19 +226,29 @@ def list_neighbours_along_trajectory(
             pos_cent = None if same else fb.select(sel_cent, n_all)
             yield pos_env, pos_cent, box
 
-    def build_csr() -> tuple[np.ndarray, np.ndarray, np.ndarray]:
-        indptrs, offs, idxs = [], [0], []
-        for pos_env, pos_cent, box in batches():
-            nb = engine.neighbor_lists(pos_env, box, r_cut, pos_cent, respect_pbc)
-            indptrs.append(nb.indptr.cpu().numpy())
-            fo = nb.frame_off.cpu().numpy()
-            offs.extend((fo[1:] + offs[-1]).tolist())
-            idxs.append(nb.indices.cpu().numpy())
-        if not indptrs:
-            return (np.zeros((0, ix_cent.size + 1), np.int32), np.zeros(1, np.int64),
-                    np.zeros(0, np.int32))  # fmt: skip
-        return (np.concatenate(indptrs, axis=0), np.asarray(offs, dtype=np.int64),
-                np.concatenate(idxs))  # fmt: skip
+    def build_csr() -> engine.NeighborBatch:
+        dev = frames.device()
+        parts = [engine.neighbor_lists(pos_env, box, r_cut, pos_cent, respect_pbc)
+                 for pos_env, pos_cent, box in batches()]  # fmt: skip
+        if not parts:
+            return engine.NeighborBatch(
+                torch.empty((0, ix_cent.size), dtype=torch.int32, device=dev),
+                torch.zeros((0, ix_cent.size + 1), dtype=torch.int32, device=dev),
+                torch.zeros(1, dtype=torch.int64, device=dev),
+                torch.zeros(0, dtype=torch.int32, device=dev), 0, ix_cent.size,
+            )  # fmt: skip
+        if len(parts) == 1:
+            return parts[0]
+        offs = [torch.zeros(1, dtype=torch.int64, device=dev)]
+        base = 0
+        for nb in parts:
+            offs.append(nb.frame_off[1:] + base)
+            base += int(nb.frame_off[-1].item())
+        return engine.NeighborBatch(
+            torch.cat([nb.counts for nb in parts]), torch.cat([nb.indptr for nb in parts]),
+            torch.cat(offs), torch.cat([nb.indices for nb in parts]),
+            sum(nb.n_frames for nb in parts), ix_cent.size,
+        )  # fmt: skip
 
     counts = []
     if fr_idx:

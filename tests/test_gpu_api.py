@@ -258,9 +258,9 @@ def test_coord_number_does_not_materialise_the_lists(trj, ref_lens):
     """Trj.get_coord_number needs the counts only: the canonical CSR (two traversals, row sorts,
     device -> host copy of all indices) is built on the first access to an element."""
     neigh, got = trj.get_coord_number(r_cut=4, centers="all", selection="all")
-    assert neigh._csr is None  # noqa: SLF001
+    assert neigh._batch is None and neigh._csr is None  # noqa: SLF001
     assert np.array_equal(ref_lens["nn_c1"], got.dataset)
     first = neigh[0][0]
-    assert neigh._csr is not None  # noqa: SLF001
+    assert neigh._batch is not None and neigh._csr is not None  # noqa: SLF001
     assert len(first) == int(got.dataset[0, 0])
     assert [len(ag) for ag in neigh[5]] == [int(v) for v in got.dataset[:, 5]]
