@@ -83,6 +83,13 @@ SIGNATURES: dict[str, tuple] = {
         [_c_ptr, _c_int, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_int, _c_ptr, _c_dbl, _c_int,
          _c_int, _c_ptr, _c_ptr, _c_ptr, _c_size, _c_ptr, _c_i64, _c_i64, _c_ptr],
     ),
+    "dsg_rows_csr_workspace_bytes": (_c_int, [_c_int, _c_int, ctypes.POINTER(_c_size)]),
+    "dsg_rows_csr_offsets": (
+        _c_int, [_c_ptr, _c_int, _c_int, _c_ptr, _c_size, _c_ptr, _c_ptr, _c_ptr],
+    ),
+    "dsg_rows_to_csr": (
+        _c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_ptr, _c_ptr],
+    ),
     "dsg_wrap_positions": (_c_int, [_c_ptr, _c_int, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr]),
     "dsg_spatial_average_rows": (
         _c_int,

@@ -473,6 +473,28 @@ neigh_kernel(const NeighArgs a) {
     }
 }
 
+// Canonical CSR from the single-traversal rows: one warp per (frame, centre) copies the row to
+// its place in the frame's CSR (coalesced) and sorts it there (same sorter as the FILL kernel).
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+rows_to_csr_kernel(const int* __restrict__ counts, const long long* __restrict__ row_start,
+                   const int* __restrict__ rows, const int* __restrict__ indptr,
+                   const long long* __restrict__ frame_off, int n_frames, int n_cent,
+                   int* __restrict__ indices) {
+    __shared__ int sort_tile[kWarpsPerBlock][kStageCap * 4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * kWarpsPerBlock + warp;
+    if (w >= (long long)n_frames * n_cent) return;
+    const int f = (int)(w / n_cent), i = (int)(w - (long long)f * n_cent);
+    const int n = counts[w];
+    const long long src0 = row_start[w];
+    if (n <= 0 || src0 < 0) return;
+    const int* __restrict__ src = rows + src0;
+    int* dst = indices + frame_off[f] + indptr[(size_t)f * (n_cent + 1) + i];
+    for (int t = lane; t < n; t += 32) dst[t] = src[t];
+    __syncwarp();
+    warp_sort_row(dst, n, sort_tile[warp], lane);
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -1295,4 +1317,54 @@ extern "C" int dsg_neigh_rows(const void* d_pos_env, const void* d_pos_cent, int
                                        respect_pbc >> 1, st);
     return set_error(DSG_ERR_INVALID_ARGUMENT, "pos_dtype=%d is neither DSG_F32 nor DSG_F64",
                      pos_dtype);
+}
+
+extern "C" int dsg_rows_csr_workspace_bytes(int n_frames, int n_cent, size_t* bytes_out) {
+    if (!bytes_out) return set_error(DSG_ERR_INVALID_ARGUMENT, "bytes_out is NULL");
+    if (n_frames < 1 || n_cent < 1)
+        return set_error(DSG_ERR_INVALID_ARGUMENT, "n_frames=%d, n_cent=%d must be >= 1", n_frames,
+                         n_cent);
+    const size_t tiles = (size_t)n_frames * (((size_t)n_cent + kScanTile - 1) / kScanTile);
+    *bytes_out = align_up(4 * tiles) + align_up(8 * (size_t)n_frames);
+    return DSG_OK;
+}
+
+extern "C" int dsg_rows_csr_offsets(const int32_t* d_counts, int n_frames, int n_cent,
+                                    void* d_workspace, size_t workspace_bytes, int32_t* d_indptr,
+                                    int64_t* d_frame_off, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t need = 0;
+    int rc = dsg_rows_csr_workspace_bytes(n_frames, n_cent, &need);
+    if (rc) return rc;
+    if (!d_counts || !d_workspace || !d_indptr || !d_frame_off)
+        return set_error(DSG_ERR_INVALID_ARGUMENT, "NULL device pointer argument");
+    if (workspace_bytes < need)
+        return set_error(DSG_ERR_WORKSPACE_TOO_SMALL, "workspace has %zu bytes, %zu needed",
+                         workspace_bytes, need);
+    const size_t tiles = (size_t)n_frames * (((size_t)n_cent + kScanTile - 1) / kScanTile);
+    int* tile_tmp = (int*)d_workspace;
+    long long* seg_totals = (long long*)((char*)d_workspace + align_up(4 * tiles));
+    rc = run_scan(d_counts, n_cent, n_frames, d_indptr, tile_tmp, seg_totals, st);
+    if (rc) return rc;
+    frame_offsets_kernel<<<1, 32, 0, st>>>(seg_totals, n_frames, (long long*)d_frame_off);
+    DSG_LAUNCH_CHECK("frame_offsets_kernel");
+    return DSG_OK;
+}
+
+extern "C" int dsg_rows_to_csr(const int32_t* d_counts, const int64_t* d_row_start,
+                               const int32_t* d_rows, const int32_t* d_indptr,
+                               const int64_t* d_frame_off, int n_frames, int n_cent,
+                               int32_t* d_indices, void* stream) {
+    if (!d_counts || !d_row_start || !d_rows || !d_indptr || !d_frame_off || !d_indices)
+        return set_error(DSG_ERR_INVALID_ARGUMENT, "NULL device pointer argument");
+    if (n_frames < 1 || n_cent < 1)
+        return set_error(DSG_ERR_INVALID_ARGUMENT, "n_frames=%d, n_cent=%d must be >= 1", n_frames,
+                         n_cent);
+    const long long warps = (long long)n_frames * n_cent;
+    const unsigned blocks = (unsigned)((warps + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    rows_to_csr_kernel<<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+        d_counts, (const long long*)d_row_start, d_rows, d_indptr, (const long long*)d_frame_off,
+        n_frames, n_cent, d_indices);
+    DSG_LAUNCH_CHECK("rows_to_csr_kernel");
+    return DSG_OK;
 }

@@ -91,11 +91,17 @@ def neighbor_lists(
     pos_cent: torch.Tensor | None = None,
     respect_pbc: bool = True,
     counts_only: bool = False,
+    two_pass: bool = False,
 ) -> NeighborBatch:
     """Sorted CSR neighbour lists for every frame of a batch.
 
     ``pos_env`` (F, N, 3) and optional ``pos_cent`` (F, M, 3): CUDA float32/float64.
     ``box`` (F, 3) or (3,) box lengths (host).  ``pos_cent=None`` means centres == env atoms.
+
+    Default: the single-traversal rows path followed by a copy-and-sort of every row into its
+    canonical CSR place (``dsg_rows_csr_offsets`` + ``dsg_rows_to_csr``).  ``two_pass=True`` uses
+    the count / fill protocol (``dsg_neigh_count`` + ``dsg_neigh_fill``, two traversals); both give
+    identical arrays.
     """
     lib = _lib.load()
     _require_cuda(pos_env, "pos_env")
@@ -113,6 +119,8 @@ def neighbor_lists(
     else:
         n_cent = n_env
     h_box = _host_box(box, n_frames)
+    if not two_pass and not counts_only:
+        return _neighbor_lists_from_rows(pos_env, h_box, r_cut, pos_cent, respect_pbc)
     dev = pos_env.device
     ws_bytes = ctypes.c_size_t(0)
     _lib.check(
@@ -146,6 +154,48 @@ def neighbor_lists(
         )
     )
     return NeighborBatch(counts, indptr, frame_off, indices[:nnz], n_frames, n_cent)
+
+
+def _neighbor_lists_from_rows(
+    pos_env: torch.Tensor,
+    box: np.ndarray | torch.Tensor,
+    r_cut: float,
+    pos_cent: torch.Tensor | None,
+    respect_pbc: bool,
+) -> NeighborBatch:
+    lib = _lib.load()
+    capacity = None
+    force_warp = False
+    while True:
+        nr = neighbor_rows(pos_env, box, r_cut, pos_cent, respect_pbc, capacity, force_warp)
+        if not nr.overflowed():
+            break
+        if nr.needs_warp_kernel():
+            force_warp = True
+        else:
+            capacity = int(nr.needed_capacity() * 1.1) + _ROW_PARTS * 2048
+    dev = pos_env.device
+    n_frames, n_cent = nr.n_frames, nr.n_cent
+    ws_bytes = ctypes.c_size_t(0)
+    _lib.check(lib.dsg_rows_csr_workspace_bytes(n_frames, n_cent, ctypes.byref(ws_bytes)))
+    workspace = torch.empty(ws_bytes.value, dtype=torch.uint8, device=dev)
+    indptr = torch.empty((n_frames, n_cent + 1), dtype=torch.int32, device=dev)
+    frame_off = torch.empty(n_frames + 1, dtype=torch.int64, device=dev)
+    _lib.check(
+        lib.dsg_rows_csr_offsets(
+            nr.counts.data_ptr(), n_frames, n_cent, workspace.data_ptr(), ws_bytes.value,
+            indptr.data_ptr(), frame_off.data_ptr(), _stream_ptr(),
+        )
+    )
+    nnz = int(frame_off[-1].item())
+    indices = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    _lib.check(
+        lib.dsg_rows_to_csr(
+            nr.counts.data_ptr(), nr.row_start.data_ptr(), nr.rows.data_ptr(), indptr.data_ptr(),
+            frame_off.data_ptr(), n_frames, n_cent, indices.data_ptr(), _stream_ptr(),
+        )
+    )
+    return NeighborBatch(nr.counts, indptr, frame_off, indices[:nnz], n_frames, n_cent)
 
 
 @dataclass

@@ -107,6 +107,22 @@ int dsg_neigh_rows(const void* d_pos_env, const void* d_pos_cent, int pos_dtype,
                    int64_t* d_row_start, int32_t* d_rows, int64_t rows_capacity,
                    int64_t* d_status, void* stream);
 
+/* Canonical CSR (what dsg_neigh_count + dsg_neigh_fill produce: numba-identical indptr, rows
+ * ascending -- lens.py:108-145) from the rows of dsg_neigh_rows, i.e. with ONE traversal of the
+ * cell list instead of two:
+ *   dsg_rows_csr_offsets: indptr (n_frames, n_cent+1) frame-local exclusive scan of the counts and
+ *     frame_off (n_frames+1); the caller reads frame_off[n_frames] (nnz) and allocates d_indices;
+ *   dsg_rows_to_csr: every row is copied to indices[frame_off[f] + indptr[f][i] ...] and sorted. */
+int dsg_rows_csr_workspace_bytes(int n_frames, int n_cent, size_t* bytes_out);
+
+int dsg_rows_csr_offsets(const int32_t* d_counts, int n_frames, int n_cent, void* d_workspace,
+                         size_t workspace_bytes, int32_t* d_indptr, int64_t* d_frame_off,
+                         void* stream);
+
+int dsg_rows_to_csr(const int32_t* d_counts, const int64_t* d_row_start, const int32_t* d_rows,
+                    const int32_t* d_indptr, const int64_t* d_frame_off, int n_frames, int n_cent,
+                    int32_t* d_indices, void* stream);
+
 /* LENS over the rows of dsg_neigh_rows (same output contract as dsg_lens_pairs).  For delay 1 one
  * thread owns one centre and a run of pairs (both rows of a pair in registers; warps that meet a
  * row longer than 32 switch to the warp-cooperative intersection).  Bit 30 of `delay` = rows are

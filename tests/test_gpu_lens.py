@@ -416,3 +416,24 @@ def test_lens_rows_thread_and_warp_kernels_agree_on_mixed_rows():
     assert np.array_equal(got_thread.cpu().numpy(), want)
     assert np.array_equal(got_warp.cpu().numpy(), want)
     del _lib
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_canonical_csr_one_traversal_equals_two_pass(numba_cases, dtype):
+    """engine.neighbor_lists builds the canonical CSR from the single-traversal rows
+    (dsg_rows_csr_offsets + dsg_rows_to_csr); the count / fill protocol (two traversals) must give
+    the same arrays, and both equal the numba goldens."""
+    from dynsight_b200 import engine
+
+    for k, case in enumerate(random_csr_cases()):
+        pe = _dev(case["pos_env"].astype(dtype)[None])
+        pc = _dev(case["pos_cent"].astype(dtype)[None])
+        one = engine.neighbor_lists(pe, case["box"], case["r_cut"], pc, case["pbc"])
+        two = engine.neighbor_lists(pe, case["box"], case["r_cut"], pc, case["pbc"], two_pass=True)
+        for a, b in ((one.indptr, two.indptr), (one.frame_off, two.frame_off),
+                     (one.indices, two.indices), (one.counts, two.counts)):  # fmt: skip
+            assert torch.equal(a, b)
+        if dtype == np.float32:
+            continue
+        assert np.array_equal(one.indptr[0].cpu().numpy(), numba_cases[f"csr{k}_indptr"])
+        assert np.array_equal(one.indices.cpu().numpy(), numba_cases[f"csr{k}_indices"])
