@@ -51,6 +51,10 @@ def compute_lens_device(
     same = ix_env.shape == ix_cent.shape and bool(np.array_equal(ix_env, ix_cent))
     dev = frames.device()
     out = torch.empty((ix_cent.size, n_pairs), dtype=torch.float64, device=dev)
+    if ix_cent.size == 0 or ix_env.size == 0:
+        # no centres: empty result; no environment atoms: every row is empty and
+        # lens_from_two_csr returns 0.0 for a + b == 0 (lens.py:171-173)
+        return out.zero_()
     if batch_frames is None:
         batch_frames = frames.pick_batch_frames(max(ix_env.size, ix_cent.size), 160.0, delay + 1)
     batch_frames = max(batch_frames, delay + 1)
@@ -251,6 +255,19 @@ def list_neighbours_along_trajectory(
         )  # fmt: skip
 
     counts = []
+    if ix_cent.size == 0 or ix_env.size == 0:  # nothing to search: all rows are empty
+        dev = frames.device()
+        zero_counts = torch.zeros((len(fr_idx), ix_cent.size), dtype=torch.int32, device=dev)
+
+        def empty_csr() -> engine.NeighborBatch:
+            return engine.NeighborBatch(
+                zero_counts, torch.zeros((len(fr_idx), ix_cent.size + 1), dtype=torch.int32,
+                                         device=dev),
+                torch.zeros(len(fr_idx) + 1, dtype=torch.int64, device=dev),
+                torch.zeros(0, dtype=torch.int32, device=dev), len(fr_idx), ix_cent.size,
+            )  # fmt: skip
+
+        return NeighbourList(ag_env, zero_counts, empty_csr)
     if fr_idx:
         for pos_env, pos_cent, box in batches():
             capacity = None

@@ -264,3 +264,20 @@ def test_coord_number_does_not_materialise_the_lists(trj, ref_lens):
     assert neigh._batch is not None and neigh._csr is not None  # noqa: SLF001
     assert len(first) == int(got.dataset[0, 0])
     assert [len(ag) for ag in neigh[5]] == [int(v) for v in got.dataset[:, 5]]
+
+
+def test_empty_selections_behave_like_the_reference(trj):
+    """No centres -> empty arrays; no environment atoms -> every neighbour row is empty, LENS 0.0
+    (lens.py:171-173) and coordination number 0."""
+    from dynsight_b200 import lens as dlens
+
+    uni = trj.universe
+    got = dlens.compute_lens(uni, 4.0, centers="name ZZ")
+    assert got.shape == (0, 200) and got.dtype == np.float64
+    got = dlens.compute_lens(uni, 4.0, selection="name ZZ")
+    assert got.shape == (7, 200) and not got.any()
+    neigh, nc = trj.get_coord_number(r_cut=4, selection="name ZZ")
+    assert nc.dataset.shape == (7, 201) and not nc.dataset.any()
+    assert len(neigh) == 201 and len(neigh[3]) == 7 and len(neigh[3][2]) == 0
+    soap = trj.get_soap(r_cut=4.0, n_max=4, l_max=4, centers="name ZZ")
+    assert soap.dataset.shape[0] == 0 and soap.dataset.shape[1] == 201
