@@ -108,3 +108,88 @@ def gather_columns(
     if rank != 0:
         return None
     return torch.cat([o[:, : int(w.item())] for o, w in zip(out, widths)], dim=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# Sharded drivers: every rank reads its own frame block (plus the halo) from the trajectory, so no
+# positions cross ranks; results stay local or are gathered on rank 0.
+# ------------------------------------------------------------------------------------------------
+def block_slice(n_frames: int, trajslice: slice | None, shard_start: int, shard_stop: int) -> slice:
+    """The slice of the trajectory that holds positions ``shard_start .. shard_stop - 1`` of the
+    frame sequence ``range(n_frames)[trajslice]``."""
+    seq = range(n_frames)[trajslice if trajslice is not None else slice(None)]
+    sub = seq[shard_start:shard_stop]
+    if len(sub) == 0:
+        return slice(0, 0)
+    stop = sub[-1] + sub.step
+    return slice(sub[0], stop if stop >= 0 else None, sub.step)
+
+
+def compute_lens_sharded(
+    universe: object,
+    r_cut: float,
+    delay: int = 1,
+    centers: str = "all",
+    selection: str = "all",
+    trajslice: slice | None = None,
+    respect_pbc: bool = True,
+    gather: bool = True,
+    group: dist.ProcessGroup | None = None,
+) -> torch.Tensor | None:
+    """``compute_lens`` with the frame pairs split over the ranks of ``group`` (one GPU each).
+
+    Rank ``r`` loads frames ``[F*r/W, F*(r+1)/W + delay)`` itself and computes the pairs that start
+    in its block.  Returns the full (n_centers, n_pairs) tensor on rank 0 (``None`` elsewhere) or,
+    with ``gather=False``, every rank's own slab.
+    """
+    from dynsight_b200 import frames, lens
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_seq = len(frames.frame_sequence(universe.trajectory.n_frames, trajslice))
+    if delay < 1 or n_seq - delay < 1:
+        msg = "No valid pairs found."
+        raise RuntimeError(msg)
+    shard = shard_frames(n_seq, world, rank, delay)
+    n_cent = universe.select_atoms(centers).n_atoms
+    if shard.n_pairs_owned > 0:
+        sl = block_slice(universe.trajectory.n_frames, trajslice, shard.start,
+                         shard.start + shard.n_pairs_owned + delay)  # fmt: skip
+        local = lens.compute_lens_device(universe, r_cut, delay, centers, selection, sl,
+                                         respect_pbc)  # fmt: skip
+    else:
+        local = torch.empty((n_cent, 0), dtype=torch.float64, device=frames.device())
+    return gather_columns(local, group) if gather else local
+
+
+def timesoap_sharded(
+    universe: object,
+    soaprcut: float,
+    soapnmax: int = 8,
+    soaplmax: int = 8,
+    delay: int = 1,
+    selection: str = "all",
+    soap_respectpbc: bool = True,
+    centers: str = "all",
+    trajslice: slice | None = None,
+    gather: bool = True,
+    group: dist.ProcessGroup | None = None,
+) -> torch.Tensor | None:
+    """timeSOAP straight from positions (``soap.timesoap_from_trajectory``) with the frame pairs
+    split over the ranks of ``group``; same ownership rule as :func:`compute_lens_sharded`."""
+    from dynsight_b200 import frames, soap
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_seq = len(frames.frame_sequence(universe.trajectory.n_frames, trajslice))
+    if delay < 1 or delay >= n_seq:
+        msg = "delay value outside bounds"
+        raise ValueError(msg)
+    shard = shard_frames(n_seq, world, rank, delay)
+    if shard.n_pairs_owned > 0:
+        sl = block_slice(universe.trajectory.n_frames, trajslice, shard.start,
+                         shard.start + shard.n_pairs_owned + delay)  # fmt: skip
+        local = soap.timesoap_from_trajectory(universe, soaprcut, soapnmax, soaplmax, delay,
+                                              selection, soap_respectpbc, centers, sl)  # fmt: skip
+    else:
+        n_cent = len(soap._centre_positions(universe.select_atoms(selection), centers))  # noqa: SLF001
+        local = torch.empty((n_cent, 0), dtype=torch.float64, device=frames.device())
+    return gather_columns(local, group) if gather else local

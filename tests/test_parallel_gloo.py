@@ -94,3 +94,55 @@ def test_shard_arithmetic():
                 assert shards[-1].halo == 0
     with pytest.raises(ValueError):
         parallel.shard_frames(10, 2, 2)
+
+
+def _driver_worker(rank: int, world: int, port: int, n_frames: int, delay: int, out_dir: str
+                   ) -> None:  # fmt: skip
+    """compute_lens_sharded with the device compute replaced by the CPU oracle (test-only stub):
+    checks the driver's slicing / ownership / gather logic without a GPU."""
+    for p in (str(ROOT), str(ROOT / "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from golden_cases import fluid_case
+
+        from dynsight_b200 import frames, lens, parallel
+        from dynsight_b200.universe import ArrayUniverse
+        from oracle import lens_oracle as lo
+
+        pos, box, r_cut = fluid_case(n_side=6, n_frames=n_frames)
+        dims = np.tile(np.concatenate([box, [90, 90, 90]]).astype(np.float32), (n_frames, 1))
+        uni = ArrayUniverse(pos, dims, ["A"] * pos.shape[1], ["A"] * pos.shape[1])
+
+        def cpu_lens(universe, r_cut, delay, centers, selection, trajslice, respect_pbc):
+            idx = list(range(universe.trajectory.n_frames))[trajslice]
+            return torch.as_tensor(lo.compute_lens_arrays(pos[idx], dims[idx], r_cut, delay=delay))
+
+        lens.compute_lens_device = cpu_lens
+        frames.device = lambda: torch.device("cpu")
+        sl = slice(1, None)  # composed with the shard's block
+        full = parallel.compute_lens_sharded(uni, r_cut, delay, trajslice=sl)
+        if rank == 0:
+            np.save(Path(out_dir) / "driver_lens.npy", full.numpy())
+        else:
+            assert full is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize(("world", "n_frames", "delay"), [(2, 9, 1), (3, 11, 2)])
+def test_sharded_driver_slices_and_gathers(tmp_path, world, n_frames, delay):
+    from golden_cases import fluid_case
+
+    from oracle import lens_oracle as lo
+
+    port = _free_port()
+    mp.spawn(_driver_worker, args=(world, port, n_frames, delay, str(tmp_path)), nprocs=world,
+             join=True)  # fmt: skip
+    pos, box, r_cut = fluid_case(n_side=6, n_frames=n_frames)
+    dims = np.tile(np.concatenate([box, [90, 90, 90]]).astype(np.float32), (n_frames, 1))
+    want = lo.compute_lens_arrays(pos[1:], dims[1:], r_cut, delay=delay)
+    assert np.array_equal(np.load(tmp_path / "driver_lens.npy"), want)
