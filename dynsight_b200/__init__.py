@@ -10,7 +10,25 @@ a C ABI (``include/dynsight_b200.h``, ``libdynsight_b200.so``).  There is no CPU
     lens = trj.get_lens(r_cut=15.0)
 """
 
-from dynsight_b200 import analysis, descriptors, lens, logs, soap, trajectory, universe
+from dynsight_b200 import (
+    analysis,
+    descriptors,
+    lens,
+    logs,
+    soap,
+    trajectory,
+    universe,
+    utilities,
+)
 
-__all__ = ["analysis", "descriptors", "lens", "logs", "soap", "trajectory", "universe"]
+__all__ = [
+    "analysis",
+    "descriptors",
+    "lens",
+    "logs",
+    "soap",
+    "trajectory",
+    "universe",
+    "utilities",
+]
 __version__ = "0.1.0"

@@ -281,3 +281,14 @@ def test_empty_selections_behave_like_the_reference(trj):
     assert len(neigh) == 201 and len(neigh[3]) == 7 and len(neigh[3][2]) == 0
     soap = trj.get_soap(r_cut=4.0, n_max=4, l_max=4, centers="name ZZ")
     assert soap.dataset.shape[0] == 0 and soap.dataset.shape[1] == 201
+
+
+def test_load_or_compute_soap_roundtrip(trj, tmp_path):
+    """utilities.load_or_compute_soap (utilities.py:67-103): computes and saves, then loads."""
+    from dynsight_b200 import utilities
+
+    path = tmp_path / "soap.json"
+    first = utilities.load_or_compute_soap(trj.with_slice(slice(0, 5)), 4.0, 4, 4, soap_path=path)
+    assert path.exists() and first.meta["name"] == "soap"
+    again = utilities.load_or_compute_soap(trj, 99.0, 1, 1, soap_path=path)  # loaded, not computed
+    assert np.array_equal(first.dataset, again.dataset) and again.meta == first.meta
