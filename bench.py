@@ -626,6 +626,34 @@ def widened_section(engine, dev, hbm_peak: float, fp64_peak_tflops: float) -> di
                          "frac": gbs / hbm_peak, "algorithmic_bytes_per_pf": bytes_pf},
         }  # fmt: skip
         del pos, values, res, state
+    # neighbour-list consumers (section 8f row 2): canonical CSR, then psi_6 and phi
+    n, nf = 1_000_000, 4
+    box_l = (n / 0.8) ** (1.0 / 3.0)
+    pos = (torch.rand((nf, n, 3), device=dev, generator=gen) * box_l).float()
+    box = np.full((nf, 3), box_l)
+    state = {}
+
+    def run_csr() -> None:
+        state["nb"] = engine.neighbor_lists(pos, box, 1.5)
+
+    ms_csr = timed(run_csr)
+    nb = state["nb"]
+    k = float(nb.counts.float().mean().item())
+    ms_psi = timed(lambda: engine.orientational_op_device(pos, nb, 6))
+    ms_phi = timed(lambda: engine.velocity_alignment_device(pos, nb, displacement=True))
+    for name, ms, npf, bytes_pf in (
+        ("canonical_csr", ms_csr, n * nf, 12 + 4 + 4 * k),
+        ("orientational_op", ms_psi, n * nf, 4 * 2 + 4 * k + 8 * (k + 1) + 8),
+        ("velocity_alignment", ms_phi, n * (nf - 1), 4 * 2 + 4 * k + 12 * 2 * (k + 1) + 8),
+    ):
+        gbs = bytes_pf * npf / (ms * 1e-3) / 1e9
+        out[name] = {
+            "workload": f"{n} particles x {nf} frames, rho*=0.8, r_cut=1.5, k={k:.1f}",
+            "value": npf / (ms * 1e-3), "unit": UNIT, "ms": ms,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": gbs / hbm_peak, "algorithmic_bytes_per_pf": bytes_pf},
+        }  # fmt: skip
+    del pos, nb, state
     # self time-correlation function, all lags
     n_part, n_frames = 20_000, 2_000
     data = torch.randn((n_part, n_frames), device=dev, generator=gen, dtype=torch.float64).cumsum(1)
