@@ -292,3 +292,21 @@ def test_load_or_compute_soap_roundtrip(trj, tmp_path):
     assert path.exists() and first.meta["name"] == "soap"
     again = utilities.load_or_compute_soap(trj, 99.0, 1, 1, soap_path=path)  # loaded, not computed
     assert np.array_equal(first.dataset, again.dataset) and again.meta == first.meta
+
+
+def test_cfg1_full_size_lens_and_coordination_bit_exact():
+    """BASELINE cfg1 at full size (2 197 particles x 200 frames, r_cut = 1.5 sigma): LENS and the
+    coordination numbers through the Trj API equal the oracle bit for bit."""
+    from golden_cases import fluid_case
+    from oracle import lens_oracle as lo
+
+    from dynsight_b200.trajectory import Trj
+    from dynsight_b200.universe import ArrayUniverse
+
+    pos, box, r_cut = fluid_case(n_side=13, n_frames=200)
+    dims = np.tile(np.concatenate([box, [90, 90, 90]]).astype(np.float32), (200, 1))
+    t = Trj(ArrayUniverse(pos, dims, ["A"] * pos.shape[1], ["A"] * pos.shape[1]))
+    lens = t.get_lens(r_cut=r_cut)
+    _, n_c = t.get_coord_number(r_cut=r_cut)
+    assert np.array_equal(lens.dataset, lo.compute_lens_arrays(pos, dims, r_cut))
+    assert np.array_equal(n_c.dataset, lo.coord_number_arrays(pos, dims, r_cut))

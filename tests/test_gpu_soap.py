@@ -203,3 +203,31 @@ def test_multi_species_invariances_at_cfg4_parameters():
     zs = np.array([13, 28, 29])
     want = so.soap_trajectory(pos, zs[sp_idx], pick, np.tile(box, (1, 1)), 5.0, 8, 10)
     assert _rel_err(base.cpu().numpy()[pick], want) < REL
+
+
+def test_cfg2_full_size_materialised_equals_streamed():
+    """BASELINE cfg2 at full size (10 000 atoms x 1 000 frames, SOAP(5 A, 8, 8): a 25.9 GB tensor):
+    SOAP materialised on the device + timeSOAP equals the streamed ``timesoap_from_trajectory``
+    (frame batches overlapping by ``delay``), and every spectrum is finite with unit-safe norms."""
+    from dynsight_b200 import engine, soap
+    from dynsight_b200.universe import ArrayUniverse
+
+    n, nf = 10_000, 1_000
+    box_l = (n / 0.0334) ** (1 / 3)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    cur = torch.rand((n, 3), device="cuda", generator=g) * box_l
+    steps = 0.1 * torch.randn((nf, n, 3), device="cuda", generator=g)
+    pos = torch.remainder(cur[None] + steps.cumsum(0), box_l).float()
+    pos.clamp_(max=float(np.nextafter(np.float32(box_l), np.float32(0))))
+    dims = np.tile(np.array([box_l] * 3 + [90] * 3, dtype=np.float32), (nf, 1))
+    uni = ArrayUniverse(pos.cpu().numpy(), dims, ["O"] * n, ["O"] * n)
+    del steps
+    spectra = soap.saponify_trajectory_device(uni, 5.0, 8, 8)
+    assert spectra.shape == (n, nf, 324)
+    assert bool(torch.isfinite(spectra[:, ::97]).all())
+    full = engine.timesoap_device(spectra, 2)
+    del spectra
+    streamed = soap.timesoap_from_trajectory(uni, 5.0, 8, 8, delay=2, batch_frames=128)
+    assert full.shape == streamed.shape == (n, nf - 2)
+    assert float((full - streamed).abs().max()) < 1e-9
+    assert 0.0 < float(full.mean()) < 1.5
