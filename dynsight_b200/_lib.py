@@ -88,7 +88,7 @@ SIGNATURES: dict[str, tuple] = {
         _c_int, [_c_ptr, _c_int, _c_int, _c_ptr, _c_size, _c_ptr, _c_ptr, _c_ptr],
     ),
     "dsg_rows_to_csr": (
-        _c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_ptr, _c_ptr],
+        _c_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_ptr, _c_int, _c_ptr],
     ),
     "dsg_wrap_positions": (_c_int, [_c_ptr, _c_int, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr]),
     "dsg_spatial_average_rows": (

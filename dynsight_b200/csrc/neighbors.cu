@@ -495,6 +495,82 @@ rows_to_csr_kernel(const int* __restrict__ counts, const long long* __restrict__
     warp_sort_row(dst, n, sort_tile[warp], lane);
 }
 
+// Short rows: ONE THREAD per (frame, centre).  The row sits in registers (up to 32 values, loaded in
+// chunks of 8 up to the longest row of the warp), is sorted by a bitonic network with compile-time
+// indices (8 / 16 / 32 wide, chosen per warp) and written to its CSR place.  A warp that meets a
+// row longer than 32 handles its 32 rows with the warp-cooperative copy-and-sort.
+template <int N>
+__device__ __forceinline__ void sort_regs(int (&v)[32]) {
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const bool asc = (i & k) == 0;
+                    const int lo = min(v[i], v[p]), hi = max(v[i], v[p]);
+                    v[i] = asc ? lo : hi;
+                    v[p] = asc ? hi : lo;
+                }
+            }
+        }
+    }
+}
+
+constexpr int kRtThreads = 128;
+__global__ void __launch_bounds__(kRtThreads)
+rows_to_csr_thread_kernel(const int* __restrict__ counts, const long long* __restrict__ row_start,
+                          const int* __restrict__ rows, const int* __restrict__ indptr,
+                          const long long* __restrict__ frame_off, int n_frames, int n_cent,
+                          int* __restrict__ indices) {
+    __shared__ int sort_tile[kRtThreads / 32][kStageCap * 4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long w = (long long)blockIdx.x * kRtThreads + threadIdx.x;
+    const bool active = w < (long long)n_frames * n_cent;
+    int n = 0;
+    long long src0 = -1;
+    int* dst = nullptr;
+    if (active) {
+        const int f = (int)(w / n_cent), i = (int)(w - (long long)f * n_cent);
+        n = counts[w];
+        src0 = row_start[w];
+        if (src0 < 0) n = 0;
+        dst = indices + frame_off[f] + indptr[(size_t)f * (n_cent + 1) + i];
+    }
+    const int wmax = __reduce_max_sync(kFull, n);
+    if (wmax == 0) return;
+    if (wmax <= 32) {
+        int v[32];
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+            const bool need = c8 * 8 < wmax;   // warp-uniform
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                v[c8 * 8 + j] = (need && c8 * 8 + j < n) ? rows[src0 + c8 * 8 + j] : INT_MAX;
+        }
+        if (wmax <= 8) sort_regs<8>(v);
+        else if (wmax <= 16) sort_regs<16>(v);
+        else sort_regs<32>(v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (j < n) dst[j] = v[j];
+    } else {
+        for (int src = 0; src < 32; ++src) {
+            const int n_s = __shfl_sync(kFull, n, src);
+            const long long s_s = __shfl_sync(kFull, src0, src);
+            const long long d_s = __shfl_sync(kFull, (long long)(dst - indices), src);
+            if (n_s <= 0) continue;
+            int* d = indices + d_s;
+            for (int t = lane; t < n_s; t += 32) d[t] = rows[s_s + t];
+            __syncwarp();
+            warp_sort_row(d, n_s, sort_tile[warp], lane);
+            __syncwarp();
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -1354,13 +1430,21 @@ extern "C" int dsg_rows_csr_offsets(const int32_t* d_counts, int n_frames, int n
 extern "C" int dsg_rows_to_csr(const int32_t* d_counts, const int64_t* d_row_start,
                                const int32_t* d_rows, const int32_t* d_indptr,
                                const int64_t* d_frame_off, int n_frames, int n_cent,
-                               int32_t* d_indices, void* stream) {
+                               int32_t* d_indices, int expected_row_len, void* stream) {
     if (!d_counts || !d_row_start || !d_rows || !d_indptr || !d_frame_off || !d_indices)
         return set_error(DSG_ERR_INVALID_ARGUMENT, "NULL device pointer argument");
     if (n_frames < 1 || n_cent < 1)
         return set_error(DSG_ERR_INVALID_ARGUMENT, "n_frames=%d, n_cent=%d must be >= 1", n_frames,
                          n_cent);
     const long long warps = (long long)n_frames * n_cent;
+    if (expected_row_len > 0 && expected_row_len <= 24) {   // short rows: one thread per row
+        const unsigned blocks = (unsigned)((warps + kRtThreads - 1) / kRtThreads);
+        rows_to_csr_thread_kernel<<<blocks, kRtThreads, 0, (cudaStream_t)stream>>>(
+            d_counts, (const long long*)d_row_start, d_rows, d_indptr,
+            (const long long*)d_frame_off, n_frames, n_cent, d_indices);
+        DSG_LAUNCH_CHECK("rows_to_csr_thread_kernel");
+        return DSG_OK;
+    }
     const unsigned blocks = (unsigned)((warps + kWarpsPerBlock - 1) / kWarpsPerBlock);
     rows_to_csr_kernel<<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
         d_counts, (const long long*)d_row_start, d_rows, d_indptr, (const long long*)d_frame_off,

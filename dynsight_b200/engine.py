@@ -192,7 +192,8 @@ def _neighbor_lists_from_rows(
     _lib.check(
         lib.dsg_rows_to_csr(
             nr.counts.data_ptr(), nr.row_start.data_ptr(), nr.rows.data_ptr(), indptr.data_ptr(),
-            frame_off.data_ptr(), n_frames, n_cent, indices.data_ptr(), _stream_ptr(),
+            frame_off.data_ptr(), n_frames, n_cent, indices.data_ptr(),
+            int(np.ceil(nr.k_est)) if nr.k_est > 0 else 0, _stream_ptr(),
         )
     )
     return NeighborBatch(nr.counts, indptr, frame_off, indices[:nnz], n_frames, n_cent)

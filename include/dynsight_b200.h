@@ -112,7 +112,8 @@ int dsg_neigh_rows(const void* d_pos_env, const void* d_pos_cent, int pos_dtype,
  * cell list instead of two:
  *   dsg_rows_csr_offsets: indptr (n_frames, n_cent+1) frame-local exclusive scan of the counts and
  *     frame_off (n_frames+1); the caller reads frame_off[n_frames] (nnz) and allocates d_indices;
- *   dsg_rows_to_csr: every row is copied to indices[frame_off[f] + indptr[f][i] ...] and sorted. */
+ *   dsg_rows_to_csr: every row is copied to indices[frame_off[f] + indptr[f][i] ...] and sorted;
+ *     expected_row_len (0 = unknown) picks one thread per row (<= 24) or one warp per row. */
 int dsg_rows_csr_workspace_bytes(int n_frames, int n_cent, size_t* bytes_out);
 
 int dsg_rows_csr_offsets(const int32_t* d_counts, int n_frames, int n_cent, void* d_workspace,
@@ -121,7 +122,7 @@ int dsg_rows_csr_offsets(const int32_t* d_counts, int n_frames, int n_cent, void
 
 int dsg_rows_to_csr(const int32_t* d_counts, const int64_t* d_row_start, const int32_t* d_rows,
                     const int32_t* d_indptr, const int64_t* d_frame_off, int n_frames, int n_cent,
-                    int32_t* d_indices, void* stream);
+                    int32_t* d_indices, int expected_row_len, void* stream);
 
 /* LENS over the rows of dsg_neigh_rows (same output contract as dsg_lens_pairs).  For delay 1 one
  * thread owns one centre and a run of pairs (both rows of a pair in registers; warps that meet a

@@ -437,3 +437,17 @@ def test_canonical_csr_one_traversal_equals_two_pass(numba_cases, dtype):
             continue
         assert np.array_equal(one.indptr[0].cpu().numpy(), numba_cases[f"csr{k}_indptr"])
         assert np.array_equal(one.indices.cpu().numpy(), numba_cases[f"csr{k}_indices"])
+
+
+def test_canonical_csr_thread_sort_with_a_dense_spot():
+    """Sparse fluid (expected row length ~11 -> one thread sorts one row) with 80 atoms packed
+    into a corner: the warps that hold a row longer than 32 switch to the warp-cooperative
+    copy-and-sort.  The CSR must equal the oracle's."""
+    from dynsight_b200 import engine
+
+    pos, box, r_cut = fluid_case(n_side=16, n_frames=3)
+    dense = pos.copy()
+    dense[:, :80] = (dense[:, :80] % 1.0) * 0.9 + 0.05
+    batch = engine.neighbor_lists(_dev(dense), box, r_cut, None, True)
+    assert int(batch.counts.max()) > 32
+    _check_batch_vs_oracle(batch, dense, None, box, r_cut, True)
