@@ -61,12 +61,12 @@ SIGNATURES: dict[str, tuple] = {
     "dsg_orientational_op": (
         _c_int,
         [_c_ptr, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_ptr, _c_i64, _c_i64,
-         _c_ptr],
+         _c_int, _c_ptr],
     ),
     "dsg_velocity_alignment": (
         _c_int,
         [_c_ptr, _c_int, _c_int, _c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_ptr, _c_i64, _c_i64,
-         _c_ptr],
+         _c_int, _c_ptr],
     ),
     "dsg_timesoap": (
         _c_int,

@@ -582,6 +582,12 @@ def soap_power_spectrum(
     return out
 
 
+def _mean_row_len(batch: NeighborBatch) -> int:
+    """Mean neighbours per (atom, frame) from sizes already known on the host (0 = unknown)."""
+    cells = batch.n_frames * batch.n_cent
+    return int(np.ceil(batch.indices.numel() / cells)) if cells > 0 else 0
+
+
 def orientational_op_device(
     pos: torch.Tensor, batch: NeighborBatch, order: int = 6, out: torch.Tensor | None = None,
     col0: int = 0,
@@ -601,7 +607,7 @@ def orientational_op_device(
         lib.dsg_orientational_op(
             pos.data_ptr(), _dtype_code(pos), batch.indptr.data_ptr(), batch.frame_off.data_ptr(),
             batch.indices.data_ptr(), n_frames, n_atoms, int(order), out.data_ptr(), out.stride(0),
-            int(col0), _stream_ptr(),
+            int(col0), _mean_row_len(batch), _stream_ptr(),
         )
     )  # fmt: skip
     return out
@@ -627,7 +633,7 @@ def velocity_alignment_device(
         lib.dsg_velocity_alignment(
             vec.data_ptr(), _dtype_code(vec), int(bool(displacement)), batch.indptr.data_ptr(),
             batch.frame_off.data_ptr(), batch.indices.data_ptr(), n_out, n_atoms, out.data_ptr(),
-            out.stride(0), int(col0), _stream_ptr(),
+            out.stride(0), int(col0), _mean_row_len(batch), _stream_ptr(),
         )
     )  # fmt: skip
     return out

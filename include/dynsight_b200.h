@@ -166,16 +166,18 @@ int dsg_counts_to_f64(const int32_t* d_counts, int n_frames, int n_cent, double*
  *   d_vec holds positions (n_out+1, n_atoms, 3) and the vector of output f is
  *   pos[f+1] - pos[0] (the reference never advances r_0, misc.py:207-213) with the rows of frame
  *   f; displacement == 0: d_vec holds (n_out, n_atoms, 3) velocities, rows of the same frame.
- * ------------------------------------------------------------------------------------------ */
+ * ------------------------------------------------------------------------------------------  * expected_row_len (0 = unknown): mean neighbours per atom; 4, 8, 16 or 32 lanes share one
+ * (atom, frame) accordingly.
+ */
 int dsg_orientational_op(const void* d_pos, int pos_dtype, const int32_t* d_indptr,
                          const int64_t* d_frame_off, const int32_t* d_indices, int n_frames,
                          int n_atoms, int order, double* d_out, int64_t ld_out, int64_t col0,
-                         void* stream);
+                         int expected_row_len, void* stream);
 
 int dsg_velocity_alignment(const void* d_vec, int dtype, int displacement,
                            const int32_t* d_indptr, const int64_t* d_frame_off,
                            const int32_t* d_indices, int n_out, int n_atoms, double* d_out,
-                           int64_t ld_out, int64_t col0, void* stream);
+                           int64_t ld_out, int64_t col0, int expected_row_len, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * timeSOAP (replaces timesoap/timesoap.py:13-179: normalize_soap + soap_distance + timesoap).
