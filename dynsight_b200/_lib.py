@@ -94,7 +94,7 @@ SIGNATURES: dict[str, tuple] = {
     "dsg_spatial_average_rows": (
         _c_int,
         [_c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_ptr, _c_i64, _c_i64, _c_ptr, _c_i64,
-         _c_i64, _c_ptr],
+         _c_i64, _c_int, _c_ptr],
     ),
     "dsg_tcf_workspace_bytes": (_c_int, [_c_int, _c_int, _c_int, ctypes.POINTER(_c_size)]),
     "dsg_self_time_correlation": (

@@ -34,30 +34,34 @@ wrap_kernel(const T* __restrict__ pos, const double* __restrict__ box, int n_ato
     out[g] = v;
 }
 
-// Scalar descriptor: one warp per (particle, frame); lanes stride over the row, shuffle reduction.
+// Scalar descriptor: G lanes per (particle, frame) (4 for rows of ~10 entries ... 32 for long rows);
+// the lanes stride over the row, shuffle reduction inside the group.
+template <int G>
 __global__ void __launch_bounds__(kSpWarps * 32)
 spatial_mean_scalar_kernel(const int* __restrict__ counts, const long long* __restrict__ row_start,
                            const int* __restrict__ rows, int n_frames, int n_cent,
                            const double* __restrict__ val, long long v_stride_i,
                            long long v_stride_f, double* __restrict__ out, long long o_stride_i,
                            long long o_stride_f) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long w = (long long)blockIdx.x * kSpWarps + warp;
-    if (w >= (long long)n_frames * n_cent) return;
+    const int lane = threadIdx.x & (G - 1);
+    long long w = ((long long)blockIdx.x * (kSpWarps * 32) + threadIdx.x) / G;
+    const bool active = w < (long long)n_frames * n_cent;
+    if (!active) w = 0;  // stay for the group shuffles
     const int f = (int)(w / n_cent), i = (int)(w % n_cent);
     const size_t fi = (size_t)f * n_cent + i;
-    const int n = counts[fi];
+    const int n = active ? counts[fi] : 0;
     const long long rs = row_start[fi];
     const double* __restrict__ vf = val + (long long)f * v_stride_f;
     double s = 0.0;
     if (rs >= 0) {
         const int* __restrict__ row = rows + rs;
-        for (int t = lane; t < n; t += 32) s += vf[(long long)row[t] * v_stride_i];
+        for (int t = lane; t < n; t += G) s += vf[(long long)row[t] * v_stride_i];
     }
     if (lane == 0) s += vf[(long long)i * v_stride_i];  // the particle itself
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(kFullSp, s, off);
-    if (lane == 0) out[(long long)i * o_stride_i + (long long)f * o_stride_f] = s / (double)(n + 1);
+    for (int off = G / 2; off > 0; off >>= 1) s += __shfl_xor_sync(kFullSp, s, off);
+    if (lane == 0 && active)
+        out[(long long)i * o_stride_i + (long long)f * o_stride_f] = s / (double)(n + 1);
 }
 
 // Vector descriptor (components contiguous): one warp per (particle, frame); lanes own components
@@ -154,7 +158,7 @@ extern "C" int dsg_spatial_average_rows(const int32_t* d_counts, const int64_t* 
                                         const int32_t* d_rows, int n_frames, int n_cent,
                                         int n_comp, const double* d_values, int64_t v_stride_i,
                                         int64_t v_stride_f, double* d_out, int64_t o_stride_i,
-                                        int64_t o_stride_f, void* stream) {
+                                        int64_t o_stride_f, int expected_row_len, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!d_counts || !d_row_start || !d_rows || !d_values || !d_out)
         return set_error(DSG_ERR_INVALID_ARGUMENT, "NULL device pointer argument");
@@ -164,9 +168,18 @@ extern "C" int dsg_spatial_average_rows(const int32_t* d_counts, const int64_t* 
     const long long warps = (long long)n_frames * n_cent;
     const unsigned blocks = (unsigned)((warps + kSpWarps - 1) / kSpWarps);
     if (n_comp == 1) {
-        spatial_mean_scalar_kernel<<<blocks, kSpWarps * 32, 0, st>>>(
-            d_counts, (const long long*)d_row_start, d_rows, n_frames, n_cent, d_values,
-            v_stride_i, v_stride_f, d_out, o_stride_i, o_stride_f);
+        const int g = expected_row_len <= 0 ? 32
+                      : expected_row_len <= 12 ? 4
+                      : expected_row_len <= 24 ? 8
+                      : expected_row_len <= 48 ? 16 : 32;
+        const unsigned gb = (unsigned)((warps * g + kSpWarps * 32 - 1) / (kSpWarps * 32));
+#define DSG_SPM(G)                                                                               \
+    spatial_mean_scalar_kernel<G><<<gb, kSpWarps * 32, 0, st>>>(                                 \
+        d_counts, (const long long*)d_row_start, d_rows, n_frames, n_cent, d_values, v_stride_i, \
+        v_stride_f, d_out, o_stride_i, o_stride_f)
+        if (g == 4) DSG_SPM(4); else if (g == 8) DSG_SPM(8);
+        else if (g == 16) DSG_SPM(16); else DSG_SPM(32);
+#undef DSG_SPM
     } else {
         spatial_mean_vector_kernel<<<blocks, kSpWarps * 32, 0, st>>>(
             d_counts, (const long long*)d_row_start, d_rows, n_frames, n_cent, n_comp, d_values,

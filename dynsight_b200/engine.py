@@ -379,7 +379,8 @@ def spatial_average_rows(
         lib.dsg_spatial_average_rows(
             nr.counts.data_ptr(), nr.row_start.data_ptr(), nr.rows.data_ptr(), nr.n_frames,
             nr.n_cent, int(n_comp), v.data_ptr(), v.stride(0), v.stride(1), o.data_ptr(),
-            o.stride(0), o.stride(1), _stream_ptr(),
+            o.stride(0), o.stride(1), int(np.ceil(nr.k_est)) if nr.k_est > 0 else 0,
+            _stream_ptr(),
         )
     )  # fmt: skip
     return out

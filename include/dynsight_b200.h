@@ -232,7 +232,8 @@ int dsg_soap(const void* d_pos, int pos_dtype, const int32_t* d_species, const i
  *   respect_pbc = 1 | 4 (minimum image, inclusive cutoff).
  * dsg_spatial_average_rows: out[i, f, c] = (values[i, f, c] + sum_{j in row(f, i)} values[j, f, c])
  *   / (counts[f, i] + 1); values / out float64 with element strides v_stride_i / v_stride_f
- *   (components contiguous, n_comp = 1 for a scalar descriptor).
+ *   (components contiguous, n_comp = 1 for a scalar descriptor); expected_row_len (0 = unknown)
+ *   picks how many lanes share one (particle, frame) of a scalar descriptor.
  * ------------------------------------------------------------------------------------------ */
 int dsg_wrap_positions(const void* d_pos, int pos_dtype, int n_frames, int n_atoms,
                        const double* d_box, void* d_out, void* stream);
@@ -240,7 +241,8 @@ int dsg_wrap_positions(const void* d_pos, int pos_dtype, int n_frames, int n_ato
 int dsg_spatial_average_rows(const int32_t* d_counts, const int64_t* d_row_start,
                              const int32_t* d_rows, int n_frames, int n_cent, int n_comp,
                              const double* d_values, int64_t v_stride_i, int64_t v_stride_f,
-                             double* d_out, int64_t o_stride_i, int64_t o_stride_f, void* stream);
+                             double* d_out, int64_t o_stride_i, int64_t o_stride_f,
+                             int expected_row_len, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Self time-correlation function (replaces analysis/time_correlations.py:60-92 -- SURVEY.md
