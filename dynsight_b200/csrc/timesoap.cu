@@ -3,7 +3,8 @@
 // Replaces timesoap/timesoap.py:13-179 (normalize_soap + soap_distance + timesoap: >= 4 full-size
 // numpy temporaries) with one pass: a warp owns one particle and a run of frames, streams the
 // SOAP vectors once (coalesced 256-byte warp loads), keeps the previous vector and its squared
-// norm in registers (delay == 1) and emits sqrt(max(0, 2 - 2 clip(cos))) per frame pair.
+// norm in registers (a ring of `delay` vectors for delay <= 4) and emits
+// sqrt(max(0, 2 - 2 clip(cos))) per frame pair.
 // HBM-bound: 8*C bytes read + 8 bytes written per particle-frame.
 #include "common.cuh"
 
@@ -36,49 +37,62 @@ struct TsArgs {
     int seg_len, n_seg;
 };
 
-// delay == 1, n_comp <= 32*KV: previous vector lives in registers.
-template <int KV>
+// delay D <= 4, n_comp <= 32*KV: the D previous vectors (and their squared norms) live in
+// registers as a ring whose rotation is resolved at compile time (the frame loop is unrolled by D),
+// so every vector is read once whatever the delay.
+template <int KV, int D>
 __global__ void __launch_bounds__(kTsWarps * 32)
 timesoap_stream_kernel(const TsArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long w = (long long)blockIdx.x * kTsWarps + warp;
     if (w >= (long long)a.n_particles * a.n_seg) return;
     const int i = (int)(w / a.n_seg), seg = (int)(w % a.n_seg);
-    const int n_out = a.n_frames - 1;
+    const int n_out = a.n_frames - D;
     const int f_begin = seg * a.seg_len;
     const int f_end = min(n_out, f_begin + a.seg_len);
     const double* __restrict__ base = a.soap + (long long)i * a.stride_i;
-    double prev[KV];
-    double psq = 0.0;
-    {
-        const double* __restrict__ v = base + (long long)f_begin * a.stride_f;
+    double prev[D][KV];
+    double psq[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        // frames f_begin .. f_begin + D - 1 all exist: f_begin < n_out = n_frames - D
+        const double* __restrict__ v = base + (long long)(f_begin + d) * a.stride_f;
+        double sq = 0.0;
 #pragma unroll
         for (int k = 0; k < KV; ++k) {
             const int c = lane + 32 * k;
-            prev[k] = c < a.n_comp ? v[c] : 0.0;
-            psq = fma(prev[k], prev[k], psq);
+            prev[d][k] = c < a.n_comp ? v[c] : 0.0;
+            sq = fma(prev[d][k], prev[d][k], sq);
         }
-        psq = warp_sum(psq);
+        psq[d] = warp_sum(sq);
     }
-    for (int f = f_begin; f < f_end; ++f) {
-        const double* __restrict__ v = base + (long long)(f + 1) * a.stride_f;
-        double cur[KV];
+    for (int f0 = f_begin; f0 < f_end; f0 += D) {
 #pragma unroll
-        for (int k = 0; k < KV; ++k) {
-            const int c = lane + 32 * k;
-            cur[k] = c < a.n_comp ? v[c] : 0.0;
-        }
-        double csq = 0.0, dot = 0.0;
+        for (int d = 0; d < D; ++d) {
+            const int f = f0 + d;   // ring slot d holds frame f
+            if (f < f_end) {
+                const double* __restrict__ v = base + (long long)(f + D) * a.stride_f;
+                double cur[KV];
 #pragma unroll
-        for (int k = 0; k < KV; ++k) {
-            csq = fma(cur[k], cur[k], csq);
-            dot = fma(cur[k], prev[k], dot);
-            prev[k] = cur[k];
+                for (int k = 0; k < KV; ++k) {
+                    const int c = lane + 32 * k;
+                    cur[k] = c < a.n_comp ? v[c] : 0.0;
+                }
+                double csq = 0.0, dot = 0.0;
+#pragma unroll
+                for (int k = 0; k < KV; ++k) {
+                    csq = fma(cur[k], cur[k], csq);
+                    dot = fma(cur[k], prev[d][k], dot);
+                    prev[d][k] = cur[k];
+                }
+                csq = warp_sum(csq);
+                dot = warp_sum(dot);
+                if (lane == 0)
+                    a.out[(long long)i * a.ld_out + a.col0 + f] =
+                        soap_dist_from_sums(psq[d], csq, dot);
+                psq[d] = csq;
+            }
         }
-        csq = warp_sum(csq);
-        dot = warp_sum(dot);
-        if (lane == 0) a.out[(long long)i * a.ld_out + a.col0 + f] = soap_dist_from_sums(psq, csq, dot);
-        psq = csq;
     }
 }
 
@@ -181,12 +195,20 @@ extern "C" int dsg_timesoap(const double* d_soap, int n_particles, int n_frames,
     if (blocks > 0x7fffffffLL) return set_error(DSG_ERR_OVERFLOW, "grid too large");
     cudaStream_t st = (cudaStream_t)stream;
     const int kv = (n_comp + 31) / 32;
-    if (delay == 1 && kv <= 16) {
-        if (kv <= 2) timesoap_stream_kernel<2><<<(unsigned)blocks, kTsWarps * 32, 0, st>>>(a);
-        else if (kv <= 4) timesoap_stream_kernel<4><<<(unsigned)blocks, kTsWarps * 32, 0, st>>>(a);
-        else if (kv <= 8) timesoap_stream_kernel<8><<<(unsigned)blocks, kTsWarps * 32, 0, st>>>(a);
-        else if (kv <= 12) timesoap_stream_kernel<12><<<(unsigned)blocks, kTsWarps * 32, 0, st>>>(a);
-        else timesoap_stream_kernel<16><<<(unsigned)blocks, kTsWarps * 32, 0, st>>>(a);
+    if (delay <= 4 && kv <= (delay == 1 ? 16 : 12)) {
+#define DSG_TS(KV, D) timesoap_stream_kernel<KV, D><<<(unsigned)blocks, kTsWarps * 32, 0, st>>>(a)
+#define DSG_TS_KV(D)                                                                             \
+    do {                                                                                         \
+        if (kv <= 2) DSG_TS(2, D); else if (kv <= 4) DSG_TS(4, D);                               \
+        else if (kv <= 8) DSG_TS(8, D); else DSG_TS(12, D);                                      \
+    } while (0)
+        if (delay == 1) {
+            if (kv <= 12) DSG_TS_KV(1); else DSG_TS(16, 1);
+        } else if (delay == 2) DSG_TS_KV(2);
+        else if (delay == 3) DSG_TS_KV(3);
+        else DSG_TS_KV(4);
+#undef DSG_TS_KV
+#undef DSG_TS
         DSG_LAUNCH_CHECK("timesoap_stream_kernel");
     } else {
         timesoap_general_kernel<<<(unsigned)blocks, kTsWarps * 32, 0, st>>>(a);
