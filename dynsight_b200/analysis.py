@@ -62,7 +62,7 @@ def spatialaverage_device(
         pos = engine.wrap_positions(fb.select(sel_all, n_all), box)  # FastNS bins wrapped positions
         capacity = None
         force_warp = False
-        while True:
+        for attempt in range(engine._MAX_ROW_RETRIES):  # noqa: SLF001
             nr = engine.neighbor_rows(pos, box, float(r_cut), None, True, capacity, force_warp,
                                       inclusive_cutoff=True)  # fmt: skip
             engine.spatial_average_rows(nr, values, out, frame0=fb.seq0)
@@ -71,7 +71,11 @@ def spatialaverage_device(
             if nr.needs_warp_kernel():
                 force_warp = True
             else:
-                capacity = int(nr.needed_capacity() * 1.1) + 2048 * 256
+                capacity = engine._next_capacity(nr, capacity)  # noqa: SLF001
+        else:
+            msg = "neighbour rows still overflow after several attempts"
+            raise RuntimeError(msg)
+        del attempt
     return out
 
 

@@ -988,6 +988,9 @@ neigh_rows_kernel(const RowsArgs a) {
     const FrameParams* __restrict__ p = a.fp + f;
     const int nx = p->ncell[0], ny = p->ncell[1], nz = p->ncell[2];
     const int c = blockIdx.x * kWarpsPerBlock + warp;
+    // the number of reservation regions goes into the status block whatever cell 0 holds (the
+    // caller sizes its retry from it)
+    if (blockIdx.x == 0 && f == 0 && threadIdx.x == 0) a.status[1] = a.n_parts;
     if (c >= nx * ny * nz) return;
     const int base_cell = p->cell_base;
     const int cbeg = a.cent_start[base_cell + c];
@@ -1039,7 +1042,6 @@ neigh_rows_kernel(const RowsArgs a) {
     const T* __restrict__ pos_cent_f = (const T*)a.pos_cent + (size_t)f * a.n_cent * 3;
     const double r2 = a.r2;
     const int part = (c + f * 131) & (a.n_parts - 1);
-    if (c == 0 && f == 0 && lane == 0) a.status[1] = a.n_parts;
 
     // stage candidates [base, base+clen) with the run's shift applied
     auto stage_chunk = [&](int base, int clen) {

@@ -156,6 +156,41 @@ def neighbor_lists(
     return NeighborBatch(counts, indptr, frame_off, indices[:nnz], n_frames, n_cent)
 
 
+_MAX_ROW_RETRIES = 8
+
+
+def _next_capacity(nr: "NeighborRows", previous: int | None) -> int:
+    """Rows capacity for the retry after a reservation overflow: what the cursors say was needed
+    (+10 %), and never less than twice the previous attempt, so the retry loop always ends."""
+    need = int(nr.needed_capacity() * 1.1) + _ROW_PARTS * 2048
+    prev = int(previous) if previous is not None else int(nr.rows.numel())
+    return max(need, 2 * prev)
+
+
+def neighbor_rows_checked(
+    pos_env: torch.Tensor,
+    box: np.ndarray | torch.Tensor,
+    r_cut: float,
+    pos_cent: torch.Tensor | None = None,
+    respect_pbc: bool = True,
+    capacity: int | None = None,
+    inclusive_cutoff: bool = False,
+) -> "NeighborRows":
+    """:func:`neighbor_rows` + the overflow check (one host sync) and the retries."""
+    force_warp = False
+    for _ in range(_MAX_ROW_RETRIES):
+        nr = neighbor_rows(pos_env, box, r_cut, pos_cent, respect_pbc, capacity, force_warp,
+                           inclusive_cutoff)  # fmt: skip
+        if not nr.overflowed():
+            return nr
+        if nr.needs_warp_kernel():
+            force_warp = True
+        else:
+            capacity = _next_capacity(nr, capacity)
+    msg = f"neighbour rows still overflow after {_MAX_ROW_RETRIES} attempts (capacity {capacity})"
+    raise RuntimeError(msg)
+
+
 def _neighbor_lists_from_rows(
     pos_env: torch.Tensor,
     box: np.ndarray | torch.Tensor,
@@ -164,16 +199,7 @@ def _neighbor_lists_from_rows(
     respect_pbc: bool,
 ) -> NeighborBatch:
     lib = _lib.load()
-    capacity = None
-    force_warp = False
-    while True:
-        nr = neighbor_rows(pos_env, box, r_cut, pos_cent, respect_pbc, capacity, force_warp)
-        if not nr.overflowed():
-            break
-        if nr.needs_warp_kernel():
-            force_warp = True
-        else:
-            capacity = int(nr.needed_capacity() * 1.1) + _ROW_PARTS * 2048
+    nr = neighbor_rows_checked(pos_env, box, r_cut, pos_cent, respect_pbc)
     dev = pos_env.device
     n_frames, n_cent = nr.n_frames, nr.n_cent
     ws_bytes = ctypes.c_size_t(0)
@@ -328,7 +354,7 @@ def lens_from_positions(
     """LENS for all frame pairs of a batch straight from positions (rows path + retry on the rare
     reservation overflow).  Returns the (M, n_pairs) result and the rows batch (for the counts)."""
     force_warp = False
-    while True:
+    for _ in range(_MAX_ROW_RETRIES):
         nr = neighbor_rows(pos_env, box, r_cut, pos_cent, respect_pbc, capacity, force_warp)
         res = lens_pairs_rows(nr, delay, out=out, col0=col0)
         if not nr.overflowed():
@@ -336,7 +362,9 @@ def lens_from_positions(
         if nr.needs_warp_kernel():
             force_warp = True  # rows longer than the thread kernel's tile: one warp per cell
         else:
-            capacity = int(nr.needed_capacity() * 1.1) + _ROW_PARTS * 2048
+            capacity = _next_capacity(nr, capacity)
+    msg = f"neighbour rows still overflow after {_MAX_ROW_RETRIES} attempts (capacity {capacity})"
+    raise RuntimeError(msg)
 
 
 def wrap_positions(pos: torch.Tensor, box: np.ndarray | torch.Tensor) -> torch.Tensor:

@@ -67,7 +67,7 @@ def compute_lens_device(
         if nr.overflowed():
             engine.lens_from_positions(
                 pos_env, box, r_cut, delay, pos_cent, respect_pbc, out=out, col0=fb.seq0,
-                capacity=None if nr.needs_warp_kernel() else int(nr.needed_capacity() * 1.1),
+                capacity=None if nr.needs_warp_kernel() else engine._next_capacity(nr, None),  # noqa: SLF001
             )
 
     # Software pipeline over batches: asking the iterator for batch k issues its host -> device
@@ -270,17 +270,8 @@ def list_neighbours_along_trajectory(
         return NeighbourList(ag_env, zero_counts, empty_csr)
     if fr_idx:
         for pos_env, pos_cent, box in batches():
-            capacity = None
-            force_warp = False
-            while True:  # counts only: rows are written to a scratch buffer and dropped
-                nr = engine.neighbor_rows(pos_env, box, r_cut, pos_cent, respect_pbc, capacity,
-                                          force_warp)  # fmt: skip
-                if not nr.overflowed():
-                    break
-                if nr.needs_warp_kernel():
-                    force_warp = True
-                else:
-                    capacity = int(nr.needed_capacity() * 1.1) + 2048 * 256
+            # counts only: the rows go to a scratch buffer and are dropped
+            nr = engine.neighbor_rows_checked(pos_env, box, r_cut, pos_cent, respect_pbc)
             counts.append(nr.counts)
     dev_counts = (torch.cat(counts, dim=0) if counts else
                   torch.empty((0, ix_cent.size), dtype=torch.int32, device=frames.device()))  # fmt: skip

@@ -451,3 +451,29 @@ def test_canonical_csr_thread_sort_with_a_dense_spot():
     batch = engine.neighbor_lists(_dev(dense), box, r_cut, None, True)
     assert int(batch.counts.max()) > 32
     _check_batch_vs_oracle(batch, dense, None, box, r_cut, True)
+
+
+def test_clustered_atoms_overflow_retry_terminates():
+    """Regression (found by scripts/fuzz_neighbors.py): atoms clustered in a large, mostly empty box
+    with one short axis (warp-per-cell kernel, rint image on that axis).  The density-based
+    capacity is far too small, cell 0 is empty, and the retry must size itself from the number of
+    reservation regions reported in the status block -- it used to loop forever."""
+    from dynsight_b200 import engine
+
+    rng = np.random.default_rng(169)
+    nf, n, r_cut = 3, 1500, 2.5
+    box = np.array([120.5, 9.26, 114.3], dtype=np.float32)
+    centres = rng.random((nf, n // 40, 3)) * box
+    pos = (centres[:, rng.integers(0, centres.shape[1], n)] + rng.normal(0, 0.3, (nf, n, 3))).astype(
+        np.float32)  # fmt: skip
+    first = engine.neighbor_rows(_dev(pos), box, r_cut, None, True, capacity=256 * 64)
+    assert first.overflowed() and int(first.status[1]) > 0   # regions reported although cell 0 is empty
+    assert first.needed_capacity() >= int(first.counts.sum()) // 2
+    nr_ok = engine.neighbor_rows_checked(_dev(pos), box, r_cut, None, True, capacity=256 * 64)
+    _check_rows_vs_oracle(nr_ok, pos, None, box, r_cut, True)
+    batch = engine.neighbor_lists(_dev(pos), box, r_cut, None, True)
+    _check_batch_vs_oracle(batch, pos, None, box, r_cut, True)
+    dims = np.tile(np.concatenate([box, [90, 90, 90]]).astype(np.float32), (nf, 1))
+    lens, nr = engine.lens_from_positions(_dev(pos), box, r_cut, 1, capacity=256 * 64)
+    assert not nr.overflowed()
+    assert np.array_equal(lens.cpu().numpy(), lo.compute_lens_arrays(pos, dims, r_cut))
