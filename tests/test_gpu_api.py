@@ -310,3 +310,28 @@ def test_cfg1_full_size_lens_and_coordination_bit_exact():
     _, n_c = t.get_coord_number(r_cut=r_cut)
     assert np.array_equal(lens.dataset, lo.compute_lens_arrays(pos, dims, r_cut))
     assert np.array_equal(n_c.dataset, lo.coord_number_arrays(pos, dims, r_cut))
+
+
+@pytest.mark.parametrize("scale", [1.0, 1.35, 1.8, 2.4])
+def test_psi_phi_lane_groups_vs_oracle(scale):
+    """The psi / phi kernels use 4, 8, 16 or 32 lanes per atom depending on the mean row length:
+    every variant against the restated reference loops (rows of ~11 ... ~150 entries)."""
+    from golden_cases import fluid_case
+    from oracle import descriptors_oracle as do
+    from oracle import lens_oracle as lo
+
+    from dynsight_b200 import descriptors
+    from dynsight_b200.trajectory import Trj
+    from dynsight_b200.universe import ArrayUniverse
+
+    pos, box, r_cut = fluid_case(n_side=8, n_frames=3)
+    r_cut *= scale
+    dims = np.tile(np.concatenate([box, [90, 90, 90]]).astype(np.float32), (3, 1))
+    u = ArrayUniverse(pos, dims)
+    neig, n_c = Trj(u).get_coord_number(r_cut=r_cut)
+    csr = [lo.neighbors(pos[f], pos[f], r_cut, box, True) for f in range(3)]
+    assert abs(n_c.dataset.mean() - np.mean([np.diff(c[0]).mean() for c in csr])) < 1e-9
+    np.testing.assert_allclose(descriptors.orientational_order_param(u, neig, order=6),
+                               do.orientational_order_param(pos, csr, 6), rtol=1e-5, atol=1e-6)  # fmt: skip
+    np.testing.assert_allclose(descriptors.velocity_alignment(u, neig),
+                               do.velocity_alignment(pos, csr), rtol=1e-5, atol=1e-6)  # fmt: skip
