@@ -101,6 +101,11 @@ SIGNATURES: dict[str, tuple] = {
         _c_int,
         [_c_ptr, _c_i64, _c_int, _c_int, _c_int, _c_ptr, _c_size, _c_ptr, _c_ptr, _c_ptr],
     ),
+    "dsg_cross_tcf_workspace_bytes": (_c_int, [_c_int, _c_int, _c_int, ctypes.POINTER(_c_size)]),
+    "dsg_cross_time_correlation": (
+        _c_int,
+        [_c_ptr, _c_i64, _c_int, _c_int, _c_int, _c_ptr, _c_size, _c_ptr, _c_ptr, _c_ptr],
+    ),
     "dsg_xtc_index": (
         _c_int,
         [ctypes.c_char_p, ctypes.POINTER(_c_i64), ctypes.POINTER(ctypes.c_int32), _c_ptr, _c_i64],

@@ -130,3 +130,35 @@ def self_time_correlation(
     correlation_error = frames.to_host(std) / (valid * np.sqrt(n_part))
     norm_fact = correlation[0]
     return correlation / norm_fact, correlation_error / norm_fact
+
+
+def cross_time_correlation(
+    data: NDArray[np.float64] | torch.Tensor,
+    max_delay: int | None = None,
+) -> tuple[NDArray[np.float64], NDArray[np.float64]]:
+    """Computes the mean cross time correlation function for time-series.
+
+    For each ordered pair of particles ``i != j`` the cross-TCF of the mean-subtracted series is
+    computed; returns its average over the pairs and the standard error for the delays
+    ``0 .. max_delay - 1`` (time_correlations.py:95-178; not normalised at delay 0).
+
+    Raises:
+        ValueError: if ``max_delay`` is outside ``1 .. n_frames`` or there are fewer than two
+            particles (the reference returns NaN there).
+    """
+    dev = frames.device()
+    values = torch.as_tensor(data).to(device=dev, dtype=torch.float64).contiguous()
+    n_part, n_frames = values.shape
+    if max_delay is None:
+        max_delay = n_frames
+    if max_delay < 1 or max_delay > n_frames:
+        msg = f"max_delay={max_delay} must be in 1..{n_frames}"
+        raise ValueError(msg)
+    if n_part < 2:  # noqa: PLR2004
+        msg = "cross_time_correlation needs at least two particles"
+        raise ValueError(msg)
+    mean, std = engine.self_time_correlation_device(values, int(max_delay), cross=True)
+    valid = n_frames - np.arange(max_delay, dtype=np.float64)
+    cross_correlation = frames.to_host(mean) / valid
+    correlation_error = frames.to_host(std) / (valid * np.sqrt(n_part * (n_part - 1)))
+    return cross_correlation, correlation_error

@@ -33,26 +33,49 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return s;
 }
 
-template <bool SMEM>
+// CROSS = false: block b correlates row b with itself.  CROSS = true: block b is the ordered pair
+// (i, j), i != j, b = i (N-1) + (j < i ? j : j - 1); x_i(t) is multiplied with x_j(t + t').
+template <bool SMEM, bool CROSS>
 __global__ void __launch_bounds__(kTcfThreads)
-tcf_dot_kernel(const double* __restrict__ data, long long stride_i, int n_part, int n_frames,
-               int lag0, int n_lags, double* __restrict__ c) {
+tcf_dot_kernel(const double* __restrict__ data, long long stride_i, int n_part, int n_rows,
+               int n_frames, int lag0, int n_lags, double* __restrict__ c) {
     extern __shared__ __align__(16) double tcf_smem[];
     __shared__ double red[kTcfThreads / 32];
-    const int i = blockIdx.x, tid = threadIdx.x;
-    const double* __restrict__ row = data + (long long)i * stride_i;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    int ia = b, ib = b;
+    if (CROSS) {
+        ia = b / (n_part - 1);
+        const int jj = b - ia * (n_part - 1);
+        ib = jj < ia ? jj : jj + 1;
+    }
+    const double* __restrict__ row_a = data + (long long)ia * stride_i;
+    const double* __restrict__ row_b = data + (long long)ib * stride_i;
     double part = 0.0;
-    for (int t = tid; t < n_frames; t += kTcfThreads) part += row[t];
-    const double mean = block_sum(part, red) / (double)n_frames;
-    double* xs = tcf_smem;
+    for (int t = tid; t < n_frames; t += kTcfThreads) part += row_a[t];
+    const double mean_a = block_sum(part, red) / (double)n_frames;
+    double mean_b = mean_a;
+    if (CROSS) {
+        part = 0.0;
+        for (int t = tid; t < n_frames; t += kTcfThreads) part += row_b[t];
+        mean_b = block_sum(part, red) / (double)n_frames;
+    }
+    const int padded = tcf_pad(n_frames + kTcfTail) + 2;
+    double* xa = tcf_smem;
+    double* xb = CROSS ? tcf_smem + padded : tcf_smem;
     if (SMEM) {
-        for (int t = tid; t < n_frames + kTcfTail; t += kTcfThreads)
-            xs[tcf_pad(t)] = t < n_frames ? row[t] - mean : 0.0;
+        for (int t = tid; t < n_frames + kTcfTail; t += kTcfThreads) {
+            xa[tcf_pad(t)] = t < n_frames ? row_a[t] - mean_a : 0.0;
+            if (CROSS) xb[tcf_pad(t)] = t < n_frames ? row_b[t] - mean_b : 0.0;
+        }
         __syncthreads();
     }
-    auto x_at = [&](int t) -> double {
-        if (SMEM) return xs[tcf_pad(t)];
-        return t < n_frames ? row[t] - mean : 0.0;
+    auto a_at = [&](int t) -> double {
+        if (SMEM) return xa[tcf_pad(t)];
+        return t < n_frames ? row_a[t] - mean_a : 0.0;
+    };
+    auto b_at = [&](int t) -> double {
+        if (SMEM) return xb[tcf_pad(t)];
+        return t < n_frames ? row_b[t] - mean_b : 0.0;
     };
     for (int l_rel = tid * kTcfLags; l_rel < n_lags; l_rel += kTcfThreads * kTcfLags) {
         const int lag = lag0 + l_rel;
@@ -60,22 +83,22 @@ tcf_dot_kernel(const double* __restrict__ data, long long stride_i, int n_part, 
 #pragma unroll
         for (int k = 0; k < kTcfLags; ++k) {
             acc[k] = 0.0;
-            w[k] = x_at(min(lag + k, n_frames + kTcfTail - 1));
+            w[k] = b_at(min(lag + k, n_frames + kTcfTail - 1));
         }
         const int t_end = n_frames - lag;  // terms t >= t_end multiply zero padding
         for (int t = 0; t < t_end; t += kTcfLags) {
 #pragma unroll
             for (int u = 0; u < kTcfLags; ++u) {
-                const double a = x_at(t + u);
+                const double a = a_at(t + u);
 #pragma unroll
                 for (int k = 0; k < kTcfLags; ++k)
                     acc[k] = fma(a, w[(k + u) & (kTcfLags - 1)], acc[k]);  // w slot = x(t+u+lag+k)
-                w[u] = x_at(min(t + u + lag + kTcfLags, n_frames + kTcfTail - 1));
+                w[u] = b_at(min(t + u + lag + kTcfLags, n_frames + kTcfTail - 1));
             }
         }
 #pragma unroll
         for (int k = 0; k < kTcfLags; ++k)
-            if (l_rel + k < n_lags) c[(size_t)(l_rel + k) * n_part + i] = acc[k];
+            if (l_rel + k < n_lags) c[(size_t)(l_rel + k) * n_rows + b] = acc[k];
     }
 }
 
@@ -115,48 +138,87 @@ static int tcf_chunk_lags(int n_part, int max_delay) {
 
 using namespace dsg;
 
-extern "C" int dsg_tcf_workspace_bytes(int n_part, int n_frames, int max_delay, size_t* bytes_out) {
-    if (!bytes_out) return set_error(DSG_ERR_INVALID_ARGUMENT, "bytes_out is NULL");
-    if (n_part < 1 || n_frames < 1 || max_delay < 1 || max_delay > n_frames)
+static int tcf_impl(bool cross, const double* d_data, int64_t stride_i, int n_part, int n_frames,
+                    int max_delay, void* d_workspace, size_t workspace_bytes, double* d_mean_out,
+                    double* d_std_out, cudaStream_t st, size_t* bytes_only) {
+    if (n_part < (cross ? 2 : 1) || n_frames < 1 || max_delay < 1 || max_delay > n_frames)
         return set_error(DSG_ERR_INVALID_ARGUMENT,
-                         "n_part=%d, n_frames=%d, max_delay=%d: need 1 <= max_delay <= n_frames",
-                         n_part, n_frames, max_delay);
-    *bytes_out = 8 * (size_t)n_part * (size_t)tcf_chunk_lags(n_part, max_delay);
-    return DSG_OK;
-}
-
-extern "C" int dsg_self_time_correlation(const double* d_data, int64_t stride_i, int n_part,
-                                         int n_frames, int max_delay, void* d_workspace,
-                                         size_t workspace_bytes, double* d_mean_out,
-                                         double* d_std_out, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    size_t need = 0;
-    int rc = dsg_tcf_workspace_bytes(n_part, n_frames, max_delay, &need);
-    if (rc) return rc;
+                         "n_part=%d, n_frames=%d, max_delay=%d: need 1 <= max_delay <= n_frames%s",
+                         n_part, n_frames, max_delay, cross ? " and n_part >= 2" : "");
+    const long long rows_ll = cross ? (long long)n_part * (n_part - 1) : n_part;
+    if (rows_ll > 0x7fffffffLL) return set_error(DSG_ERR_OVERFLOW, "too many particle pairs");
+    const int n_rows = (int)rows_ll;
+    const int chunk = tcf_chunk_lags(n_rows, max_delay);
+    const size_t need = 8 * (size_t)n_rows * (size_t)chunk;
+    if (bytes_only) {
+        *bytes_only = need;
+        return DSG_OK;
+    }
     if (!d_data || !d_workspace || !d_mean_out || !d_std_out)
         return set_error(DSG_ERR_INVALID_ARGUMENT, "NULL device pointer argument");
     if (workspace_bytes < need)
         return set_error(DSG_ERR_WORKSPACE_TOO_SMALL, "workspace has %zu bytes, %zu needed",
                          workspace_bytes, need);
     double* c = (double*)d_workspace;
-    const int chunk = tcf_chunk_lags(n_part, max_delay);
-    const size_t smem = 8 * (size_t)(tcf_pad(n_frames + kTcfTail) + 2);
+    const size_t smem = 8 * (size_t)(tcf_pad(n_frames + kTcfTail) + 2) * (cross ? 2 : 1);
     const bool use_smem = smem <= 200 * 1024;
-    if (use_smem)
-        DSG_CUDA_CHECK(cudaFuncSetAttribute(tcf_dot_kernel<true>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (use_smem) {
+        if (cross)
+            DSG_CUDA_CHECK(cudaFuncSetAttribute(tcf_dot_kernel<true, true>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)smem));
+        else
+            DSG_CUDA_CHECK(cudaFuncSetAttribute(tcf_dot_kernel<true, false>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)smem));
+    }
     for (int lag0 = 0; lag0 < max_delay; lag0 += chunk) {
         const int n_lags = max_delay - lag0 < chunk ? max_delay - lag0 : chunk;
-        if (use_smem)
-            tcf_dot_kernel<true><<<n_part, kTcfThreads, smem, st>>>(d_data, stride_i, n_part,
-                                                                    n_frames, lag0, n_lags, c);
+        if (use_smem && cross)
+            tcf_dot_kernel<true, true><<<n_rows, kTcfThreads, smem, st>>>(
+                d_data, stride_i, n_part, n_rows, n_frames, lag0, n_lags, c);
+        else if (use_smem)
+            tcf_dot_kernel<true, false><<<n_rows, kTcfThreads, smem, st>>>(
+                d_data, stride_i, n_part, n_rows, n_frames, lag0, n_lags, c);
+        else if (cross)
+            tcf_dot_kernel<false, true><<<n_rows, kTcfThreads, 0, st>>>(
+                d_data, stride_i, n_part, n_rows, n_frames, lag0, n_lags, c);
         else
-            tcf_dot_kernel<false><<<n_part, kTcfThreads, 0, st>>>(d_data, stride_i, n_part, n_frames,
-                                                                  lag0, n_lags, c);
+            tcf_dot_kernel<false, false><<<n_rows, kTcfThreads, 0, st>>>(
+                d_data, stride_i, n_part, n_rows, n_frames, lag0, n_lags, c);
         DSG_LAUNCH_CHECK("tcf_dot_kernel");
-        tcf_stats_kernel<<<n_lags, kTcfThreads, 0, st>>>(c, n_part, n_lags, d_mean_out + lag0,
+        tcf_stats_kernel<<<n_lags, kTcfThreads, 0, st>>>(c, n_rows, n_lags, d_mean_out + lag0,
                                                         d_std_out + lag0);
         DSG_LAUNCH_CHECK("tcf_stats_kernel");
     }
     return DSG_OK;
+}
+
+extern "C" int dsg_tcf_workspace_bytes(int n_part, int n_frames, int max_delay, size_t* bytes_out) {
+    if (!bytes_out) return set_error(DSG_ERR_INVALID_ARGUMENT, "bytes_out is NULL");
+    return tcf_impl(false, nullptr, 0, n_part, n_frames, max_delay, nullptr, 0, nullptr, nullptr,
+                    nullptr, bytes_out);
+}
+
+extern "C" int dsg_self_time_correlation(const double* d_data, int64_t stride_i, int n_part,
+                                         int n_frames, int max_delay, void* d_workspace,
+                                         size_t workspace_bytes, double* d_mean_out,
+                                         double* d_std_out, void* stream) {
+    return tcf_impl(false, d_data, stride_i, n_part, n_frames, max_delay, d_workspace,
+                    workspace_bytes, d_mean_out, d_std_out, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int dsg_cross_tcf_workspace_bytes(int n_part, int n_frames, int max_delay,
+                                             size_t* bytes_out) {
+    if (!bytes_out) return set_error(DSG_ERR_INVALID_ARGUMENT, "bytes_out is NULL");
+    return tcf_impl(true, nullptr, 0, n_part, n_frames, max_delay, nullptr, 0, nullptr, nullptr,
+                    nullptr, bytes_out);
+}
+
+extern "C" int dsg_cross_time_correlation(const double* d_data, int64_t stride_i, int n_part,
+                                          int n_frames, int max_delay, void* d_workspace,
+                                          size_t workspace_bytes, double* d_mean_out,
+                                          double* d_std_out, void* stream) {
+    return tcf_impl(true, d_data, stride_i, n_part, n_frames, max_delay, d_workspace,
+                    workspace_bytes, d_mean_out, d_std_out, (cudaStream_t)stream, nullptr);
 }

@@ -415,10 +415,11 @@ def spatial_average_rows(
 
 
 def self_time_correlation_device(
-    data: torch.Tensor, max_delay: int
+    data: torch.Tensor, max_delay: int, cross: bool = False
 ) -> tuple[torch.Tensor, torch.Tensor]:
     """Per-lag mean and standard deviation over the particles of the un-normalised self
-    correlation ``c_i(t') = sum_t x_i(t) x_i(t+t')`` of the mean-subtracted rows of ``data``."""
+    correlation ``c_i(t') = sum_t x_i(t) x_i(t+t')`` of the mean-subtracted rows of ``data``
+    (``cross=True``: over all ordered pairs ``i != j`` of ``sum_t x_i(t) x_j(t+t')``)."""
     lib = _lib.load()
     _require_cuda(data, "data")
     if data.dtype != torch.float64 or data.ndim != 2 or data.stride(1) != 1:  # noqa: PLR2004
@@ -426,12 +427,14 @@ def self_time_correlation_device(
         raise ValueError(msg)
     n_part, n_frames = data.shape
     ws_bytes = ctypes.c_size_t(0)
-    _lib.check(lib.dsg_tcf_workspace_bytes(n_part, n_frames, int(max_delay), ctypes.byref(ws_bytes)))
+    ws_fn = lib.dsg_cross_tcf_workspace_bytes if cross else lib.dsg_tcf_workspace_bytes
+    run_fn = lib.dsg_cross_time_correlation if cross else lib.dsg_self_time_correlation
+    _lib.check(ws_fn(n_part, n_frames, int(max_delay), ctypes.byref(ws_bytes)))
     workspace = torch.empty(ws_bytes.value, dtype=torch.uint8, device=data.device)
     mean = torch.empty(int(max_delay), dtype=torch.float64, device=data.device)
     std = torch.empty_like(mean)
     _lib.check(
-        lib.dsg_self_time_correlation(
+        run_fn(
             data.data_ptr(), data.stride(0), n_part, n_frames, int(max_delay),
             workspace.data_ptr(), ws_bytes.value, mean.data_ptr(), std.data_ptr(), _stream_ptr(),
         )

@@ -258,6 +258,15 @@ int dsg_self_time_correlation(const double* d_data, int64_t stride_i, int n_part
                               int max_delay, void* d_workspace, size_t workspace_bytes,
                               double* d_mean_out, double* d_std_out, void* stream);
 
+/* Cross time-correlation (analysis/time_correlations.py:155-176): the same sums over all ordered
+ * pairs i != j, c_ij(t') = sum_t x_i(t) x_j(t + t'); mean / std over the n_part (n_part - 1) pairs
+ * per lag (n_part >= 2).  The caller divides by (n_frames - t') (no lag-0 normalisation there). */
+int dsg_cross_tcf_workspace_bytes(int n_part, int n_frames, int max_delay, size_t* bytes_out);
+
+int dsg_cross_time_correlation(const double* d_data, int64_t stride_i, int n_part, int n_frames,
+                               int max_delay, void* d_workspace, size_t workspace_bytes,
+                               double* d_mean_out, double* d_std_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * XTC ingest (host code; replaces the MDAnalysis XTCReader behind Trj.init_from_xtc,
  * trajectory/trajectory.py:68-79 -- SURVEY.md section 8f row 3).  Handles uncompressed

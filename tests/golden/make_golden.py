@@ -180,8 +180,18 @@ def main() -> None:
     np.random.seed(1234)  # doctest of time_correlations.py:44-57
     kat, _ = tcf_oracle.self_time_correlation(np.random.rand(100, 100))
     assert np.isclose(kat[1], 0.005519088806189553, rtol=1e-12)
-    np.savez_compressed(HERE / "tcorr.npz", t_corr=t_corr, std_dev=t_std,
-                        kat_rand_lag1=0.005519088806189553)
+    c_corr = np.load(REF_TESTS / "analysis/tcorr/c_corr.npy")
+    c_std = np.load(REF_TESTS / "analysis/tcorr/ctd_dev.npy")
+    cc, ce = tcf_oracle.cross_time_correlation(tcf_oracle.reference_walk())
+    print("cross tcf oracle vs reference golden:", np.abs(cc - c_corr).max(), np.abs(ce - c_std).max())
+    assert np.allclose(cc, c_corr, rtol=1e-11, atol=1e-13)
+    assert np.allclose(ce, c_std, rtol=1e-11, atol=1e-13)
+    np.random.seed(1234)  # doctest of time_correlations.py:128-141
+    kat_c, _ = tcf_oracle.cross_time_correlation(np.random.rand(100, 100))
+    assert np.isclose(kat_c[0], 0.0002474572311281272, rtol=1e-10)
+    np.savez_compressed(HERE / "tcorr.npz", t_corr=t_corr, std_dev=t_std, c_corr=c_corr,
+                        ctd_dev=c_std, kat_rand_lag1=0.005519088806189553,
+                        kat_cross_lag0=0.0002474572311281272)
     for f in sorted(HERE.glob("*.npz")):
         print(f.name, f.stat().st_size)
 

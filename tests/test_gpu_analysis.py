@@ -162,3 +162,29 @@ def test_tcf_errors():
 
     with pytest.raises(ValueError, match="max_delay"):
         analysis.self_time_correlation(np.zeros((3, 10)), 11)
+
+
+def test_cross_tcf_reference_goldens_and_oracle():
+    """tests/analysis/test_time_correlations.py:66-73 and the doctest of time_correlations.py:141,
+    plus random series against the oracle (all ordered pairs i != j)."""
+    from conftest import GOLDEN
+    from oracle import tcf_oracle
+
+    from dynsight_b200 import analysis
+
+    fx = np.load(GOLDEN / "tcorr.npz")
+    corr, std = analysis.cross_time_correlation(tcf_oracle.reference_walk())
+    assert np.allclose(corr, fx["c_corr"])
+    assert np.allclose(std, fx["ctd_dev"])
+    np.random.seed(1234)  # noqa: NPY002
+    time_corr, _ = analysis.cross_time_correlation(np.random.rand(100, 100))  # noqa: NPY002
+    assert np.isclose(time_corr[0], float(fx["kat_cross_lag0"]))
+    rng = np.random.default_rng(8)
+    for n_part, n_frames, max_delay in ((2, 50, None), (17, 300, 40), (6, 30000, 16)):
+        data = np.cumsum(rng.normal(size=(n_part, n_frames)), axis=1)
+        got_c, got_e = analysis.cross_time_correlation(data, max_delay)
+        want_c, want_e = tcf_oracle.cross_time_correlation(data, max_delay)
+        assert np.allclose(got_c, want_c, rtol=1e-9, atol=1e-9 * np.abs(want_c).max())
+        assert np.allclose(got_e, want_e, rtol=1e-8, atol=1e-9 * np.abs(want_e).max())
+    with pytest.raises(ValueError, match="two particles"):
+        analysis.cross_time_correlation(np.zeros((1, 10)))
