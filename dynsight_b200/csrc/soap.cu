@@ -302,11 +302,24 @@ __host__ __device__ constexpr int harm_len(int lt) {
     return lt != 8 ? (lt + 1) * (lt + 2) : harm_off(lt, lt) + 2 * lt + 2;
 }
 
+// Packed rows for l_max = 8 exactly (soap_kernel<8, 20, 0, 0, 0>): the longest-processing-time
+// packing gives lane group g the angular momenta {8 - g, 1 + g} with (17 - 2g) + (3 + 2g) = 20
+// values, so each group's values are laid out as one contiguous run of 20 doubles at g * 20 (no
+// padding; the four runs start 160 bytes apart = 8 banks, so the 128-bit broadcast reads of the four
+// groups never share a bank) and every lane accumulates exactly 20 slots instead of 17 + 9.
+constexpr int kPackSlots = 20;
+__host__ __device__ constexpr int pack_size0(int g) { return 17 - 2 * g; }
+template <int LT, bool PK>
+__host__ __device__ constexpr int hoff(int l) {
+    if (!PK) return harm_off(LT, l);
+    return l >= 5 ? (8 - l) * kPackSlots : (l - 1) * kPackSlots + pack_size0(l - 1);
+}
+
 // Phase B: un-normalised regular solid harmonics of one displacement:
 //   rt[off(l) + l + m] = S_l^m(z, r2) * A_m(x, y),   rt[off(l) + l - m] = S_l^m * B_m   (m > 0)
 //   A_m + i B_m = (x + i y)^m ;  S_m^m = (2m-1)!!, S_{m+1}^m = (2m+1) z S_m^m,
 //   S_l^m = ((2l-1) z S_{l-1}^m - (l+m-1) r2 S_{l-2}^m) / (l-m)
-template <int LT>
+template <int LT, bool PK>
 __device__ __forceinline__ void solid_harmonics(double x, double y, double z, double r2,
                                                 double* __restrict__ rt) {
     double am = 1.0, bm = 0.0, dfact = 1.0;
@@ -320,13 +333,13 @@ __device__ __forceinline__ void solid_harmonics(double x, double y, double z, do
         }
         double s0 = dfact;  // S_m^m
         if (m > 0) {
-            rt[harm_off(LT, m) + 2 * m] = s0 * am;
-            rt[harm_off(LT, m)] = s0 * bm;
+            rt[hoff<LT, PK>(m) + 2 * m] = s0 * am;
+            rt[hoff<LT, PK>(m)] = s0 * bm;
         }
         if (m + 1 <= LT) {
             double s1 = (double)(2 * m + 1) * z * s0;  // S_{m+1}^m
             {
-                const int o = harm_off(LT, m + 1) + m + 1;
+                const int o = hoff<LT, PK>(m + 1) + m + 1;
                 rt[o + m] = s1 * am;
                 if (m > 0) rt[o - m] = s1 * bm;
             }
@@ -335,7 +348,7 @@ __device__ __forceinline__ void solid_harmonics(double x, double y, double z, do
                 const double inv = 1.0 / (double)(l - m);  // compile-time constant after unrolling
                 const double s2 =
                     ((double)(2 * l - 1) * z * s1 - (double)(l + m - 1) * r2 * s0) * inv;
-                const int o = harm_off(LT, l) + l;
+                const int o = hoff<LT, PK>(l) + l;
                 rt[o + m] = s2 * am;
                 if (m > 0) rt[o - m] = s2 * bm;
                 s0 = s1;
@@ -357,6 +370,46 @@ __device__ __forceinline__ void accumulate(Acc<S>& a, double e, const double* __
         a.v[s + 1] = fma(e, v.y, a.v[s + 1]);
     }
     if (S & 1) a.v[S - 1] = fma(e, r[S - 1], a.v[S - 1]);
+}
+
+// packed l_max = 8 rows: slot s of lane group g belongs to l = 8 - g while s < 17 - 2g, to l = 1 + g
+// after that; e0 / e1 are the two Gaussians of the lane.  Slots 11..16 change owner with g: three
+// selects per neighbour instead of six padded FMAs and three padded 128-bit loads.
+__device__ __forceinline__ void accumulate_packed(Acc<kPackSlots>& a, double e0, double e1, int g,
+                                                  const double* __restrict__ r) {
+    const double2* __restrict__ r2p = reinterpret_cast<const double2*>(r);
+    const double ea = g < 3 ? e0 : e1, eb = g < 2 ? e0 : e1, ec = g < 1 ? e0 : e1;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const double2 v = r2p[s];
+        a.v[2 * s] = fma(e0, v.x, a.v[2 * s]);
+        a.v[2 * s + 1] = fma(e0, v.y, a.v[2 * s + 1]);
+    }
+    double2 v = r2p[5];
+    a.v[10] = fma(e0, v.x, a.v[10]);
+    a.v[11] = fma(ea, v.y, a.v[11]);
+    v = r2p[6];
+    a.v[12] = fma(ea, v.x, a.v[12]);
+    a.v[13] = fma(eb, v.y, a.v[13]);
+    v = r2p[7];
+    a.v[14] = fma(eb, v.x, a.v[14]);
+    a.v[15] = fma(ec, v.y, a.v[15]);
+    v = r2p[8];
+    a.v[16] = fma(ec, v.x, a.v[16]);
+    a.v[17] = fma(e1, v.y, a.v[17]);
+    v = r2p[9];
+    a.v[18] = fma(e1, v.x, a.v[18]);
+    a.v[19] = fma(e1, v.y, a.v[19]);
+}
+
+__device__ __forceinline__ void store_packed(const Acc<kPackSlots>& a, int g, int k, int n,
+                                             double* __restrict__ cz) {
+    const int size0 = pack_size0(g), la = 8 - g, lb = 1 + g;
+#pragma unroll
+    for (int s = 0; s < kPackSlots; ++s) {
+        const int lm = s < size0 ? la * la + s : lb * lb + s - size0;
+        cz[lm * n + k] = a.v[s];
+    }
 }
 
 template <int S>
@@ -456,9 +509,10 @@ __device__ __forceinline__ void mix_and_spectrum(const SoapArgs& a, const double
 // soap_spectrum_kernel finishes the centres.  No per-warp coefficient buffer is needed, so the
 // occupancy is the single-species one whatever the number of species.
 template <int LT, int S0, int S1, int S2, int S3, bool SPLIT>
-__global__ void __launch_bounds__(64, (S0 <= 17) ? DSG_SOAP_MIN_BLOCKS
+__global__ void __launch_bounds__(64, (S0 <= 20) ? DSG_SOAP_MIN_BLOCKS
                                                     : (S0 <= 21 ? DSG_SOAP_MIN_BLOCKS_L10 : 4))
 soap_kernel(const SoapArgs a) {
+    constexpr bool PK = LT == 8 && S0 == kPackSlots;  // packed l_max = 8 rows (see hoff)
     extern __shared__ __align__(16) double smem_all[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warps = blockDim.x >> 5;
@@ -573,17 +627,23 @@ soap_kernel(const SoapArgs a) {
                 const int nh = min(kChunk, fill - h0);
                 if (lane < nh) {   // phase B
                     const double* d = nbuf + (h0 + lane) * 4;
-                    solid_harmonics<LT>(d[0], d[1], d[2], d[3], rbuf + lane * P);
+                    solid_harmonics<LT, PK>(d[0], d[1], d[2], d[3], rbuf + lane * P);
                 }
                 __syncwarp();
 #pragma unroll kUnrollC
                 for (int jj = 0; jj < nh; ++jj) {   // phase C
                     const double r2 = nbuf[(h0 + jj) * 4 + 3];
                     const double* __restrict__ rt = rbuf + jj * P;
-                    if (S0 > 0) accumulate<S0>(a0, exp_scaled(gam[0] * r2, exp_tab), rt + ioff[0]);
-                    if (S1 > 0) accumulate<S1>(a1, exp_scaled(gam[1] * r2, exp_tab), rt + ioff[1]);
-                    if (S2 > 0) accumulate<S2>(a2, exp_scaled(gam[2] * r2, exp_tab), rt + ioff[2]);
-                    if (S3 > 0) accumulate<S3>(a3, exp_scaled(gam[3] * r2, exp_tab), rt + ioff[3]);
+                    if constexpr (PK) {
+                        const double e0 = exp_scaled(gam[0] * r2, exp_tab);
+                        const double e1 = exp_scaled(gam[1] * r2, exp_tab);
+                        accumulate_packed(a0, e0, e1, g, rt + g * kPackSlots);
+                    } else {
+                        if (S0 > 0) accumulate<S0>(a0, exp_scaled(gam[0] * r2, exp_tab), rt + ioff[0]);
+                        if (S1 > 0) accumulate<S1>(a1, exp_scaled(gam[1] * r2, exp_tab), rt + ioff[1]);
+                        if (S2 > 0) accumulate<S2>(a2, exp_scaled(gam[2] * r2, exp_tab), rt + ioff[2]);
+                        if (S3 > 0) accumulate<S3>(a3, exp_scaled(gam[3] * r2, exp_tab), rt + ioff[3]);
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < kChunk / 4; ++q) {   // l = 0, a quarter of the chunk per lane
@@ -736,7 +796,8 @@ soap_kernel(const SoapArgs a) {
                            : rbuf;
         if (kact) {
             if (g == 0) cz[k] = acc00;  // lm = 0: S_0^0 = 1
-            store_item<S0>(a0, il[0], k, n, cz);
+            if constexpr (PK) store_packed(a0, g, k, n, cz);
+            else store_item<S0>(a0, il[0], k, n, cz);
             store_item<S1>(a1, il[1], k, n, cz);
             store_item<S2>(a2, il[2], k, n, cz);
             store_item<S3>(a3, il[3], k, n, cz);
@@ -986,6 +1047,7 @@ static int soap_layout(int n_frames, int n_atoms, int n_cent, int n_species, int
 
 // lt = compile-time l cap of the instantiation, s0 = its widest item
 static void make_plan(int n_species, int n_max, int l_max, int lt, int s0, SoapPlan* pl) {
+    const bool packed = lt == 8 && s0 == kPackSlots;
     pl->n_max = n_max;
     pl->l_max = l_max;
     pl->n_species = n_species;
@@ -994,7 +1056,7 @@ static void make_plan(int n_species, int n_max, int l_max, int lt, int s0, SoapP
     // harmonics rows (harm_len doubles per neighbour); the stride is = 2 mod 4 so that the
     // phase-B stores of the lanes spread over the banks
     pl->kblocks = (n_max + kKBlock - 1) / kKBlock;
-    int p = harm_len(lt);
+    int p = packed ? kGroups * kPackSlots : harm_len(lt);
     while (p % (lt == 8 ? 4 : 16) != 2) ++p;
     pl->row_stride = p;
     int rb = kChunk * p + s0 + 2;  // tail: item rows are read S_t wide past the last row
@@ -1015,7 +1077,7 @@ static void make_plan(int n_species, int n_max, int l_max, int lt, int s0, SoapP
         int best = 0;
         for (int g = 1; g < kGroups; ++g)
             if (load[g] < load[best]) best = g;
-        pl->item_off[best][cnt[best]] = harm_off(lt, l);
+        pl->item_off[best][cnt[best]] = packed ? hoff<8, true>(l) : harm_off(lt, l);
         pl->item_l[best][cnt[best]++] = l;
         load[best] += 2 * l + 1;
     }
@@ -1158,7 +1220,11 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     int lt, s0;
     if (l_max <= 4) { lt = 4; s0 = 9; }
     else if (l_max <= 6) { lt = 6; s0 = 13; }
-    else if (l_max <= 8) { lt = 8; s0 = 17; }
+#ifndef DSG_SOAP_PACK
+#define DSG_SOAP_PACK 1
+#endif
+    else if (l_max < 8 || (l_max == 8 && !DSG_SOAP_PACK)) { lt = 8; s0 = 17; }
+    else if (l_max == 8) { lt = 8; s0 = kPackSlots; }  // packed rows: 20 slots per lane
     else if (l_max <= 10) { lt = 10; s0 = 21; }
     else { lt = 12; s0 = 25; }
     make_plan(n_species, n_max, l_max, lt, s0, &a.plan);
@@ -1208,7 +1274,14 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     } while (0)
     if (l_max <= 4) DSG_SOAP_LAUNCH(4, 9, 0, 0, 0);
     else if (l_max <= 6) DSG_SOAP_LAUNCH(6, 13, 5, 0, 0);
-    else if (l_max <= 8) DSG_SOAP_LAUNCH(8, 17, 9, 0, 0);
+    else if (l_max < 8 || (l_max == 8 && !DSG_SOAP_PACK)) DSG_SOAP_LAUNCH(8, 17, 9, 0, 0);
+    else if (l_max == 8) {
+        // the packed kernel hard-codes the packing {8 - g, 1 + g} of lane group g
+        for (int g = 0; g < kGroups; ++g)
+            if (a.plan.item_l[g][0] != 8 - g || a.plan.item_l[g][1] != 1 + g)
+                return set_error(DSG_ERR_UNSUPPORTED, "unexpected l packing for l_max = 8");
+        DSG_SOAP_LAUNCH(8, kPackSlots, 0, 0, 0);
+    }
     else if (l_max <= 10) DSG_SOAP_LAUNCH(10, 21, 13, 5, 0);
     else DSG_SOAP_LAUNCH(12, 25, 17, 9, 0);
 #undef DSG_SOAP_LAUNCH
