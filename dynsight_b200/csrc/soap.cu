@@ -52,6 +52,9 @@ constexpr int kListCap = 32;     // displacement list entries per warp
 constexpr int kCellTab = 32;     // (cell range, shift) entries resolved per pass
 constexpr int kBatchCap = 64;    // 32-candidate batches listed per pass
 constexpr int kBatchDoubles = kBatchCap * 3 / 2;  // int2 + int per batch
+__host__ __device__ constexpr int soap_warp_fixed(bool list) {
+    return list ? kListCap * 4 + kCellTab * 3 : kListCap * 4 + kCellTab * 4 + kBatchDoubles;
+}
 
 enum AxisMode : int { kWide = 0, kNarrow = 1, kOpen = 2 };
 
@@ -100,8 +103,16 @@ struct SoapArgs {
     double* out;
     long long stride_i, stride_f;
     double* gscr;           // split mode: primitive sums G (n_frames, n_cent, S, n_lm, n)
+    // neighbour rows built by soap_list_kernel (list mode): row of sorted slot s at rows + s * row_cap,
+    // entry = slot of the neighbour inside its frame | (cell-table entry 0..26) << kListEntryShift
+    int* rows;
+    int* rowcnt;
+    int row_cap;
+    int* list_flag;         // != 0: some row overflowed row_cap -> the in-kernel gather runs instead
+    int list_role;          // 0 no lists; 1 consumer of the lists; 2 fallback (runs iff the flag is set)
     SoapPlan plan;
 };
+constexpr int kListEntryShift = 26;
 
 // ---- orderable encoding of floats for atomicMin/Max ---------------------------------------
 __device__ __forceinline__ unsigned enc_float(float v) {
@@ -232,6 +243,69 @@ __global__ void __launch_bounds__(256)
 soap_centre_map_kernel(const int* __restrict__ centres, int n_cent, int* __restrict__ map) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_cent) map[centres[i]] = i;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// list mode: neighbour rows of every centre, one thread per sorted slot
+// ------------------------------------------------------------------------------------------
+// The distance search of the main kernel costs a warp 27 dependent rounds of candidate loads per
+// centre (about a fifth of its time, all exposed latency at 3 resident warps per scheduler).  For
+// periodic frames with >= 3 cells per axis this kernel does the search instead, one *thread* per
+// centre at full occupancy: consecutive threads sit in the same cell, so their candidate loads are
+// warp-wide broadcasts.  It keeps, per centre, the list of (neighbour slot, cell-table entry) codes
+// in the order the in-kernel gather would have found them; the main kernel then fetches 32
+// neighbours per round trip, one per lane, and recomputes the displacements itself.
+__global__ void __launch_bounds__(128)
+soap_list_kernel(const SoapArgs a) {
+    const int f = blockIdx.y;
+    const int slot_local = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot_local >= a.n_atoms) return;
+    const size_t slot = (size_t)f * a.n_atoms + slot_local;
+    if (a.centre_of_atom[a.sid[slot]] < 0) return;
+    const SoapFrame* __restrict__ fr = a.frames + f;
+    const double xc = a.sx[slot], yc = a.sy[slot], zc = a.sz[slot];
+    int cc[3];
+    {
+        double w[3];
+        soap_locate(fr, xc, yc, zc, w, cc);
+    }
+    const int nc0 = fr->nc[0], nc1 = fr->nc[1], nc2 = fr->nc[2];
+    const double b0 = fr->box[0], b1 = fr->box[1], b2 = fr->box[2];
+    const int cell_base = fr->cell_base;
+    const int frame_first = f * a.n_atoms;
+    int* __restrict__ row = a.rows + slot * (size_t)a.row_cap;
+    const int cap = a.row_cap;
+    const double r2max = a.r2max;
+    int cnt = 0;
+    for (int i0 = 0; i0 < 3; ++i0) {
+        int c0 = cc[0] + i0 - 1;
+        double s0 = -xc;
+        if (c0 < 0) { c0 += nc0; s0 -= b0; } else if (c0 >= nc0) { c0 -= nc0; s0 += b0; }
+        for (int i1 = 0; i1 < 3; ++i1) {
+            int c1 = cc[1] + i1 - 1;
+            double s1 = -yc;
+            if (c1 < 0) { c1 += nc1; s1 -= b1; } else if (c1 >= nc1) { c1 -= nc1; s1 += b1; }
+            for (int i2 = 0; i2 < 3; ++i2) {
+                int c2 = cc[2] + i2 - 1;
+                double s2 = -zc;
+                if (c2 < 0) { c2 += nc2; s2 -= b2; } else if (c2 >= nc2) { c2 -= nc2; s2 += b2; }
+                const int cell = cell_base + (c0 * nc1 + c1) * nc2 + c2;
+                const int qb = a.cell_start[cell], qe = a.cell_start[cell + 1];
+                const int ecode = ((i0 * 3 + i1) * 3 + i2) << kListEntryShift;
+                for (int q = qb; q < qe; ++q) {
+                    const double dx = a.sx[q] + s0, dy = a.sy[q] + s1, dz = a.sz[q] + s2;
+                    const double r2 = dx * dx + dy * dy + dz * dz;
+                    if (r2 <= r2max) {
+                        if (cnt < cap) row[cnt] = (q - frame_first) | ecode;
+                        ++cnt;
+                    }
+                }
+            }
+        }
+    }
+    a.rowcnt[slot] = cnt;
+    if (cnt > cap) *a.list_flag = 1;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -508,11 +582,27 @@ __device__ __forceinline__ void mix_and_spectrum(const SoapArgs& a, const double
 // (species, radial block) pass and writes that slice of G to a global scratch;
 // soap_spectrum_kernel finishes the centres.  No per-warp coefficient buffer is needed, so the
 // occupancy is the single-species one whatever the number of species.
-template <int LT, int S0, int S1, int S2, int S3, bool SPLIT>
-__global__ void __launch_bounds__(64, (S0 <= 20) ? DSG_SOAP_MIN_BLOCKS
-                                                    : (S0 <= 21 ? DSG_SOAP_MIN_BLOCKS_L10 : 4))
+#ifndef DSG_SOAP_LIST_WARPS
+#define DSG_SOAP_LIST_WARPS 2
+#endif
+#ifndef DSG_SOAP_LIST_BLOCKS
+#define DSG_SOAP_LIST_BLOCKS 6
+#endif
+// List mode needs neither the prefetch registers nor the batch tables of the in-kernel search, so
+// it also fits 4 blocks of 4 warps per SM at 128 registers (DSG_SOAP_LIST_WARPS=4,
+// DSG_SOAP_LIST_BLOCKS=4).  Measured on the 100 000-atom box: 4.30e7 centre-frames/s for 4 x 4
+// against 4.38e7 for 6 x 2 at 168 registers -- the tighter register budget costs the schedule what
+// the four extra warps bring, so the default stays 6 x 2.
+constexpr int kListWarps = DSG_SOAP_LIST_WARPS;
+template <int LT, int S0, int S1, int S2, int S3, bool SPLIT, bool LIST>
+__global__ void __launch_bounds__(
+    (LIST && S0 <= 20) ? 32 * kListWarps : 64,
+    (S0 <= 20) ? (LIST ? DSG_SOAP_LIST_BLOCKS : DSG_SOAP_MIN_BLOCKS)
+               : (S0 <= 21 ? DSG_SOAP_MIN_BLOCKS_L10 : 4))
 soap_kernel(const SoapArgs a) {
     constexpr bool PK = LT == 8 && S0 == kPackSlots;  // packed l_max = 8 rows (see hoff)
+    // list mode: the consumer runs unless a row overflowed, the fallback only if one did
+    if (a.list_role != 0 && ((*a.list_flag != 0) != (a.list_role == 2))) return;
     extern __shared__ __align__(16) double smem_all[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warps = blockDim.x >> 5;
@@ -553,13 +643,15 @@ soap_kernel(const SoapArgs a) {
     const SoapPlan& pl = a.plan;
     const int n = pl.n_max, P = pl.row_stride, n_lm = pl.n_lm;
     const int c_doubles = pl.n_species * n_lm * n;
-    const int per_warp = (kListCap * 4 + kCellTab * 4 + kBatchDoubles + pl.rbuf_doubles + 1) & ~1;
+    // per-warp fixed part: displacement list + cell table (+ batch list of the in-kernel search)
+    constexpr int kWarpFixed = soap_warp_fixed(LIST);
+    const int per_warp = (kWarpFixed + pl.rbuf_doubles + 1) & ~1;
     double* nbuf = smem + (size_t)warp * per_warp;     // [32][4] dx dy dz r2
     double* tab_sh = nbuf + kListCap * 4;                // [3][32] image shifts of the cell table
     int2* tab_q = reinterpret_cast<int2*>(tab_sh + 3 * kCellTab);  // [32] candidate ranges
     int2* bl_q = reinterpret_cast<int2*>(tab_sh + kCellTab * 4);   // [64] batch (start, count)
     int* bl_e = reinterpret_cast<int*>(bl_q + kBatchCap);             // [64] batch -> table entry
-    double* rbuf = tab_sh + kCellTab * 4 + kBatchDoubles;  // [kChunk][P] harmonics; later G / mixed
+    double* rbuf = nbuf + kWarpFixed;  // [kChunk][P] harmonics; later G / mixed
 
     const SoapFrame* __restrict__ fr = a.frames + f;
     int ne[3], mode[3], nc[3], nimg[3];
@@ -630,9 +722,11 @@ soap_kernel(const SoapArgs a) {
                     solid_harmonics<LT, PK>(d[0], d[1], d[2], d[3], rbuf + lane * P);
                 }
                 __syncwarp();
+                double r2_next = nbuf[h0 * 4 + 3];   // one neighbour ahead: hides the shared load
 #pragma unroll kUnrollC
                 for (int jj = 0; jj < nh; ++jj) {   // phase C
-                    const double r2 = nbuf[(h0 + jj) * 4 + 3];
+                    const double r2 = r2_next;
+                    r2_next = nbuf[(h0 + min(jj + 1, nh - 1)) * 4 + 3];
                     const double* __restrict__ rt = rbuf + jj * P;
                     if constexpr (PK) {
                         const double e0 = exp_scaled(gam[0] * r2, exp_tab);
@@ -654,139 +748,185 @@ soap_kernel(const SoapArgs a) {
             }
         };
 
-        // ---- gather ----
-        // The (cell range, image shift) entries around the centre's cell are resolved by the
-        // lanes in parallel into a per-warp table; consecutive centres of the same cell reuse it.
-        int fill = 0;
-        const int n_ent_total = ne[0] * ne[1] * ne[2];
+        if constexpr (LIST) {
+        // ---- gather from the rows of soap_list_kernel: 32 neighbours per round trip ----
         const int my_cell = (cc[0] * nc[1] + cc[1]) * nc[2] + cc[2];
-        for (int e0 = 0; e0 < n_ent_total; e0 += kCellTab) {
-            if (!(n_ent_total <= kCellTab && cached_cell == my_cell)) {
-                __syncwarp();
-                const int e = e0 + lane;
-                int qb = 0, qe = 0;
-                double sh[3] = {0.0, 0.0, 0.0};
-                if (e < n_ent_total) {
-                    int idx[3];
-                    idx[2] = e % ne[2];
-                    idx[1] = (e / ne[2]) % ne[1];
-                    idx[0] = e / (ne[2] * ne[1]);
-                    int cj[3];
-                    bool ok = true;
+        if (cached_cell != my_cell) {   // image shifts of the 27 cell-table entries
+            __syncwarp();
+            if (lane < 27) {
+                const int idx[3] = {lane / 9, (lane / 3) % 3, lane % 3};
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) {
-                        if (mode[d] == kNarrow) {
-                            cj[d] = 0;
-                            sh[d] = (double)(idx[d] - nimg[d]) * box[d];
-                        } else {
-                            cj[d] = cc[d] + idx[d] - 1;
-                            if (mode[d] == kWide) {
-                                if (cj[d] < 0) { cj[d] += nc[d]; sh[d] = -box[d]; }
-                                else if (cj[d] >= nc[d]) { cj[d] -= nc[d]; sh[d] = box[d]; }
-                            } else if (cj[d] < 0 || cj[d] >= nc[d]) ok = false;
+                for (int d = 0; d < 3; ++d) {
+                    const int cj = cc[d] + idx[d] - 1;
+                    tab_sh[d * kCellTab + lane] = cj < 0 ? -box[d] : (cj >= nc[d] ? box[d] : 0.0);
+                }
+            }
+            __syncwarp();
+            cached_cell = my_cell;
+        }
+        const int n_nb = a.rowcnt[slot];
+        const int* __restrict__ row = a.rows + slot * (size_t)a.row_cap;
+        const size_t frame_first = (size_t)f * a.n_atoms;
+        // coordinates one batch ahead, list codes two batches ahead (two dependent round trips)
+        double px = 0.0, py = 0.0, pz = 0.0;
+        int pe = 0;
+        auto fetch = [&](int code, int h) {
+            if (h < n_nb) {
+                const size_t q = frame_first + (size_t)(code & ((1 << kListEntryShift) - 1));
+                pe = code >> kListEntryShift;
+                px = a.sx[q]; py = a.sy[q]; pz = a.sz[q];
+            }
+        };
+        fetch(lane < n_nb ? row[lane] : 0, lane);
+        int code_next = 32 + lane < n_nb ? row[32 + lane] : 0;
+        for (int h0 = 0; h0 < n_nb; h0 += 32) {
+            const int nh = min(32, n_nb - h0);
+            if (lane < nh) {
+                const double dx = px + tab_sh[pe] - xc, dy = py + tab_sh[kCellTab + pe] - yc;
+                const double dz = pz + tab_sh[2 * kCellTab + pe] - zc;
+                double* d = nbuf + lane * 4;
+                d[0] = dx; d[1] = dy; d[2] = dz; d[3] = dx * dx + dy * dy + dz * dz;
+            }
+            fetch(code_next, h0 + 32 + lane);
+            code_next = h0 + 64 + lane < n_nb ? row[h0 + 64 + lane] : 0;
+            __syncwarp();
+            process(nh);
+        }
+        } else {
+            // ---- gather ----
+            // The (cell range, image shift) entries around the centre's cell are resolved by the
+            // lanes in parallel into a per-warp table; consecutive centres of the same cell reuse it.
+            int fill = 0;
+            const int n_ent_total = ne[0] * ne[1] * ne[2];
+            const int my_cell = (cc[0] * nc[1] + cc[1]) * nc[2] + cc[2];
+            for (int e0 = 0; e0 < n_ent_total; e0 += kCellTab) {
+                if (!(n_ent_total <= kCellTab && cached_cell == my_cell)) {
+                    __syncwarp();
+                    const int e = e0 + lane;
+                    int qb = 0, qe = 0;
+                    double sh[3] = {0.0, 0.0, 0.0};
+                    if (e < n_ent_total) {
+                        int idx[3];
+                        idx[2] = e % ne[2];
+                        idx[1] = (e / ne[2]) % ne[1];
+                        idx[0] = e / (ne[2] * ne[1]);
+                        int cj[3];
+                        bool ok = true;
+    #pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            if (mode[d] == kNarrow) {
+                                cj[d] = 0;
+                                sh[d] = (double)(idx[d] - nimg[d]) * box[d];
+                            } else {
+                                cj[d] = cc[d] + idx[d] - 1;
+                                if (mode[d] == kWide) {
+                                    if (cj[d] < 0) { cj[d] += nc[d]; sh[d] = -box[d]; }
+                                    else if (cj[d] >= nc[d]) { cj[d] -= nc[d]; sh[d] = box[d]; }
+                                } else if (cj[d] < 0 || cj[d] >= nc[d]) ok = false;
+                            }
+                        }
+                        if (ok) {
+                            const int cell = cell_base + (cj[0] * nc[1] + cj[1]) * nc[2] + cj[2];
+                            qb = a.cell_start[cell];
+                            qe = a.cell_start[cell + 1];
                         }
                     }
-                    if (ok) {
-                        const int cell = cell_base + (cj[0] * nc[1] + cj[1]) * nc[2] + cj[2];
-                        qb = a.cell_start[cell];
-                        qe = a.cell_start[cell + 1];
+                    tab_q[lane] = make_int2(qb, qe);
+                    tab_sh[lane] = sh[0];
+                    tab_sh[kCellTab + lane] = sh[1];
+                    tab_sh[2 * kCellTab + lane] = sh[2];
+                    // flat list of 32-candidate batches so that loads can be prefetched across cells
+                    const int nbat = qe > qb ? (qe - qb + 31) >> 5 : 0;
+                    int incl = nbat;
+    #pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const int t = __shfl_up_sync(kFullS, incl, off);
+                        if (lane >= off) incl += t;
                     }
-                }
-                tab_q[lane] = make_int2(qb, qe);
-                tab_sh[lane] = sh[0];
-                tab_sh[kCellTab + lane] = sh[1];
-                tab_sh[2 * kCellTab + lane] = sh[2];
-                // flat list of 32-candidate batches so that loads can be prefetched across cells
-                const int nbat = qe > qb ? (qe - qb + 31) >> 5 : 0;
-                int incl = nbat;
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const int t = __shfl_up_sync(kFullS, incl, off);
-                    if (lane >= off) incl += t;
-                }
-                n_batches = __shfl_sync(kFullS, incl, 31);
-                if (n_batches <= kBatchCap) {
-                    for (int i = 0; i < nbat; ++i) {
-                        bl_q[incl - nbat + i] = make_int2(qb + 32 * i, min(32, qe - qb - 32 * i));
-                        bl_e[incl - nbat + i] = lane;
+                    n_batches = __shfl_sync(kFullS, incl, 31);
+                    if (n_batches <= kBatchCap) {
+                        for (int i = 0; i < nbat; ++i) {
+                            bl_q[incl - nbat + i] = make_int2(qb + 32 * i, min(32, qe - qb - 32 * i));
+                            bl_e[incl - nbat + i] = lane;
+                        }
                     }
-                }
-                __syncwarp();
-                cached_cell = n_ent_total <= kCellTab ? my_cell : -1;
-            }
-            auto consume = [&](double dx, double dy, double dz, double r2, bool hit) {
-                const unsigned m = __ballot_sync(kFullS, hit);
-                if (m == 0u) return;
-                const int cnt = __popc(m), rank = __popc(m & lt_mask);
-                const int room = kListCap - fill;
-                if (hit && rank < room) {
-                    double* d = nbuf + (fill + rank) * 4;
-                    d[0] = dx; d[1] = dy; d[2] = dz; d[3] = r2;
-                }
-                if (cnt >= room) {
                     __syncwarp();
-                    process(kListCap);
-                    if (hit && rank >= room) {
-                        double* d = nbuf + (rank - room) * 4;
+                    cached_cell = n_ent_total <= kCellTab ? my_cell : -1;
+                }
+                auto consume = [&](double dx, double dy, double dz, double r2, bool hit) {
+                    const unsigned m = __ballot_sync(kFullS, hit);
+                    if (m == 0u) return;
+                    const int cnt = __popc(m), rank = __popc(m & lt_mask);
+                    const int room = kListCap - fill;
+                    if (hit && rank < room) {
+                        double* d = nbuf + (fill + rank) * 4;
                         d[0] = dx; d[1] = dy; d[2] = dz; d[3] = r2;
                     }
-                    fill = cnt - room;
-                } else {
-                    fill += cnt;
-                }
-            };
-            if (n_batches <= kBatchCap) {
-                // two batches in flight ahead of the one being tested
-                double x1 = 0.0, y1 = 0.0, z1 = 0.0, x2 = 0.0, y2 = 0.0, z2 = 0.0;
-                bool v1 = false, v2 = false;
-                auto fetch = [&](int b, double& x, double& y, double& z, bool& valid) {
-                    valid = false;
-                    if (b < n_batches) {
-                        const int2 q = bl_q[b];
-                        if (lane < q.y) {
-                            x = a.sx[q.x + lane]; y = a.sy[q.x + lane]; z = a.sz[q.x + lane];
-                            valid = true;
+                    if (cnt >= room) {
+                        __syncwarp();
+                        process(kListCap);
+                        if (hit && rank >= room) {
+                            double* d = nbuf + (rank - room) * 4;
+                            d[0] = dx; d[1] = dy; d[2] = dz; d[3] = r2;
                         }
+                        fill = cnt - room;
+                    } else {
+                        fill += cnt;
                     }
                 };
-                fetch(0, x1, y1, z1, v1);
-                fetch(1, x2, y2, z2, v2);
-                for (int b = 0; b < n_batches; ++b) {
-                    const int e = bl_e[b];
-                    const double vx = x1, vy = y1, vz = z1;
-                    const bool vv = v1;
-                    x1 = x2; y1 = y2; z1 = z2; v1 = v2;
-                    fetch(b + 2, x2, y2, z2, v2);
-                    const double dx = vx + tab_sh[e] - xc, dy = vy + tab_sh[kCellTab + e] - yc;
-                    const double dz = vz + tab_sh[2 * kCellTab + e] - zc;
-                    const double r2 = dx * dx + dy * dy + dz * dz;
-                    consume(dx, dy, dz, r2, vv && r2 <= a.r2max);
-                }
-            } else {
-                const int n_ent = min(kCellTab, n_ent_total - e0);
-                for (int t = 0; t < n_ent; ++t) {
-                    const int2 qr = tab_q[t];
-                    const int qb = qr.x, qe = qr.y;
-                    if (qb >= qe) continue;
-                    const double shx = tab_sh[t], shy = tab_sh[kCellTab + t];
-                    const double shz = tab_sh[2 * kCellTab + t];
-                    for (int q0 = qb; q0 < qe; q0 += 32) {
-                        const int q = q0 + lane;
-                        double dx = 0.0, dy = 0.0, dz = 0.0, r2 = 0.0;
-                        bool hit = false;
-                        if (q < qe) {
-                            dx = a.sx[q] + shx - xc; dy = a.sy[q] + shy - yc;
-                            dz = a.sz[q] + shz - zc;
-                            r2 = dx * dx + dy * dy + dz * dz;
-                            hit = r2 <= a.r2max;
+                if (n_batches <= kBatchCap) {
+                    // two batches in flight ahead of the one being tested
+                    double x1 = 0.0, y1 = 0.0, z1 = 0.0, x2 = 0.0, y2 = 0.0, z2 = 0.0;
+                    bool v1 = false, v2 = false;
+                    auto fetch = [&](int b, double& x, double& y, double& z, bool& valid) {
+                        valid = false;
+                        if (b < n_batches) {
+                            const int2 q = bl_q[b];
+                            if (lane < q.y) {
+                                x = a.sx[q.x + lane]; y = a.sy[q.x + lane]; z = a.sz[q.x + lane];
+                                valid = true;
+                            }
                         }
-                        consume(dx, dy, dz, r2, hit);
+                    };
+                    fetch(0, x1, y1, z1, v1);
+                    fetch(1, x2, y2, z2, v2);
+                    for (int b = 0; b < n_batches; ++b) {
+                        const int e = bl_e[b];
+                        const double vx = x1, vy = y1, vz = z1;
+                        const bool vv = v1;
+                        x1 = x2; y1 = y2; z1 = z2; v1 = v2;
+                        fetch(b + 2, x2, y2, z2, v2);
+                        const double dx = vx + tab_sh[e] - xc, dy = vy + tab_sh[kCellTab + e] - yc;
+                        const double dz = vz + tab_sh[2 * kCellTab + e] - zc;
+                        const double r2 = dx * dx + dy * dy + dz * dz;
+                        consume(dx, dy, dz, r2, vv && r2 <= a.r2max);
+                    }
+                } else {
+                    const int n_ent = min(kCellTab, n_ent_total - e0);
+                    for (int t = 0; t < n_ent; ++t) {
+                        const int2 qr = tab_q[t];
+                        const int qb = qr.x, qe = qr.y;
+                        if (qb >= qe) continue;
+                        const double shx = tab_sh[t], shy = tab_sh[kCellTab + t];
+                        const double shz = tab_sh[2 * kCellTab + t];
+                        for (int q0 = qb; q0 < qe; q0 += 32) {
+                            const int q = q0 + lane;
+                            double dx = 0.0, dy = 0.0, dz = 0.0, r2 = 0.0;
+                            bool hit = false;
+                            if (q < qe) {
+                                dx = a.sx[q] + shx - xc; dy = a.sy[q] + shy - yc;
+                                dz = a.sz[q] + shz - zc;
+                                r2 = dx * dx + dy * dy + dz * dz;
+                                hit = r2 <= a.r2max;
+                            }
+                            consume(dx, dy, dz, r2, hit);
+                        }
                     }
                 }
             }
+            __syncwarp();
+            if (fill > 0) process(fill);
         }
-        __syncwarp();
-        if (fill > 0) process(fill);
 
         // ---- registers -> G[z][lm][k] (shared: fused epilogue; global: split mode) ----
         acc00 += __shfl_xor_sync(kFullS, acc00, 8);
@@ -930,6 +1070,9 @@ struct SoapLayout {
     size_t off_tile = 0, off_gscr = 0, off_tasks = 0;
     int n_tasks = 0;
     size_t off_gamma = 0, off_bmat = 0, off_wlm = 0, off_lml = 0, off_decode = 0, off_exptab = 0;
+    // list mode (soap_list_kernel): fused single-species kernel, periodic, >= 3 cells per axis
+    int row_cap = 0;  // 0 = the main kernel searches by itself
+    size_t off_rows = 0, off_rowcnt = 0, off_listflag = 0;
     size_t bytes = 0;
 };
 
@@ -967,6 +1110,8 @@ static int soap_layout(int n_frames, int n_atoms, int n_cent, int n_species, int
     const double r_cell = soap_radius(r_cut) * (1.0 + 1e-9);
     L->periodic = h_box != nullptr;
     long long total = 0;
+    bool any_narrow = false;
+    double k_max = 0.0;   // expected neighbours inside the search radius at the densest frame
     if (frames) frames->assign(n_frames, SoapFrame{});
     for (int f = 0; f < n_frames; ++f) {
         long long cells = 1;
@@ -992,7 +1137,12 @@ static int soap_layout(int n_frames, int n_atoms, int n_cent, int n_species, int
                 }
                 fr.inv_edge[k] = (double)fr.nc[k] / b;
                 cells *= fr.nc[k];
+                any_narrow = any_narrow || fr.mode[k] == kNarrow;
             }
+            const double rs = soap_radius(r_cut);
+            const double k_est = (double)n_atoms * 4.18879020478639 * rs * rs * rs /
+                                 (h_box[3 * f] * h_box[3 * f + 1] * h_box[3 * f + 2]);
+            if (k_est > k_max) k_max = k_est;
         } else {
             cells = (long long)kOpenCellsPerAxis * kOpenCellsPerAxis * kOpenCellsPerAxis;
             for (int k = 0; k < 3; ++k) {
@@ -1040,6 +1190,18 @@ static int soap_layout(int n_frames, int n_atoms, int n_cent, int n_species, int
         L->n_tasks = n_species * (tiles * (tiles + 1) / 2) +
                      n_species * (n_species - 1) / 2 * tiles * tiles;
         L->off_tasks = take(sizeof(SpecTask) * (size_t)L->n_tasks);
+    }
+#ifndef DSG_SOAP_LIST
+#define DSG_SOAP_LIST 1
+#endif
+    // rows sized for 1.5 x the mean neighbour count + 64 (a Poisson gas of 100 neighbours stays
+    // 6 sigma below that); a denser-than-expected region only costs the fallback launch
+    if (DSG_SOAP_LIST && !soap_split(n_species, n_max) && h_box && !any_narrow &&
+        n_atoms < (1 << kListEntryShift) && k_max < 600.0) {
+        L->row_cap = ((int)(1.5 * k_max) + 64 + 31) & ~31;
+        L->off_rows = take(4 * fa * (size_t)L->row_cap);
+        L->off_rowcnt = take(4 * fa);
+        L->off_listflag = take(4);
     }
     L->bytes = o;
     return DSG_OK;
@@ -1215,6 +1377,21 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     a.out = d_out;
     a.stride_i = stride_i;
     a.stride_f = stride_f;
+    a.rows = nullptr;
+    a.rowcnt = nullptr;
+    a.row_cap = L.row_cap;
+    a.list_flag = nullptr;
+    a.list_role = 0;
+    if (L.row_cap > 0) {
+        a.rows = (int*)(ws + L.off_rows);
+        a.rowcnt = (int*)(ws + L.off_rowcnt);
+        a.list_flag = (int*)(ws + L.off_listflag);
+        a.list_role = 1;
+        DSG_CUDA_CHECK(cudaMemsetAsync(a.list_flag, 0, 4, st));
+        dim3 lgrid((n_atoms + 127) / 128, n_frames);
+        soap_list_kernel<<<lgrid, 128, 0, st>>>(a);
+        DSG_LAUNCH_CHECK("soap_list_kernel");
+    }
 
     // template instantiation by l_max: compile-time l cap + slot widths of the packed items
     int lt, s0;
@@ -1245,6 +1422,12 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
 #define DSG_SOAP_EXTRA_SMEM 0
 #endif
     const size_t smem = per_warp * warps + shared_tables + DSG_SOAP_EXTRA_SMEM;  // (occupancy probe)
+    // list-mode consumer: smaller per-warp part, four warps share the block tables
+    const size_t per_warp_l =
+        8 * ((((size_t)soap_warp_fixed(true) + (size_t)a.plan.rbuf_doubles) + 1) & ~(size_t)1);
+    int warps_l = s0 <= kPackSlots ? kListWarps : 2;
+    while (warps_l > 1 && per_warp_l * warps_l + shared_tables > 227 * 1024) warps_l >>= 1;
+    const size_t smem_l = per_warp_l * warps_l + shared_tables + DSG_SOAP_EXTRA_SMEM;
     // spectrum kernel: mixed coefficients of one l per warp
     const size_t spec_bytes = 8 * (size_t)n_species * (2 * l_max + 1) * ((n_max + 1) & ~1);
     if (smem > 227 * 1024 || (split && spec_bytes + 8 * (size_t)a.bmat_smem_doubles > 227 * 1024))
@@ -1258,18 +1441,26 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     a.slots_per_warp = spw;
     const int warps_needed = (n_atoms + spw - 1) / spw;
     dim3 grid((warps_needed + warps - 1) / warps, n_frames);
+    dim3 grid_l((warps_needed + warps_l - 1) / warps_l, n_frames);
 #define DSG_SOAP_LAUNCH(LT, A, B, C, D)                                                          \
     do {                                                                                         \
         if (split) {                                                                             \
-            DSG_CUDA_CHECK(cudaFuncSetAttribute(soap_kernel<LT, A, B, C, D, true>,               \
+            DSG_CUDA_CHECK(cudaFuncSetAttribute(soap_kernel<LT, A, B, C, D, true, false>,        \
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                                 (int)smem));                                     \
-            soap_kernel<LT, A, B, C, D, true><<<grid, warps * 32, smem, st>>>(a);                \
+            soap_kernel<LT, A, B, C, D, true, false><<<grid, warps * 32, smem, st>>>(a);         \
         } else {                                                                                 \
-            DSG_CUDA_CHECK(cudaFuncSetAttribute(soap_kernel<LT, A, B, C, D, false>,              \
+            if (a.list_role == 1) {                                                              \
+                DSG_CUDA_CHECK(cudaFuncSetAttribute(soap_kernel<LT, A, B, C, D, false, true>,    \
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                    (int)smem_l));                               \
+                soap_kernel<LT, A, B, C, D, false, true><<<grid_l, warps_l * 32, smem_l, st>>>(a); \
+                a.list_role = 2;   /* the same centres by the in-kernel search iff a row overflowed */ \
+            }                                                                                    \
+            DSG_CUDA_CHECK(cudaFuncSetAttribute(soap_kernel<LT, A, B, C, D, false, false>,       \
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                                 (int)smem));                                     \
-            soap_kernel<LT, A, B, C, D, false><<<grid, warps * 32, smem, st>>>(a);               \
+            soap_kernel<LT, A, B, C, D, false, false><<<grid, warps * 32, smem, st>>>(a);        \
         }                                                                                        \
     } while (0)
     if (l_max <= 4) DSG_SOAP_LAUNCH(4, 9, 0, 0, 0);

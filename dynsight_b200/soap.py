@@ -86,9 +86,11 @@ def saponify_trajectory_device(
     centres_t = torch.as_tensor(centers_list, device=dev)
     n_all = len(universe.atoms)
     if batch_frames is None:
-        # workspace per atom-frame: sorted copies + (several species / n_max > 8) primitive sums
+        # workspace per atom-frame: sorted copies + (several species / n_max > 8) primitive sums,
+        # or (one species) the neighbour rows of the list kernel (about 1 KB at liquid densities)
         scratch = soap_basis.scratch_doubles(n_species, soapnmax, soaplmax) * 8.0
-        batch_frames = frames.pick_batch_frames(sel_ix.size, 80.0 + scratch, 1, maximum=1024)
+        batch_frames = frames.pick_batch_frames(sel_ix.size, 80.0 + max(scratch, 1000.0), 1,
+                                                maximum=1024)
     sel_all = frames.Selection(sel_ix, n_all)
     for fb in frames.iter_batches(universe, fr_idx, batch_frames):
         box = frames.soap_boxes(fb, bool(soap_respectpbc))

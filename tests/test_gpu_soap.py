@@ -106,6 +106,12 @@ def test_doctest_known_answers(xyz60):
         (220, 33.0, 6.0, 3, 12, 2, torch.float32),  # l_max = 12
         (180, 29.0, 5.0, 9, 4, 2, torch.float32),   # odd n_max > 8 with 2 species (split mode)
         (120, 12.0, 4.0, 5, 6, 3, torch.float64),   # narrow box, 3 species
+        # list mode (one species, >= 3 cells per axis) for every l_max instantiation
+        (300, 30.0, 5.0, 7, 4, 1, torch.float32),
+        (300, 30.0, 5.0, 8, 6, 1, torch.float32),
+        (300, 30.0, 5.0, 8, 7, 1, torch.float64),
+        (200, 30.0, 5.0, 6, 10, 1, torch.float32),
+        (200, 30.0, 5.0, 4, 12, 1, torch.float32),
     ],
 )
 def test_random_boxes_vs_oracle(n_atoms, box_l, r_cut, n_max, l_max, n_species, dtype):
@@ -123,6 +129,25 @@ def test_random_boxes_vs_oracle(n_atoms, box_l, r_cut, n_max, l_max, n_species, 
         pos, zs[sp_idx], centres, np.tile(box, (2, 1)), r_cut, n_max, l_max
     )
     assert got.shape == want.shape
+    assert _rel_err(got, want) < REL
+
+
+def test_list_rows_overflow_falls_back_to_the_in_kernel_search():
+    """Neighbour rows are sized from the mean density; a dense droplet in a dilute box overflows
+    them and the launch must fall back to the in-kernel search with identical results."""
+    rng = np.random.default_rng(21)
+    box = np.array([40.0, 41.0, 39.0])
+    pos = rng.random((2, 400, 3)) * box
+    pos[:, :170] = box / 2 + rng.normal(size=(2, 170, 3)) * 2.0   # 170 atoms within a few A
+    pos = pos.astype(np.float32)
+    centres = np.arange(0, 400, 9)
+    got = _soap_gpu(pos, np.zeros(400), centres, box, 5.0, 8, 8)
+    want = so.soap_trajectory(pos, np.zeros(400, int), centres, np.tile(box, (2, 1)), 5.0, 8, 8)
+    assert _rel_err(got, want) < REL
+    # and a frame batch in which only one frame overflows
+    pos[1] = (rng.random((400, 3)) * box).astype(np.float32)
+    got = _soap_gpu(pos, np.zeros(400), centres, box, 5.0, 8, 8)
+    want = so.soap_trajectory(pos, np.zeros(400, int), centres, np.tile(box, (2, 1)), 5.0, 8, 8)
     assert _rel_err(got, want) < REL
 
 
