@@ -397,16 +397,16 @@ def run_b200(args: argparse.Namespace) -> None:
     lens_gbs = lens_bytes_pf * pf_per_step / ((part_ms["neigh"] + part_ms["lens"]) * 1e-3) / 1e9
     ts_gbs = (8 * n_feat + 8) * pf_per_step / (part_ms["tsoap"] * 1e-3) / 1e9
     roofline = {
-        "kernel": "soap_kernel<8,17,9,0,0,false> (+ binning, <1%)",
+        "kernel": "soap_kernel<8,20,0,0,0,false,LIST=true> (+ soap_list_kernel 3.5 %, binning < 1 %)",
         "bound": "fp64",
         "achieved": soap_tflops,
         "peak": fp64_peak_tflops,
         "unit": "TFLOP/s",
         "frac": soap_tflops / fp64_peak_tflops if fp64_peak_tflops else None,
         # dram__bytes_read+write of this kernel from the ncu --set full capture summarised in
-        # profiles/r1_soap_kernel_final_summary.txt: 2283 B per centre-frame, scaled to this launch
-        "traffic": 2283.0 * soap_pf,
-        "traffic_source": "profiles/r1_soap_kernel_final_summary.txt (2283 B per centre-frame)",
+        # profiles/r1_soap_kernel_list_summary.txt: 2721 B per centre-frame, scaled to this launch
+        "traffic": 2721.0 * soap_pf,
+        "traffic_source": "profiles/r1_soap_kernel_list_summary.txt (2721 B per centre-frame)",
         "peak_source": "dsg_fp64_fma_probe measured in this run (not in MEASURED_PEAKS.json)",
         "algorithmic_flops_per_pf": fl,
         "exps_per_pf_not_counted_as_flops": ex,
