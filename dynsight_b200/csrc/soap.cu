@@ -560,6 +560,45 @@ __device__ __forceinline__ void mix_and_spectrum(const SoapArgs& a, const double
     }
     __syncwarp();
 
+#ifndef DSG_SOAP_TILE_SPECTRUM
+#define DSG_SOAP_TILE_SPECTRUM 1
+#endif
+    if (DSG_SOAP_TILE_SPECTRUM && n == 8) {
+        // 2x2 register tiles: one lane per (l, tile of the upper triangle of the 8x8 Gram matrix
+        // C_l^T C_l), two 128-bit shared loads per four FMAs, l descending so that the lanes of a
+        // round have similar trip counts.  The results are staged over G (dead after the mixing) and
+        // written out coalesced.
+        double* __restrict__ stage = const_cast<double*>(gsum);
+        const int n_tasks = (pl.l_max + 1) * 10;
+        for (int t = lane; t < n_tasks; t += 32) {
+            const int lq = t / 10, tile = t - lq * 10, l = pl.l_max - lq;
+            const int na0 = 2 * (int)((0x3221110000ULL >> (4 * tile)) & 15ULL);
+            const int nb0 = 2 * (int)((0x3323213210ULL >> (4 * tile)) & 15ULL);
+            const double2* __restrict__ ca =
+                reinterpret_cast<const double2*>(mix + (size_t)(l * l) * 8 + na0);
+            const double2* __restrict__ cb =
+                reinterpret_cast<const double2*>(mix + (size_t)(l * l) * 8 + nb0);
+            double o00 = 0.0, o01 = 0.0, o10 = 0.0, o11 = 0.0;
+            for (int mi = 0; mi < 2 * l + 1; ++mi) {
+                const double2 u = ca[mi * 4], v = cb[mi * 4];
+                o00 = fma(u.x, v.x, o00);
+                o01 = fma(u.x, v.y, o01);
+                o10 = fma(u.y, v.x, o10);
+                o11 = fma(u.y, v.y, o11);
+            }
+            double* __restrict__ ob = stage + l * 36;
+            const int r0 = na0 * 8 - (na0 * (na0 - 1)) / 2 - na0;        // row na0: index = r0 + nb
+            const int r1 = (na0 + 1) * 8 - ((na0 + 1) * na0) / 2 - (na0 + 1);
+            ob[r0 + nb0 + 1] = o01;
+            ob[r1 + nb0 + 1] = o11;
+            if (nb0 >= na0) ob[r0 + nb0] = o00;       // always (tiles of the upper triangle)
+            if (nb0 > na0) ob[r1 + nb0] = o10;        // below the diagonal inside a diagonal tile
+        }
+        __syncwarp();
+        for (int c = lane; c < pl.n_feat; c += 32) out[c] = stage[c];
+        __syncwarp();
+        return;
+    }
     for (int c = lane; c < pl.n_feat; c += 32) {
         const int code = decode[c];   // single species: l | na << 4 | nb << 9
         const int l = code & 15, na = (code >> 4) & 31, nb = (code >> 9) & 31;
