@@ -272,12 +272,17 @@ soap_list_kernel(const SoapArgs a) {
     }
     const int nc0 = fr->nc[0], nc1 = fr->nc[1], nc2 = fr->nc[2];
     const double b0 = fr->box[0], b1 = fr->box[1], b2 = fr->box[2];
-    const int cell_base = fr->cell_base;
     const int frame_first = f * a.n_atoms;
     int* __restrict__ row = a.rows + slot * (size_t)a.row_cap;
+    int* __restrict__ off = a.rowcnt + slot * (size_t)(a.plan.n_species + 1);
     const int cap = a.row_cap;
     const double r2max = a.r2max;
     int cnt = 0;
+    off[0] = 0;
+    // species after species (each has its own cell grid): the row is species-major and off[z + 1]
+    // is the end of species z, so a (species, radial block) pass of the main kernel reads one run
+    for (int z_sp = 0; z_sp < a.plan.n_species; ++z_sp) {
+    const int cell_base = fr->cell_base + z_sp * fr->spec_stride;
     for (int i0 = 0; i0 < 3; ++i0) {
         int c0 = cc[0] + i0 - 1;
         double s0 = -xc;
@@ -304,7 +309,8 @@ soap_list_kernel(const SoapArgs a) {
             }
         }
     }
-    a.rowcnt[slot] = cnt;
+    off[z_sp + 1] = cnt;
+    }
     if (cnt > cap) *a.list_flag = 1;
 }
 
@@ -803,8 +809,10 @@ soap_kernel(const SoapArgs a) {
             __syncwarp();
             cached_cell = my_cell;
         }
-        const int n_nb = a.rowcnt[slot];
-        const int* __restrict__ row = a.rows + slot * (size_t)a.row_cap;
+        const int* __restrict__ off = a.rowcnt + slot * (size_t)(pl.n_species + 1) + z_sp;
+        const int row_first = off[0];
+        const int n_nb = off[1] - row_first;
+        const int* __restrict__ row = a.rows + slot * (size_t)a.row_cap + row_first;
         const size_t frame_first = (size_t)f * a.n_atoms;
         // coordinates one batch ahead, list codes two batches ahead (two dependent round trips)
         double px = 0.0, py = 0.0, pz = 0.0;
@@ -1235,11 +1243,11 @@ static int soap_layout(int n_frames, int n_atoms, int n_cent, int n_species, int
 #endif
     // rows sized for 1.5 x the mean neighbour count + 64 (a Poisson gas of 100 neighbours stays
     // 6 sigma below that); a denser-than-expected region only costs the fallback launch
-    if (DSG_SOAP_LIST && !soap_split(n_species, n_max) && h_box && !any_narrow &&
-        n_atoms < (1 << kListEntryShift) && k_max < 600.0) {
+    if (DSG_SOAP_LIST && h_box && !any_narrow && n_atoms < (1 << kListEntryShift) &&
+        k_max < 600.0) {
         L->row_cap = ((int)(1.5 * k_max) + 64 + 31) & ~31;
         L->off_rows = take(4 * fa * (size_t)L->row_cap);
-        L->off_rowcnt = take(4 * fa);
+        L->off_rowcnt = take(4 * fa * (size_t)(n_species + 1));
         L->off_listflag = take(4);
     }
     L->bytes = o;
@@ -1426,10 +1434,6 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
         a.rowcnt = (int*)(ws + L.off_rowcnt);
         a.list_flag = (int*)(ws + L.off_listflag);
         a.list_role = 1;
-        DSG_CUDA_CHECK(cudaMemsetAsync(a.list_flag, 0, 4, st));
-        dim3 lgrid((n_atoms + 127) / 128, n_frames);
-        soap_list_kernel<<<lgrid, 128, 0, st>>>(a);
-        DSG_LAUNCH_CHECK("soap_list_kernel");
     }
 
     // template instantiation by l_max: compile-time l cap + slot widths of the packed items
@@ -1444,6 +1448,12 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     else if (l_max <= 10) { lt = 10; s0 = 21; }
     else { lt = 12; s0 = 25; }
     make_plan(n_species, n_max, l_max, lt, s0, &a.plan);
+    if (a.list_role == 1) {   // neighbour rows for the list-mode kernels (needs the plan)
+        DSG_CUDA_CHECK(cudaMemsetAsync(a.list_flag, 0, 4, st));
+        dim3 lgrid((n_atoms + 127) / 128, n_frames);
+        soap_list_kernel<<<lgrid, 128, 0, st>>>(a);
+        DSG_LAUNCH_CHECK("soap_list_kernel");
+    }
     const bool split = soap_split(n_species, n_max);
     a.gscr = split ? (double*)(ws + L.off_gscr) : nullptr;
     const size_t per_warp =
@@ -1484,6 +1494,13 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
 #define DSG_SOAP_LAUNCH(LT, A, B, C, D)                                                          \
     do {                                                                                         \
         if (split) {                                                                             \
+            if (a.list_role == 1) {                                                              \
+                DSG_CUDA_CHECK(cudaFuncSetAttribute(soap_kernel<LT, A, B, C, D, true, true>,     \
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                    (int)smem_l));                               \
+                soap_kernel<LT, A, B, C, D, true, true><<<grid_l, warps_l * 32, smem_l, st>>>(a); \
+                a.list_role = 2;                                                                 \
+            }                                                                                    \
             DSG_CUDA_CHECK(cudaFuncSetAttribute(soap_kernel<LT, A, B, C, D, true, false>,        \
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                                 (int)smem));                                     \

@@ -149,6 +149,13 @@ def test_list_rows_overflow_falls_back_to_the_in_kernel_search():
     got = _soap_gpu(pos, np.zeros(400), centres, box, 5.0, 8, 8)
     want = so.soap_trajectory(pos, np.zeros(400, int), centres, np.tile(box, (2, 1)), 5.0, 8, 8)
     assert _rel_err(got, want) < REL
+    # species-major rows (split mode): two species, the droplet still overflows
+    sp_idx = rng.integers(0, 2, 400)
+    got = _soap_gpu(pos, sp_idx, centres, box, 5.0, 6, 5)
+    want = so.soap_trajectory(
+        pos, np.array([1, 8])[sp_idx], centres, np.tile(box, (2, 1)), 5.0, 6, 5
+    )
+    assert _rel_err(got, want) < REL
 
 
 def test_non_periodic_two_species_vs_oracle():
