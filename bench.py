@@ -667,6 +667,31 @@ def widened_section(engine, dev, hbm_peak: float, fp64_peak_tflops: float) -> di
                      "unit": "TFLOP/s",
                      "frac": tfl / fp64_peak_tflops if fp64_peak_tflops else None},
     }  # fmt: skip
+    del data
+    # SOAP at the cfg4 parameters (BASELINE.json configs[3]): 3 species, l_max = 10, metal density;
+    # a bounded sample of the 250k-atom box (the kernels are per-centre, throughput is size-stable)
+    n, nf, n_sp, l_max4 = 50_000, 4, 3, 10
+    box_l = (n / 0.0857) ** (1.0 / 3.0)
+    pos = (torch.rand((nf, n, 3), device=dev, generator=gen, dtype=torch.float64) * box_l).float()
+    pos.clamp_(max=float(np.nextafter(np.float32(box_l), np.float32(0))))
+    sp3 = (torch.arange(n, device=dev, dtype=torch.int32) * 7919 % n_sp).to(torch.int32)
+    cen = torch.arange(n, dtype=torch.int32, device=dev)
+    box3 = np.full(3, np.float32(box_l), dtype=np.float32)
+    ms = timed(lambda: engine.soap_power_spectrum(pos, sp3, cen, box3, R_CUT_SOAP, N_MAX, l_max4,
+                                                  n_species=n_sp), reps=3)  # fmt: skip
+    r_s = R_CUT_SOAP + math.sqrt(-2.0 * math.log(1e-3))
+    k4 = 0.0857 * 4.0 / 3.0 * math.pi * r_s**3 + 1.0
+    lm4, sn4 = (l_max4 + 1) ** 2, n_sp * N_MAX
+    flops = 2.0 * (k4 * N_MAX * lm4 + lm4 * sn4 * (sn4 + 1) / 2) * n * nf
+    tfl = flops / (ms * 1e-3) / 1e12
+    out["soap_cfg4_parameters"] = {
+        "workload": f"{n} atoms x {nf} frames, 3 species, rho=0.0857/A^3, r_cut={R_CUT_SOAP}, "
+                    f"n_max={N_MAX}, l_max={l_max4} (3300 features, K={k4:.0f})",
+        "value": n * nf / (ms * 1e-3), "unit": UNIT, "ms": ms,
+        "roofline": {"bound": "fp64", "achieved": tfl, "peak": fp64_peak_tflops,
+                     "unit": "TFLOP/s",
+                     "frac": tfl / fp64_peak_tflops if fp64_peak_tflops else None},
+    }  # fmt: skip
     return out
 
 

@@ -332,11 +332,25 @@ struct Acc {
 // for which gamma * r^2 could exceed 690.
 constexpr int kExpTab = 16;
 constexpr double kExpScale = 23.083120654223414;  // 16 * log2(e)
-__device__ __forceinline__ double exp_scaled(double t, const double* __restrict__ tab) {
+#ifndef DSG_SOAP_EXP_HORNER
+#define DSG_SOAP_EXP_HORNER 0
+#endif
+// g = gamma * kExpScale (negative), s = r^2.  The product enters only through two FMAs: rint(g s)
+// by the magic-constant trick and the remainder v = g s - rint(g s) with a single rounding, so
+// the argument is never rounded to float64 (one operation fewer and v exact to 1e-17).
+__device__ __forceinline__ double exp_scaled(double g, double s, const double* __restrict__ tab) {
     const double magic = 6755399441055744.0;                     // 1.5 * 2^52
-    const double tn = t + magic;
+    const double tn = fma(g, s, magic);
     const int kq = __double2loint(tn);                           // 16 n + j
-    const double v = t - (tn - magic);                           // [-1/2, 1/2]
+    const double v = fma(g, s, magic - tn);                      // [-1/2, 1/2]
+#if DSG_SOAP_EXP_HORNER
+    double p = fma(9.18121957384443806176e-12, v, 1.27158719505581314889e-09);
+    p = fma(p, v, 1.46761003229194288311e-07);
+    p = fma(p, v, 1.35508077794974568162e-05);
+    p = fma(p, v, 9.38384792808987194639e-04);
+    p = fma(p, v, 4.33216987849965803892e-02);
+    p = fma(p, v, 1.0);
+#else
     // Estrin scheme: two more operations than Horner, dependency depth 4 instead of 6
     const double v2 = v * v;
     const double t0 = fma(4.33216987849965803892e-02, v, 1.0);
@@ -346,6 +360,7 @@ __device__ __forceinline__ double exp_scaled(double t, const double* __restrict_
     const double v4 = v2 * v2;
     double p = fma(t1, v2, t0);
     p = fma(t2, v4, p);
+#endif
     const double r = tab[kq & (kExpTab - 1)] * p;
     return __hiloint2double(__double2hiint(r) + ((kq >> 4) << 20), __double2loint(r));
 }
@@ -774,20 +789,20 @@ soap_kernel(const SoapArgs a) {
                     r2_next = nbuf[(h0 + min(jj + 1, nh - 1)) * 4 + 3];
                     const double* __restrict__ rt = rbuf + jj * P;
                     if constexpr (PK) {
-                        const double e0 = exp_scaled(gam[0] * r2, exp_tab);
-                        const double e1 = exp_scaled(gam[1] * r2, exp_tab);
+                        const double e0 = exp_scaled(gam[0], r2, exp_tab);
+                        const double e1 = exp_scaled(gam[1], r2, exp_tab);
                         accumulate_packed(a0, e0, e1, g, rt + g * kPackSlots);
                     } else {
-                        if (S0 > 0) accumulate<S0>(a0, exp_scaled(gam[0] * r2, exp_tab), rt + ioff[0]);
-                        if (S1 > 0) accumulate<S1>(a1, exp_scaled(gam[1] * r2, exp_tab), rt + ioff[1]);
-                        if (S2 > 0) accumulate<S2>(a2, exp_scaled(gam[2] * r2, exp_tab), rt + ioff[2]);
-                        if (S3 > 0) accumulate<S3>(a3, exp_scaled(gam[3] * r2, exp_tab), rt + ioff[3]);
+                        if (S0 > 0) accumulate<S0>(a0, exp_scaled(gam[0], r2, exp_tab), rt + ioff[0]);
+                        if (S1 > 0) accumulate<S1>(a1, exp_scaled(gam[1], r2, exp_tab), rt + ioff[1]);
+                        if (S2 > 0) accumulate<S2>(a2, exp_scaled(gam[2], r2, exp_tab), rt + ioff[2]);
+                        if (S3 > 0) accumulate<S3>(a3, exp_scaled(gam[3], r2, exp_tab), rt + ioff[3]);
                     }
                 }
 #pragma unroll
                 for (int q = 0; q < kChunk / 4; ++q) {   // l = 0, a quarter of the chunk per lane
                     const int jj = (lane >> 3) + 4 * q;
-                    if (jj < nh) acc00 += exp_scaled(gam0 * nbuf[(h0 + jj) * 4 + 3], exp_tab);
+                    if (jj < nh) acc00 += exp_scaled(gam0, nbuf[(h0 + jj) * 4 + 3], exp_tab);
                 }
                 __syncwarp();
             }
