@@ -842,8 +842,14 @@ cell_scatter_local_kernel(const T* __restrict__ pos, int n_atoms,
 constexpr int kTpcThreads = 128;
 
 // kTpcHitCap = rows that fit the staging tile (32 or 64 hits per centre)
+// 6 blocks of 128 threads per SM (80 registers, a few spilled words outside the candidate loop):
+// the kernel waits on candidate loads, 24 instead of 20 resident warps is +3.7 % at cfg3; 8 blocks
+// (64 registers) spill inside the loop and give the gain back
+#ifndef DSG_TPC_MIN_BLOCKS
+#define DSG_TPC_MIN_BLOCKS 6
+#endif
 template <typename T, int kTpcHitCap>
-__global__ void __launch_bounds__(kTpcThreads)
+__global__ void __launch_bounds__(kTpcThreads, DSG_TPC_MIN_BLOCKS)
 neigh_rows_thread_kernel(const RowsArgs a, const unsigned* __restrict__ cent_slot_cell) {
     __shared__ int stage[kTpcHitCap][kTpcThreads];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
