@@ -404,9 +404,9 @@ def run_b200(args: argparse.Namespace) -> None:
         "unit": "TFLOP/s",
         "frac": soap_tflops / fp64_peak_tflops if fp64_peak_tflops else None,
         # dram__bytes_read+write of this kernel from the ncu --set full capture summarised in
-        # profiles/r1_soap_kernel_list_summary.txt: 2721 B per centre-frame, scaled to this launch
-        "traffic": 2721.0 * soap_pf,
-        "traffic_source": "profiles/r1_soap_kernel_list_summary.txt (2721 B per centre-frame)",
+        # profiles/r1_soap_kernel_list_summary.txt: 2724 B per centre-frame, scaled to this launch
+        "traffic": 2724.0 * soap_pf,
+        "traffic_source": "profiles/r1_soap_kernel_list_summary.txt (2724 B per centre-frame)",
         "peak_source": "dsg_fp64_fma_probe measured in this run (not in MEASURED_PEAKS.json)",
         "algorithmic_flops_per_pf": fl,
         "exps_per_pf_not_counted_as_flops": ex,
