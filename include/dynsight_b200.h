@@ -211,6 +211,12 @@ int dsg_normalize_soap(const double* d_in, double* d_out, int64_t n_vectors, int
  * out[i*stride_i + f*stride_f + c], c in [0, n_feat) with
  * n_feat = (S*n_max)*(S*n_max+1)/2*(l_max+1); order: species pairs Z<=Z', then l, n, n'
  * (n'>=n when Z==Z').  float64 output, float64 arithmetic.
+ * Workspace (dsg_soap_workspace_bytes, same shapes and h_box as the call): the cell-sorted copies,
+ * the primitive sums between the two kernels when n_species > 1 or n_max > 8, and -- for periodic
+ * frames with at least three search-radius cells per axis -- per-centre neighbour rows of
+ * 4 * (1.5 * mean neighbours + 64) bytes, the mean taken from n_atoms / box volume.  Rows that
+ * overflow (strongly clustered input) are handled on the device by the in-kernel search; no status
+ * has to be read back.
  * ------------------------------------------------------------------------------------------ */
 int dsg_soap_n_features(int n_species, int n_max, int l_max);
 
