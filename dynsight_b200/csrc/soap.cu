@@ -48,6 +48,28 @@ constexpr int kOpenCellsPerAxis = 32;
 #ifndef DSG_SOAP_MIN_BLOCKS_L10
 #define DSG_SOAP_MIN_BLOCKS_L10 4
 #endif
+// Build-time switches of the measured variants (defaults = what ships)
+#ifndef DSG_SOAP_PACK
+#define DSG_SOAP_PACK 1            // l_max = 8: packed rows, 20 accumulator slots per lane
+#endif
+#ifndef DSG_SOAP_LIST
+#define DSG_SOAP_LIST 1            // neighbour rows from soap_list_kernel where the frames allow it
+#endif
+#ifndef DSG_SOAP_LIST_WARPS
+#define DSG_SOAP_LIST_WARPS 2      // warps per block of the list-mode kernel ...
+#endif
+#ifndef DSG_SOAP_LIST_BLOCKS
+#define DSG_SOAP_LIST_BLOCKS 6     // ... and its resident blocks per SM
+#endif
+#ifndef DSG_SOAP_TILE_SPECTRUM
+#define DSG_SOAP_TILE_SPECTRUM 1   // fused epilogue: 2x2 register tiles for n_max = 8
+#endif
+#ifndef DSG_SOAP_EXP_HORNER
+#define DSG_SOAP_EXP_HORNER 0      // Horner instead of Estrin in exp_scaled
+#endif
+#ifndef DSG_SOAP_EXTRA_SMEM
+#define DSG_SOAP_EXTRA_SMEM 0      // occupancy probe: dummy dynamic shared memory per block
+#endif
 constexpr int kListCap = 32;     // displacement list entries per warp
 constexpr int kCellTab = 32;     // (cell range, shift) entries resolved per pass
 constexpr int kBatchCap = 64;    // 32-candidate batches listed per pass
@@ -332,9 +354,6 @@ struct Acc {
 // for which gamma * r^2 could exceed 690.
 constexpr int kExpTab = 16;
 constexpr double kExpScale = 23.083120654223414;  // 16 * log2(e)
-#ifndef DSG_SOAP_EXP_HORNER
-#define DSG_SOAP_EXP_HORNER 0
-#endif
 // g = gamma * kExpScale (negative), s = r^2.  The product enters only through two FMAs: rint(g s)
 // by the magic-constant trick and the remainder v = g s - rint(g s) with a single rounding, so
 // the argument is never rounded to float64 (one operation fewer and v exact to 1e-17).
@@ -581,9 +600,6 @@ __device__ __forceinline__ void mix_and_spectrum(const SoapArgs& a, const double
     }
     __syncwarp();
 
-#ifndef DSG_SOAP_TILE_SPECTRUM
-#define DSG_SOAP_TILE_SPECTRUM 1
-#endif
     if (DSG_SOAP_TILE_SPECTRUM && n == 8) {
         // 2x2 register tiles: one lane per (l, tile of the upper triangle of the 8x8 Gram matrix
         // C_l^T C_l), two 128-bit shared loads per four FMAs, l descending so that the lanes of a
@@ -642,12 +658,6 @@ __device__ __forceinline__ void mix_and_spectrum(const SoapArgs& a, const double
 // (species, radial block) pass and writes that slice of G to a global scratch;
 // soap_spectrum_kernel finishes the centres.  No per-warp coefficient buffer is needed, so the
 // occupancy is the single-species one whatever the number of species.
-#ifndef DSG_SOAP_LIST_WARPS
-#define DSG_SOAP_LIST_WARPS 2
-#endif
-#ifndef DSG_SOAP_LIST_BLOCKS
-#define DSG_SOAP_LIST_BLOCKS 6
-#endif
 // List mode needs neither the prefetch registers nor the batch tables of the in-kernel search, so
 // it also fits 4 blocks of 4 warps per SM at 128 registers (DSG_SOAP_LIST_WARPS=4,
 // DSG_SOAP_LIST_BLOCKS=4).  Measured on the 100 000-atom box: 4.30e7 centre-frames/s for 4 x 4
@@ -1253,9 +1263,6 @@ static int soap_layout(int n_frames, int n_atoms, int n_cent, int n_species, int
                      n_species * (n_species - 1) / 2 * tiles * tiles;
         L->off_tasks = take(sizeof(SpecTask) * (size_t)L->n_tasks);
     }
-#ifndef DSG_SOAP_LIST
-#define DSG_SOAP_LIST 1
-#endif
     // rows sized for 1.5 x the mean neighbour count + 64 (a Poisson gas of 100 neighbours stays
     // 6 sigma below that); a denser-than-expected region only costs the fallback launch
     if (DSG_SOAP_LIST && h_box && !any_narrow && n_atoms < (1 << kListEntryShift) &&
@@ -1455,9 +1462,6 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     int lt, s0;
     if (l_max <= 4) { lt = 4; s0 = 9; }
     else if (l_max <= 6) { lt = 6; s0 = 13; }
-#ifndef DSG_SOAP_PACK
-#define DSG_SOAP_PACK 1
-#endif
     else if (l_max < 8 || (l_max == 8 && !DSG_SOAP_PACK)) { lt = 8; s0 = 17; }
     else if (l_max == 8) { lt = 8; s0 = kPackSlots; }  // packed rows: 20 slots per lane
     else if (l_max <= 10) { lt = 10; s0 = 21; }
@@ -1482,9 +1486,6 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
              (split ? 0 : (size_t)a.bmat_smem_doubles + (size_t)a.epi_smem_doubles));
     int warps = 2;
     if (per_warp * warps + shared_tables > 227 * 1024) warps = 1;
-#ifndef DSG_SOAP_EXTRA_SMEM
-#define DSG_SOAP_EXTRA_SMEM 0
-#endif
     const size_t smem = per_warp * warps + shared_tables + DSG_SOAP_EXTRA_SMEM;  // (occupancy probe)
     // list-mode consumer: smaller per-warp part, four warps share the block tables
     const size_t per_warp_l =
