@@ -225,6 +225,47 @@ def test_c_abi_exports_every_declared_symbol():
     assert b"r_cut" in loaded.dsg_last_error()
 
 
+def test_soap_workspace_plans_neighbour_rows_only_where_list_mode_applies():
+    """dsg_soap_workspace_bytes is host code: periodic frames with >= 3 search-radius cells per
+    axis get per-centre neighbour rows (4 B x (1.5 x mean neighbours + 64), rounded to 32 entries),
+    narrow boxes and non-periodic frames do not."""
+    from dynsight_b200 import _lib
+
+    lib = _lib.load()
+
+    def ws(n_frames, n_atoms, box, n_species=1, n_max=8, l_max=8, r_cut=5.0):
+        n = ctypes.c_size_t(0)
+        ptr = None
+        if box is not None:
+            arr = np.ascontiguousarray(np.tile(np.asarray(box, dtype=np.float64), (n_frames, 1)))
+            ptr = arr.ctypes.data
+        rc = lib.dsg_soap_workspace_bytes(n_frames, n_atoms, n_atoms, n_species, n_max, l_max,
+                                          ptr, r_cut, ctypes.byref(n))  # fmt: skip
+        assert rc == 0, lib.dsg_last_error()
+        return n.value
+
+    n_atoms, n_frames = 600, 4      # about 93 neighbours inside the search radius
+    radius = 5.0 + np.sqrt(-2.0 * np.log(1e-3))
+    wide = 3.0 * radius * 1.001       # three cells per axis
+    narrow = 3.0 * radius * 0.999     # one cell + explicit images on every axis
+    k_mean = n_atoms * 4.0 / 3.0 * np.pi * radius**3 / wide**3
+    cap = (int(1.5 * k_mean) + 64 + 31) & ~31
+    rows = 4 * n_frames * n_atoms * cap
+    extra = ws(n_frames, n_atoms, [wide] * 3) - ws(n_frames, n_atoms, [narrow] * 3)
+    # the two layouts differ by the rows, the per-row counters and the cell arrays (27 vs 1 cell)
+    assert rows <= extra < rows + 4 * n_frames * n_atoms * 2 + 64 * 1024
+    # one narrow axis is enough to switch the rows off
+    mixed = ws(n_frames, n_atoms, [wide, wide, narrow])
+    assert mixed < ws(n_frames, n_atoms, [wide] * 3) - rows // 2
+    # too dense for rows (mean above 600 neighbours): the in-kernel search is kept
+    dense = ws(n_frames, 20 * n_atoms, [wide] * 3) - ws(n_frames, 20 * n_atoms, [narrow] * 3)
+    assert dense < 64 * 1024
+    # several species: species-major rows, one offset per species and centre more
+    extra3 = ws(n_frames, n_atoms, [wide] * 3, n_species=3) - ws(n_frames, n_atoms, [narrow] * 3,
+                                                                  n_species=3)  # fmt: skip
+    assert rows <= extra3 < rows + 4 * n_frames * n_atoms * 4 + 256 * 1024
+
+
 def test_product_never_touches_the_oracle():
     """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may use oracle/."""
     for path in (ROOT / "dynsight_b200").rglob("*"):
