@@ -529,10 +529,12 @@ __device__ __forceinline__ void store_packed(const Acc<kPackSlots>& a, int g, in
 template <int S>
 __device__ __forceinline__ void store_item(const Acc<S>& a, int l, int k, int n,
                                            double* __restrict__ cz) {
-    if (S <= 0 || l < 0) return;
+    if constexpr (S > 0) {
+        if (l < 0) return;
 #pragma unroll
-    for (int s = 0; s < S; ++s)
-        if (s < 2 * l + 1) cz[(l * l + s) * n + k] = a.v[s];
+        for (int s = 0; s < S; ++s)
+            if (s < 2 * l + 1) cz[(l * l + s) * n + k] = a.v[s];
+    }
 }
 
 // Loewdin mixing + power spectrum of one centre.  G [S][n_lm][n] may sit in shared or global
