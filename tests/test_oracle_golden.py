@@ -203,3 +203,27 @@ def test_psi_phi_doctest_known_answers(xyz60, ref_lens):
     phi = do.velocity_alignment(pos, csr)
     assert np.isclose(psi[0][0], float(ref_lens["kat_psi00"]))
     assert np.isclose(phi[0][0], float(ref_lens["kat_phi00"]))
+
+
+def test_tcf_oracle_vs_reference_goldens():
+    """Pins oracle/tcf_oracle.py (self and cross time correlation) to the reference's own goldens
+    tests/analysis/tcorr/{t_corr,std_dev,c_corr,ctd_dev}.npy (tests/analysis/
+    test_time_correlations.py:20-73) and to the doctest values of time_correlations.py:57,141."""
+    from conftest import GOLDEN
+
+    from oracle import tcf_oracle
+
+    fx = np.load(GOLDEN / "tcorr.npz")
+    walk = tcf_oracle.reference_walk()
+    corr, err = tcf_oracle.self_time_correlation(walk)
+    assert np.allclose(corr, fx["t_corr"], rtol=1e-11, atol=1e-13)
+    assert np.allclose(err, fx["std_dev"], rtol=1e-11, atol=1e-13)
+    ccorr, cerr = tcf_oracle.cross_time_correlation(walk)
+    assert np.allclose(ccorr, fx["c_corr"], rtol=1e-11, atol=1e-13)
+    assert np.allclose(cerr, fx["ctd_dev"], rtol=1e-11, atol=1e-13)
+    np.random.seed(1234)  # noqa: NPY002
+    data = np.random.rand(100, 100)  # noqa: NPY002
+    assert np.isclose(tcf_oracle.self_time_correlation(data)[0][1], float(fx["kat_rand_lag1"]),
+                      rtol=1e-12)  # fmt: skip
+    assert np.isclose(tcf_oracle.cross_time_correlation(data)[0][0], float(fx["kat_cross_lag0"]),
+                      rtol=1e-10)  # fmt: skip
