@@ -227,3 +227,20 @@ def test_tcf_oracle_vs_reference_goldens():
                       rtol=1e-12)  # fmt: skip
     assert np.isclose(tcf_oracle.cross_time_correlation(data)[0][0], float(fx["kat_cross_lag0"]),
                       rtol=1e-10)  # fmt: skip
+
+
+def test_spatial_average_oracle_vs_reference_golden():
+    """Pins oracle/spatial_oracle.py to the reference's tests/analysis/spavg/test_spavg.npy
+    (tests/analysis/test_spatialaverage.py:53-64: x coordinate of the O atoms of the coex system,
+    r_cut = 5 A), stored in tests/golden/coex.npz by tests/golden/make_golden.py."""
+    from conftest import GOLDEN
+
+    from oracle import spatial_oracle
+
+    coex = np.load(GOLDEN / "coex.npz")
+
+    pos = coex["o_positions"]
+    values = pos[:, :, 0].T.astype(np.float64)
+    got = spatial_oracle.spatial_average(pos, coex["dims"], values, 5.0)
+    assert got.shape == coex["spavg"].shape
+    assert np.abs(got - coex["spavg"]).max() <= 1e-12 * np.abs(coex["spavg"]).max()
