@@ -1267,9 +1267,15 @@ static int soap_layout(int n_frames, int n_atoms, int n_cent, int n_species, int
     }
     // rows sized for 1.5 x the mean neighbour count + 64 (a Poisson gas of 100 neighbours stays
     // 6 sigma below that); a denser-than-expected region only costs the fallback launch
+    // The rows are indexed by sorted slot, i.e. allocated for every atom: with few centres in a large
+    // system (fewer than a quarter of the atoms and more than 256 MiB of rows) they would be mostly
+    // unused memory, and the in-kernel search only visits the centres anyway.
+    const int cap = ((int)(1.5 * k_max) + 64 + 31) & ~31;
+    const bool sparse_centres = (long long)n_cent * 4 < (long long)n_atoms &&
+                                4 * fa * (size_t)cap > ((size_t)256 << 20);
     if (DSG_SOAP_LIST && h_box && !any_narrow && n_atoms < (1 << kListEntryShift) &&
-        k_max < 600.0) {
-        L->row_cap = ((int)(1.5 * k_max) + 64 + 31) & ~31;
+        k_max < 600.0 && !sparse_centres) {
+        L->row_cap = cap;
         L->off_rows = take(4 * fa * (size_t)L->row_cap);
         L->off_rowcnt = take(4 * fa * (size_t)(n_species + 1));
         L->off_listflag = take(4);

@@ -233,14 +233,14 @@ def test_soap_workspace_plans_neighbour_rows_only_where_list_mode_applies():
 
     lib = _lib.load()
 
-    def ws(n_frames, n_atoms, box, n_species=1, n_max=8, l_max=8, r_cut=5.0):
+    def ws(n_frames, n_atoms, box, n_species=1, n_max=8, l_max=8, r_cut=5.0, n_cent=None):
         n = ctypes.c_size_t(0)
         ptr = None
         if box is not None:
             arr = np.ascontiguousarray(np.tile(np.asarray(box, dtype=np.float64), (n_frames, 1)))
             ptr = arr.ctypes.data
-        rc = lib.dsg_soap_workspace_bytes(n_frames, n_atoms, n_atoms, n_species, n_max, l_max,
-                                          ptr, r_cut, ctypes.byref(n))  # fmt: skip
+        rc = lib.dsg_soap_workspace_bytes(n_frames, n_atoms, n_cent or n_atoms, n_species, n_max,
+                                          l_max, ptr, r_cut, ctypes.byref(n))  # fmt: skip
         assert rc == 0, lib.dsg_last_error()
         return n.value
 
@@ -260,6 +260,9 @@ def test_soap_workspace_plans_neighbour_rows_only_where_list_mode_applies():
     # too dense for rows (mean above 600 neighbours): the in-kernel search is kept
     dense = ws(n_frames, 20 * n_atoms, [wide] * 3) - ws(n_frames, 20 * n_atoms, [narrow] * 3)
     assert dense < 64 * 1024
+    # a handful of centres in a large system: rows for every atom would be wasted memory
+    big_atoms, big_box = 1_000_000, [(1_000_000 / 0.0334) ** (1 / 3)] * 3
+    assert ws(8, big_atoms, big_box, n_cent=10) < ws(8, big_atoms, big_box) // 4
     # several species: species-major rows, one offset per species and centre more
     extra3 = ws(n_frames, n_atoms, [wide] * 3, n_species=3) - ws(n_frames, n_atoms, [narrow] * 3,
                                                                   n_species=3)  # fmt: skip
