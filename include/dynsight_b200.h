@@ -214,7 +214,8 @@ int dsg_normalize_soap(const double* d_in, double* d_out, int64_t n_vectors, int
  * Workspace (dsg_soap_workspace_bytes, same shapes and h_box as the call): the cell-sorted copies,
  * the primitive sums between the two kernels when n_species > 1 or n_max > 8, and -- for periodic
  * frames with at least three search-radius cells per axis -- per-centre neighbour rows of
- * 4 * (1.5 * mean neighbours + 64) bytes, the mean taken from n_atoms / box volume.  Rows that
+ * 4 * (1.5 * mean neighbours + 64) bytes per atom, the mean taken from n_atoms / box volume (left
+ * out when fewer than a quarter of the atoms are centres and the rows would exceed 256 MiB).  Rows that
  * overflow (strongly clustered input) are handled on the device by the in-kernel search; no status
  * has to be read back.
  * ------------------------------------------------------------------------------------------ */
