@@ -53,6 +53,15 @@ SIGNATURES: dict[str, tuple] = {
     "dsg_lens_pairs_rows": (
         _c_int, [_c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_ptr, _c_i64, _c_i64, _c_ptr],
     ),
+    "dsg_lens_direct_supported": (_c_int, [_c_int, _c_int, _c_ptr, _c_dbl, _c_int]),
+    "dsg_lens_direct_workspace_bytes": (
+        _c_int, [_c_int, _c_int, _c_ptr, _c_dbl, ctypes.POINTER(_c_size)],
+    ),
+    "dsg_lens_direct": (
+        _c_int,
+        [_c_ptr, _c_int, _c_int, _c_int, _c_ptr, _c_dbl, _c_int, _c_int, _c_ptr, _c_size, _c_ptr,
+         _c_ptr, _c_i64, _c_i64, _c_ptr],
+    ),
     "dsg_lens_pairs": (
         _c_int, [_c_ptr, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_ptr, _c_i64, _c_i64, _c_ptr],
     ),

@@ -58,6 +58,14 @@ __host__ __device__ inline int cell_of(double x, double box, int ncell) {
     return (int)r;
 }
 
+// LENS of one centre from the two row lengths and the size of their intersection (lens.py:167-188)
+__host__ __device__ inline double lens_value(int a, int b, int inter) {
+    const int denom = a + b;                 // lens.py:170
+    if (denom <= 0) return 0.0;              // lens.py:171-173
+    const int numer = denom - 2 * inter;     // lens.py:187
+    return (double)numer / (double)denom;    // lens.py:188 (IEEE float64 division)
+}
+
 __host__ __device__ inline int wrap_cell(int c, int n) {
     c %= n;
     return c < 0 ? c + n : c;

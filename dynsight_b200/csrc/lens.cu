@@ -58,12 +58,6 @@ __device__ __forceinline__ int warp_intersect_unsorted(const int* __restrict__ r
     return inter;
 }
 
-__device__ __forceinline__ double lens_value(int a, int b, int inter) {
-    const int denom = a + b;                 // lens.py:170
-    if (denom <= 0) return 0.0;              // lens.py:171-173
-    const int numer = denom - 2 * inter;     // lens.py:187
-    return (double)numer / (double)denom;    // lens.py:188 (IEEE float64 division)
-}
 
 // grid: (ceil(n_pairs / kLensWarps), n_cent); warp w of a block handles pair blockIdx.x*W + w of
 // centre blockIdx.y, so one block writes kLensWarps consecutive doubles of an output row and the

@@ -33,6 +33,8 @@ struct FrameParams {
     float boxf[3];
     float inv_boxf[3];
     int shift_mode[3];       // rows path: image chosen by the neighbour-cell wrap, not by rint
+    float r2_lo_img, r2_hi_img;  // guard band of the plain float32 minimum-image test (pair path)
+    int regular;             // every atom sits in [0, box): its cell needed no modulo (pair path)
 };
 
 constexpr int kWarpsPerBlock = 8;
@@ -175,6 +177,11 @@ int run_scan(const int* in, long long seg_len, int n_seg, int* out, int* tile_tm
 // ------------------------------------------------------------------------------------------
 // K1 / K3 : cell assignment and counting-sort scatter
 // ------------------------------------------------------------------------------------------
+// the truncated quotient of cell_of already lies in [0, ncell): no modulo was needed
+__device__ __forceinline__ bool in_grid(double x, double box, int ncell) {
+    return (long long)(x / box * (double)ncell) < (long long)ncell;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 cell_assign_kernel(const T* __restrict__ pos, int n_atoms, FrameParams* __restrict__ fp,
@@ -191,6 +198,11 @@ cell_assign_kernel(const T* __restrict__ pos, int n_atoms, FrameParams* __restri
         const int cy = cell_of(y, p->box[1], ny);
         const int cz = cell_of(z, p->box[2], nz);
         const int c = (cx * ny + cy) * nz + cz;
+        // an atom outside [0, box) is binned by truncation + modulo (lens.py:52-54), which is not
+        // its geometric cell: the pair path then checks cell adjacency explicitly in this frame
+        if (!(x >= 0.0 && y >= 0.0 && z >= 0.0 && in_grid(x, p->box[0], p->ncell[0]) &&
+              in_grid(y, p->box[1], ny) && in_grid(z, p->box[2], nz)))
+            atomicAnd(&fp[f].regular, 0);
         cell_id[(size_t)f * n_atoms + i] = (unsigned)c;
         atomicAdd(&cell_cnt[p->cell_base + c], 1);
         ax = __double2float_ru(fabs(x));
@@ -240,12 +252,22 @@ __global__ void frame_finalize_kernel(FrameParams* __restrict__ fp, int n_frames
     if (f >= n_frames) return;
     FrameParams* p = fp + f;
     const double u = 5.9604644775390625e-08;  // 2^-24
-    double tol = 8.0 * u * r2;
+    double tol = 8.0 * u * r2, tol_img = 8.0 * u * r2;
     bool exact_only = false;
     for (int k = 0; k < 3; ++k) {
         const double a = (double)__uint_as_float(p->amax_bits[k]);
         const double b = p->box[k] > 0.0 ? p->box[k] : 0.0;
         double delta = 32.0 * u * (a + b);
+        {
+            // pair path, partner frame: d = fl(x_j - x_i) from the caller's coordinates (rounded
+            // to float32 first if they are float64: 2 u a), error u 2a; the image n = rintf(d /
+            // b) is removed by ONE fma(-n, b_f32, d): the product is exact, the sum rounds once
+            // (u |d'| <= u b / 4 for the pairs that matter) and b_f32 is off by u b, times
+            // |n| <= 2a/b + 1.  Total u (6a + 2.25 b) against the exact difference; the
+            // reference's own float64 evaluation is within 2^-48 (a + b) of that.
+            const double d_img = u * (6.0 * a + 2.25 * b) + 3.5527136788005009e-15 * (a + b);
+            tol_img += d_img * (3.0 * r_cut + d_img);
+        }
         if (p->shift_mode[k]) {
             // rows path, shift mode: the staged value is the image next to the atom's cell,
             // |x'| <= A = b + edge <= 1.2 b (ncell >= 6), computed in float64 (error
@@ -269,6 +291,13 @@ __global__ void frame_finalize_kernel(FrameParams* __restrict__ fp, int n_frames
     } else {
         p->r2_lo = __double2float_rd(r2 - tol);
         p->r2_hi = __double2float_ru(r2 + tol);
+    }
+    if (!(tol_img < 0.5 * r2) || exact_only) {
+        p->r2_lo_img = -INFINITY;
+        p->r2_hi_img = INFINITY;
+    } else {
+        p->r2_lo_img = __double2float_rd(r2 - tol_img);
+        p->r2_hi_img = __double2float_ru(r2 + tol_img);
     }
 }
 
@@ -629,6 +658,8 @@ static int make_layout(int n_frames, int n_env, int n_cent, bool same, const dou
             }
             p.cell_base = (int)total;
             p.r2_lo = p.r2_hi = 0.f;
+            p.r2_lo_img = p.r2_hi_img = 0.f;
+            p.regular = 1;
         }
         total += cells;
         if (cells > max_cells) max_cells = (int)cells;
@@ -1330,6 +1361,320 @@ static int neigh_rows_impl(const void* d_pos_env, const void* d_pos_cent, int n_
     return DSG_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Pair path: coordination numbers and LENS straight from the half shell -- no lists at all
+// ------------------------------------------------------------------------------------------
+// With centres == environment the neighbour relation of the reference is symmetric (the 27-cell
+// adjacency is symmetric, and lens.py:17-26 / :100-104 give bit-identical dr2 for (i, j) and
+// (j, i): rint is odd), and LENS only needs three integers per centre and frame pair:
+//   a = |C_t(i)|,  b = |C_{t+delay}(i)|,  inter = |C_t(i) n C_{t+delay}(i)|   (lens.py:167-188).
+// One thread per atom of frame t walks HALF of the 27 cells (own cell behind its own slot + the 13
+// cells that follow in (x, y, z) order; the z triples of a column are contiguous, so 5 runs) with
+// the same float32 test + float64 confirmation as neigh_rows_thread_kernel.  Every hit (i, j):
+//   * counts once for i (register) and once for j (RED.ADD on acc[t][j]);
+//   * is looked up again in frame t+delay -- j in C_{t+delay}(i) <=> dr2 < r2 there (plain float32
+//     minimum image of the caller's coordinates inside its own guard band, float64 confirmation)
+//     and, when that frame has atoms outside [0, box) whose reference cells are not geometric,
+//     the two reference cells are adjacent -- and the answer goes to the upper half of the same
+//     64-bit word.
+// Half the distance tests of the rows path, no rows written, reserved, copied, re-read or merged.
+struct PairArgs {
+    const void* pos;               // (F, N, 3) caller's positions
+    int n_atoms, n_frames, delay;  // delay = 0: coordination numbers only
+    const FrameParams* fp;
+    const int* cell_start;
+    const float4* sorted;          // local representatives on shift-mode axes
+    const unsigned* slot_cell;     // packed (cx, cy, cz) of a sorted slot
+    const unsigned* cell_id;       // (F, N) reference cell of an atom (by atom index)
+    int respect_pbc;
+    double r2;
+    unsigned long long* acc;       // (F, N): count | intersection << 32
+};
+
+constexpr int kPairThreads = 128;
+constexpr int kPairCap = 32;   // staged hits per thread; a longer half row is settled inline
+#ifndef DSG_PAIR_MIN_BLOCKS
+#define DSG_PAIR_MIN_BLOCKS 6
+#endif
+
+template <typename T>
+__global__ void __launch_bounds__(kPairThreads, DSG_PAIR_MIN_BLOCKS)
+lens_pair_kernel(const PairArgs a) {
+    __shared__ int stage[kPairCap][kPairThreads];
+    const int tid = threadIdx.x;
+    const int f = blockIdx.y;
+    const int slot_local = blockIdx.x * kPairThreads + tid;
+    if (slot_local >= a.n_atoms) return;   // threads are independent (no warp collectives)
+    const FrameParams* __restrict__ p = a.fp + f;
+    const int nx = p->ncell[0], ny = p->ncell[1], nz = p->ncell[2];
+    const bool pbc = a.respect_pbc != 0;
+    const float bx = pbc ? p->boxf[0] : 0.f, by = pbc ? p->boxf[1] : 0.f, bz = pbc ? p->boxf[2] : 0.f;
+    const float r2_lo = p->r2_lo, r2_hi = p->r2_hi;
+    const int base_cell = p->cell_base;
+    const size_t n = (size_t)a.n_atoms;
+    const T* __restrict__ pos_f = (const T*)a.pos + (size_t)f * n * 3;
+    const size_t slot = (size_t)f * n + slot_local;
+    const float4 me = a.sorted[slot];
+    const int my_id = __float_as_int(me.w);
+    const unsigned pc = a.slot_cell[slot];
+    const int cx = (int)(pc >> 20), cy = (int)((pc >> 10) & 1023u), cz = (int)(pc & 1023u);
+    unsigned long long* __restrict__ acc_f = a.acc + (size_t)f * n;
+
+    // partner frame t + delay
+    const int f2 = f + a.delay;
+    const bool paired = a.delay > 0 && f2 < a.n_frames;
+    const FrameParams* __restrict__ p2 = a.fp + (paired ? f2 : f);
+    const T* __restrict__ pos_2 = (const T*)a.pos + (size_t)(paired ? f2 : f) * n * 3;
+    const unsigned* __restrict__ cell_2 = a.cell_id + (size_t)(paired ? f2 : f) * n;
+    const float b2x = p2->boxf[0], b2y = p2->boxf[1], b2z = p2->boxf[2];
+    const float i2x = pbc ? p2->inv_boxf[0] : 0.f, i2y = pbc ? p2->inv_boxf[1] : 0.f,
+                i2z = pbc ? p2->inv_boxf[2] : 0.f;
+    const float lo2 = p2->r2_lo_img, hi2 = p2->r2_hi_img;
+    const bool regular2 = p2->regular != 0;
+    float x2 = 0.f, y2 = 0.f, z2 = 0.f;
+    if (paired) {
+        x2 = (float)pos_2[(size_t)my_id * 3];
+        y2 = (float)pos_2[(size_t)my_id * 3 + 1];
+        z2 = (float)pos_2[(size_t)my_id * 3 + 2];
+    }
+    int own_inter = 0;
+    // one hit (my_id, j) of frame t: count it for j and decide membership in frame t + delay
+    auto settle = [&](int j) {
+        unsigned long long inc = 1ull;
+        if (paired) {
+            const T* __restrict__ pj = pos_2 + (size_t)j * 3;
+            float dx = (float)pj[0] - x2, dy = (float)pj[1] - y2, dz = (float)pj[2] - z2;
+            dx = fmaf(-rintf(dx * i2x), b2x, dx);   // i2 = 0 without pbc: the raw difference
+            dy = fmaf(-rintf(dy * i2y), b2y, dy);
+            dz = fmaf(-rintf(dz * i2z), b2z, dz);
+            const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+            bool hit2 = d2 < lo2;
+            if (!hit2 && !(d2 > hi2))   // inside the guard band: rare
+                hit2 = exact_test<T>(pj, pos_2 + (size_t)my_id * 3, p2->box, pbc, a.r2);
+            if (hit2 && !regular2) {
+                // atoms outside [0, box) in that frame: the reference only finds j if their
+                // (truncation + modulo) cells are adjacent (lens.py:92-97)
+                const int m2y = p2->ncell[1], m2z = p2->ncell[2], m2x = p2->ncell[0];
+                const int ci = (int)cell_2[my_id], cj = (int)cell_2[j];
+                const int ex = abs(ci / (m2y * m2z) - cj / (m2y * m2z));
+                const int ey = abs((ci / m2z) % m2y - (cj / m2z) % m2y);
+                const int ez = abs(ci % m2z - cj % m2z);
+                hit2 = (ex <= 1 || ex == m2x - 1) && (ey <= 1 || ey == m2y - 1) &&
+                       (ez <= 1 || ez == m2z - 1);
+            }
+            own_inter += hit2 ? 1 : 0;
+            inc += hit2 ? (1ull << 32) : 0ull;
+        }
+        atomicAdd(&acc_f[j], inc);
+    };
+
+    int cnt = 0;
+    auto walk = [&](auto&& on_hit) {
+        // candidates of a contiguous run of cells, four loads in flight per step
+        auto scan_run = [&](int qb, int qe, float ox, float oy, float oz) {
+            for (int q0 = qb; q0 < qe; q0 += 4) {
+                float4 cd[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) cd[u] = a.sorted[min(q0 + u, qe - 1)];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = __float_as_int(cd[u].w);
+                    const float dx = cd[u].x + ox, dy = cd[u].y + oy, dz = cd[u].z + oz;
+                    const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                    const bool valid = q0 + u < qe;
+                    bool hit = d2 < r2_lo;
+                    if (valid && !hit && !(d2 > r2_hi))   // inside the guard band: rare
+                        hit = exact_test<T>(pos_f + (size_t)j * 3, pos_f + (size_t)my_id * 3,
+                                            p->box, pbc, a.r2);
+                    on_hit(hit && valid, j);
+                }
+            }
+        };
+        // the cells (cx + ddx, cy + ddy, cz - 1 .. cz + 1): one run, or three at the z wrap
+        auto column = [&](int ddx, int ddy) {
+            const int ax = cx + ddx, ay = cy + ddy;
+            const int wx = ax >= nx ? ax - nx : ax;
+            const int wy = ay < 0 ? ay + ny : (ay >= ny ? ay - ny : ay);
+            const float ox = (ax >= nx ? bx : 0.f) - me.x;
+            const float oy = (ay < 0 ? -by : (ay >= ny ? by : 0.f)) - me.y;
+            const int rowc = base_cell + (wx * ny + wy) * nz;
+            if (cz >= 1 && cz <= nz - 2) {
+                scan_run(a.cell_start[rowc + cz - 1], a.cell_start[rowc + cz + 2], ox, oy, -me.z);
+            } else {
+                for (int ddz = -1; ddz <= 1; ++ddz) {
+                    const int az = cz + ddz;
+                    const int wz = az < 0 ? az + nz : (az >= nz ? az - nz : az);
+                    const float oz = (az < 0 ? -bz : (az >= nz ? bz : 0.f)) - me.z;
+                    scan_run(a.cell_start[rowc + wz], a.cell_start[rowc + wz + 1], ox, oy, oz);
+                }
+            }
+        };
+        // own column: the slots behind mine in my cell, then the cell above
+        const int col = base_cell + (cx * ny + cy) * nz;
+        if (cz + 1 < nz) {
+            scan_run((int)slot + 1, a.cell_start[col + cz + 2], -me.x, -me.y, -me.z);
+        } else {
+            scan_run((int)slot + 1, a.cell_start[col + cz + 1], -me.x, -me.y, -me.z);
+            scan_run(a.cell_start[col], a.cell_start[col + 1], -me.x, -me.y, bz - me.z);
+        }
+        column(0, 1);
+        column(1, -1);
+        column(1, 0);
+        column(1, 1);
+    };
+    // j is never my_id here (my own slot is not part of any run): lens.py:104 holds by construction
+    walk([&](bool hit, int j) {
+        if (hit) stage[min(cnt, kPairCap - 1)][tid] = j;   // branch-free staging
+        cnt += hit ? 1 : 0;
+    });
+    if (cnt <= kPairCap) {
+        for (int h = 0; h < cnt; ++h) settle(stage[h][tid]);
+    } else {   // more hits than the tile holds (rare): walk again and settle each hit at once
+        cnt = 0;
+        walk([&](bool hit, int j) {
+            if (hit) settle(j);
+            cnt += hit ? 1 : 0;
+        });
+    }
+    atomicAdd(&acc_f[my_id], (unsigned long long)cnt | ((unsigned long long)own_inter << 32));
+}
+
+// acc -> counts (F, N) int32 and LENS (N, n_pairs) float64 (transposed through shared memory)
+__global__ void __launch_bounds__(1024)
+pair_finalize_kernel(const unsigned long long* __restrict__ acc, int n_frames, int n_atoms,
+                     int delay, int* __restrict__ counts, double* __restrict__ lens,
+                     long long ld, long long col0) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+    {
+        const int t = t0 + ty, i = i0 + tx;
+        double v = 0.0;
+        if (t < n_frames && i < n_atoms) {
+            const unsigned long long w = acc[(size_t)t * n_atoms + i];
+            const int ca = (int)(unsigned)(w & 0xffffffffull);
+            if (counts) counts[(size_t)t * n_atoms + i] = ca;
+            if (lens && delay > 0 && t + delay < n_frames) {
+                const int cb = (int)(unsigned)(acc[(size_t)(t + delay) * n_atoms + i] & 0xffffffffull);
+                v = lens_value(ca, cb, (int)(unsigned)(w >> 32));
+            }
+        }
+        tile[ty][tx] = v;
+    }
+    __syncthreads();
+    const int t = t0 + tx, i = i0 + ty;
+    if (lens && delay > 0 && t + delay < n_frames && i < n_atoms)
+        lens[(long long)i * ld + col0 + t] = tile[tx][ty];
+}
+
+// The pair path applies when one thread per atom is the right granularity (sparse cells, short
+// rows), the slot -> cell packing fits and, under pbc, every axis is in shift mode.
+static bool pair_path_supported(const std::vector<FrameParams>& fps, int n_atoms, double r_cut,
+                                int respect_pbc) {
+    double cand_sum = 0.0, k_max = 0.0;
+    for (const auto& p : fps) {
+        for (int k = 0; k < 3; ++k) {
+            if (respect_pbc && p.ncell[k] < 6) return false;
+            if (p.ncell[k] > 1024) return false;
+        }
+        cand_sum += 27.0 * n_atoms / ((double)p.ncell[0] * p.ncell[1] * p.ncell[2]);
+        const double k_est =
+            n_atoms / (p.box[0] * p.box[1] * p.box[2]) * 4.18879 * r_cut * r_cut * r_cut;
+        if (k_est > k_max) k_max = k_est;
+    }
+    const double half = 0.5 * k_max;
+    return cand_sum / (double)fps.size() <= 200.0 && half + 4.0 * std::sqrt(half) <= kPairCap;
+}
+
+struct PairLayout {
+    NeighLayout L;
+    size_t off_acc = 0, bytes = 0;
+};
+
+static int pair_layout(int n_frames, int n_atoms, const double* h_box, double r_cut, PairLayout* P,
+                       std::vector<FrameParams>* fps) {
+    int rc = make_layout(n_frames, n_atoms, n_atoms, true, h_box, r_cut, &P->L, fps);
+    if (rc) return rc;
+    P->off_acc = align_up(P->L.bytes);
+    P->bytes = P->off_acc + align_up(8 * (size_t)n_frames * n_atoms);
+    return DSG_OK;
+}
+
+template <typename T>
+static int lens_direct_impl(const void* d_pos, int n_frames, int n_atoms, const double* h_box,
+                            double r_cut, int respect_pbc, int delay, void* d_ws, size_t ws_bytes,
+                            int32_t* d_counts, double* d_lens, int64_t lens_stride, int64_t col0,
+                            cudaStream_t st) {
+    PairLayout P;
+    std::vector<FrameParams> fps;
+    int rc = pair_layout(n_frames, n_atoms, h_box, r_cut, &P, &fps);
+    if (rc) return rc;
+    if (!pair_path_supported(fps, n_atoms, r_cut, respect_pbc))
+        return set_error(DSG_ERR_UNSUPPORTED,
+                         "the pair path needs sparse cells and >= 6 cells per periodic axis; use "
+                         "dsg_neigh_rows + dsg_lens_pairs_rows");
+    if (!d_ws || ws_bytes < P.bytes)
+        return set_error(DSG_ERR_WORKSPACE_TOO_SMALL, "workspace has %zu bytes, %zu needed",
+                         ws_bytes, P.bytes);
+    if (!d_pos || (!d_counts && !d_lens))
+        return set_error(DSG_ERR_INVALID_ARGUMENT, "NULL device pointer argument");
+    if (delay < 0 || (d_lens && (delay < 1 || delay >= n_frames)))
+        return set_error(DSG_ERR_INVALID_ARGUMENT, "delay=%d needs 1 <= delay < n_frames=%d", delay,
+                         n_frames);
+    const NeighLayout& L = P.L;
+    for (auto& p : fps)
+        for (int k = 0; k < 3; ++k) p.shift_mode[k] = respect_pbc ? 1 : 0;
+    char* ws = (char*)d_ws;
+    FrameParams* d_fp = (FrameParams*)(ws + L.off_fp);
+    unsigned* cid = (unsigned*)(ws + L.off_cell_id_e);
+    int* cnt = (int*)(ws + L.off_cnt_e);
+    int* start = (int*)(ws + L.off_start_e);
+    float4* sorted = (float4*)(ws + L.off_sorted_e);
+    int* tile_tmp = (int*)(ws + L.off_tile_tmp);
+    unsigned* slot_cell = (unsigned*)(ws + L.off_slot_cell_e);
+    unsigned long long* acc = (unsigned long long*)(ws + P.off_acc);
+    const double rc_eff = r_cut - 1e-6;   // lens.py:78
+    const double r2 = rc_eff * rc_eff;
+
+    DSG_CUDA_CHECK(cudaMemcpyAsync(d_fp, fps.data(), sizeof(FrameParams) * n_frames,
+                                   cudaMemcpyHostToDevice, st));
+    DSG_CUDA_CHECK(cudaMemsetAsync(cnt, 0, 4 * (size_t)L.total_cells, st));
+    DSG_CUDA_CHECK(cudaMemsetAsync(acc, 0, 8 * (size_t)n_frames * n_atoms, st));
+    dim3 agrid((n_atoms + 255) / 256, n_frames);
+    cell_assign_kernel<T><<<agrid, 256, 0, st>>>((const T*)d_pos, n_atoms, d_fp, cid, cnt);
+    DSG_LAUNCH_CHECK("cell_assign_kernel");
+    rc = run_scan(cnt, L.total_cells, 1, start, tile_tmp, nullptr, st);
+    if (rc) return rc;
+    cell_scatter_local_kernel<T><<<agrid, 256, 0, st>>>((const T*)d_pos, n_atoms, d_fp, cid, cnt,
+                                                        start, sorted, slot_cell);
+    DSG_LAUNCH_CHECK("cell_scatter_local_kernel");
+    frame_finalize_kernel<<<(n_frames + 127) / 128, 128, 0, st>>>(d_fp, n_frames, r_cut, r2);
+    DSG_LAUNCH_CHECK("frame_finalize_kernel");
+
+    PairArgs a;
+    a.pos = d_pos;
+    a.n_atoms = n_atoms;
+    a.n_frames = n_frames;
+    a.delay = d_lens ? delay : 0;
+    a.fp = d_fp;
+    a.cell_start = start;
+    a.sorted = sorted;
+    a.slot_cell = slot_cell;
+    a.cell_id = cid;
+    a.respect_pbc = respect_pbc;
+    a.r2 = r2;
+    a.acc = acc;
+    dim3 pgrid((n_atoms + kPairThreads - 1) / kPairThreads, n_frames);
+    lens_pair_kernel<T><<<pgrid, kPairThreads, 0, st>>>(a);
+    DSG_LAUNCH_CHECK("lens_pair_kernel");
+    dim3 fgrid((n_atoms + 31) / 32, (n_frames + 31) / 32);
+    pair_finalize_kernel<<<fgrid, dim3(32, 32), 0, st>>>(acc, n_frames, n_atoms, a.delay, d_counts,
+                                                         d_lens, lens_stride, col0);
+    DSG_LAUNCH_CHECK("pair_finalize_kernel");
+    return DSG_OK;
+}
+
 }  // namespace dsg
 
 using namespace dsg;
@@ -1459,4 +1804,40 @@ extern "C" int dsg_rows_to_csr(const int32_t* d_counts, const int64_t* d_row_sta
         n_frames, n_cent, d_indices);
     DSG_LAUNCH_CHECK("rows_to_csr_kernel");
     return DSG_OK;
+}
+
+extern "C" int dsg_lens_direct_supported(int n_frames, int n_atoms, const double* h_box,
+                                         double r_cut, int respect_pbc) {
+    PairLayout P;
+    std::vector<FrameParams> fps;
+    int rc = pair_layout(n_frames, n_atoms, h_box, r_cut, &P, &fps);
+    if (rc) return rc;
+    return pair_path_supported(fps, n_atoms, r_cut, respect_pbc) ? 1 : 0;
+}
+
+extern "C" int dsg_lens_direct_workspace_bytes(int n_frames, int n_atoms, const double* h_box,
+                                               double r_cut, size_t* bytes_out) {
+    if (!bytes_out) return set_error(DSG_ERR_INVALID_ARGUMENT, "bytes_out is NULL");
+    PairLayout P;
+    int rc = pair_layout(n_frames, n_atoms, h_box, r_cut, &P, nullptr);
+    if (rc) return rc;
+    *bytes_out = P.bytes;
+    return DSG_OK;
+}
+
+extern "C" int dsg_lens_direct(const void* d_pos, int pos_dtype, int n_frames, int n_atoms,
+                               const double* h_box, double r_cut, int respect_pbc, int delay,
+                               void* d_workspace, size_t workspace_bytes, int32_t* d_counts,
+                               double* d_lens, int64_t lens_stride, int64_t col0, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pos_dtype == DSG_F32)
+        return lens_direct_impl<float>(d_pos, n_frames, n_atoms, h_box, r_cut, respect_pbc != 0,
+                                       delay, d_workspace, workspace_bytes, d_counts, d_lens,
+                                       lens_stride, col0, st);
+    if (pos_dtype == DSG_F64)
+        return lens_direct_impl<double>(d_pos, n_frames, n_atoms, h_box, r_cut, respect_pbc != 0,
+                                        delay, d_workspace, workspace_bytes, d_counts, d_lens,
+                                        lens_stride, col0, st);
+    return set_error(DSG_ERR_INVALID_ARGUMENT, "pos_dtype=%d is neither DSG_F32 nor DSG_F64",
+                     pos_dtype);
 }

@@ -67,6 +67,9 @@ constexpr int kOpenCellsPerAxis = 32;
 #ifndef DSG_SOAP_EXP_HORNER
 #define DSG_SOAP_EXP_HORNER 0      // Horner instead of Estrin in exp_scaled
 #endif
+#ifndef DSG_SOAP_KO_HALFLOADS
+#define DSG_SOAP_KO_HALFLOADS 0    // timing probe: half of the harmonics loads of phase C (wrong results)
+#endif
 #ifndef DSG_SOAP_EXTRA_SMEM
 #define DSG_SOAP_EXTRA_SMEM 0      // occupancy probe: dummy dynamic shared memory per block
 #endif
@@ -499,6 +502,23 @@ __device__ __forceinline__ void accumulate_packed(Acc<kPackSlots>& a, double e0,
         a.v[2 * s] = fma(e0, v.x, a.v[2 * s]);
         a.v[2 * s + 1] = fma(e0, v.y, a.v[2 * s + 1]);
     }
+#if DSG_SOAP_KO_HALFLOADS   // timing probe only (wrong results): how much do the shared loads cost?
+    double2 v = r2p[0];
+    a.v[10] = fma(e0, v.x, a.v[10]);
+    a.v[11] = fma(ea, v.y, a.v[11]);
+    v = r2p[1];
+    a.v[12] = fma(ea, v.x, a.v[12]);
+    a.v[13] = fma(eb, v.y, a.v[13]);
+    v = r2p[2];
+    a.v[14] = fma(eb, v.x, a.v[14]);
+    a.v[15] = fma(ec, v.y, a.v[15]);
+    v = r2p[3];
+    a.v[16] = fma(ec, v.x, a.v[16]);
+    a.v[17] = fma(e1, v.y, a.v[17]);
+    v = r2p[4];
+    a.v[18] = fma(e1, v.x, a.v[18]);
+    a.v[19] = fma(e1, v.y, a.v[19]);
+#else
     double2 v = r2p[5];
     a.v[10] = fma(e0, v.x, a.v[10]);
     a.v[11] = fma(ea, v.y, a.v[11]);
@@ -514,6 +534,7 @@ __device__ __forceinline__ void accumulate_packed(Acc<kPackSlots>& a, double e0,
     v = r2p[9];
     a.v[18] = fma(e1, v.x, a.v[18]);
     a.v[19] = fma(e1, v.y, a.v[19]);
+#endif
 }
 
 __device__ __forceinline__ void store_packed(const Acc<kPackSlots>& a, int g, int k, int n,

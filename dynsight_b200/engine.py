@@ -350,10 +350,11 @@ def lens_from_positions(
     out: torch.Tensor | None = None,
     col0: int = 0,
     capacity: int | None = None,
+    force_warp: bool = False,
 ) -> tuple[torch.Tensor, NeighborRows]:
     """LENS for all frame pairs of a batch straight from positions (rows path + retry on the rare
-    reservation overflow).  Returns the (M, n_pairs) result and the rows batch (for the counts)."""
-    force_warp = False
+    reservation overflow).  Returns the (M, n_pairs) result and the rows batch (for the counts).
+    ``force_warp`` starts with the warp-per-cell kernel (a caller that already saw status 2)."""
     for _ in range(_MAX_ROW_RETRIES):
         nr = neighbor_rows(pos_env, box, r_cut, pos_cent, respect_pbc, capacity, force_warp)
         res = lens_pairs_rows(nr, delay, out=out, col0=col0)
@@ -365,6 +366,72 @@ def lens_from_positions(
             capacity = _next_capacity(nr, capacity)
     msg = f"neighbour rows still overflow after {_MAX_ROW_RETRIES} attempts (capacity {capacity})"
     raise RuntimeError(msg)
+
+
+def lens_direct_supported(
+    n_frames: int, n_atoms: int, box: np.ndarray | torch.Tensor, r_cut: float,
+    respect_pbc: bool = True,
+) -> bool:  # fmt: skip
+    """Whether :func:`lens_direct` (pair path, centres == environment) applies to such a batch."""
+    if n_frames < 1 or n_atoms < 1:
+        return False
+    h_box = _host_box(box, n_frames)
+    if not bool(np.all(np.isfinite(h_box) & (h_box > 0.0))):
+        return False
+    rc = _lib.load().dsg_lens_direct_supported(
+        n_frames, n_atoms, h_box.ctypes.data, float(r_cut), int(bool(respect_pbc))
+    )
+    return rc == 1
+
+
+def lens_direct(
+    pos: torch.Tensor,
+    box: np.ndarray | torch.Tensor,
+    r_cut: float,
+    delay: int = 1,
+    respect_pbc: bool = True,
+    out: torch.Tensor | None = None,
+    col0: int = 0,
+    want_lens: bool = True,
+    want_counts: bool = True,
+) -> tuple[torch.Tensor | None, torch.Tensor | None]:
+    """LENS and coordination numbers of a batch straight from positions, centres == environment,
+    without neighbour lists (``dsg_lens_direct``: half-shell pair search, every pair found in frame
+    t is looked up in frame t + delay).  Returns ``(lens (N, F - delay) float64 | None,
+    counts (F, N) int32 | None)``; raises ``DsgError`` (unsupported) when
+    :func:`lens_direct_supported` is false."""
+    lib = _lib.load()
+    _require_cuda(pos, "pos")
+    n_frames, n_atoms, _ = pos.shape
+    h_box = _host_box(box, n_frames)
+    dev = pos.device
+    ws_bytes = ctypes.c_size_t(0)
+    _lib.check(
+        lib.dsg_lens_direct_workspace_bytes(
+            n_frames, n_atoms, h_box.ctypes.data, float(r_cut), ctypes.byref(ws_bytes)
+        )
+    )
+    workspace = torch.empty(ws_bytes.value, dtype=torch.uint8, device=dev)
+    counts = torch.empty((n_frames, n_atoms), dtype=torch.int32, device=dev) if want_counts else None
+    if want_lens:
+        if n_frames - delay < 1 or delay < 1:
+            msg = "No valid pairs found."
+            raise RuntimeError(msg)
+        if out is None:
+            out = torch.empty((n_atoms, n_frames - delay), dtype=torch.float64, device=dev)
+            col0 = 0
+    else:
+        out = None
+    _lib.check(
+        lib.dsg_lens_direct(
+            pos.data_ptr(), _dtype_code(pos), n_frames, n_atoms, h_box.ctypes.data, float(r_cut),
+            int(bool(respect_pbc)), int(delay) if want_lens else 0, workspace.data_ptr(),
+            ws_bytes.value, counts.data_ptr() if counts is not None else None,
+            out.data_ptr() if out is not None else None,
+            out.stride(0) if out is not None else 0, int(col0), _stream_ptr(),
+        )
+    )  # fmt: skip
+    return out, counts
 
 
 def wrap_positions(pos: torch.Tensor, box: np.ndarray | torch.Tensor) -> torch.Tensor:

@@ -42,7 +42,7 @@ def compute_lens_device(
     ag_cent = universe.select_atoms(centers)
     fr_idx = frames.frame_sequence(universe.trajectory.n_frames, trajslice)
     n_pairs = len(fr_idx) - delay
-    if delay < 1 or n_pairs < 1:  # "pairs" would be empty (lens.py:255-260)
+    if delay < 0 or n_pairs < 1:  # "pairs" would be empty (lens.py:255-260)
         msg = "No valid pairs found."
         raise RuntimeError(msg)
     n_all = len(universe.atoms)
@@ -51,12 +51,21 @@ def compute_lens_device(
     same = ix_env.shape == ix_cent.shape and bool(np.array_equal(ix_env, ix_cent))
     dev = frames.device()
     out = torch.empty((ix_cent.size, n_pairs), dtype=torch.float64, device=dev)
-    if ix_cent.size == 0 or ix_env.size == 0:
+    if ix_cent.size == 0 or ix_env.size == 0 or delay == 0:
         # no centres: empty result; no environment atoms: every row is empty and
-        # lens_from_two_csr returns 0.0 for a + b == 0 (lens.py:171-173)
+        # lens_from_two_csr returns 0.0 for a + b == 0 (lens.py:171-173); delay = 0 pairs every
+        # frame with itself (lens.py:255-257): identical lists, LENS = 0.0 everywhere
         return out.zero_()
+    k_est = 0.0
     if batch_frames is None:
-        batch_frames = frames.pick_batch_frames(max(ix_env.size, ix_cent.size), 160.0, delay + 1)
+        # rows path: 1.3 k int32 row entries + counts / row starts / cell-sorted copies per
+        # atom-frame; the pair path needs 44 B.  k from the density of the first frame.
+        host, dims = frames._load_host(universe, fr_idx[:1])  # noqa: SLF001
+        box0 = (dims[:, :3].astype(np.float64) if dims is not None else
+                (host.amax(dim=1) - host.amin(dim=1)).numpy().astype(np.float64) * 1.01)  # fmt: skip
+        k_est = _mean_neighbours_estimate(ix_env.size, box0, r_cut)
+        batch_frames = frames.pick_batch_frames(max(ix_env.size, ix_cent.size),
+                                                60.0 + 5.2 * k_est, delay + 1)  # fmt: skip
     batch_frames = max(batch_frames, delay + 1)
 
     def settle(job: tuple | None) -> None:
@@ -65,9 +74,11 @@ def compute_lens_device(
             return
         fb, box, pos_env, pos_cent, nr = job
         if nr.overflowed():
+            warp = nr.needs_warp_kernel()
             engine.lens_from_positions(
                 pos_env, box, r_cut, delay, pos_cent, respect_pbc, out=out, col0=fb.seq0,
-                capacity=None if nr.needs_warp_kernel() else engine._next_capacity(nr, None),  # noqa: SLF001
+                capacity=None if warp else engine._next_capacity(nr, None),  # noqa: SLF001
+                force_warp=warp,
             )
 
     # Software pipeline over batches: asking the iterator for batch k issues its host -> device
@@ -78,6 +89,14 @@ def compute_lens_device(
     for fb in frames.iter_batches(universe, fr_idx, batch_frames, overlap=delay):
         box = frames.lens_boxes(fb, 1.01)
         pos_env = fb.select(sel_env, n_all)
+        if same and engine.lens_direct_supported(pos_env.shape[0], pos_env.shape[1], box, r_cut,
+                                                 respect_pbc):  # fmt: skip
+            # centres == environment, sparse cells: pair path, no lists and nothing to retry
+            engine.lens_direct(pos_env, box, r_cut, delay, respect_pbc, out=out, col0=fb.seq0,
+                               want_counts=False)  # fmt: skip
+            settle(pending)
+            pending = None
+            continue
         pos_cent = None if same else fb.select(sel_cent, n_all)
         nr = engine.neighbor_rows(pos_env, box, r_cut, pos_cent, respect_pbc)
         engine.lens_pairs_rows(nr, delay, out=out, col0=fb.seq0)
@@ -101,6 +120,9 @@ def compute_lens(
 
     Returns LENS values for each centre and each pair of frames, shape (n_centers, n_pairs),
     float64 -- identical (bit for bit) to the reference's result.
+
+    ``delay=0`` pairs every frame with itself like the reference does and returns zeros of shape
+    (n_centers, n_frames).
 
     Raises:
         RuntimeError: "No valid pairs found." when the frame selection is shorter than ``delay``.
@@ -270,6 +292,12 @@ def list_neighbours_along_trajectory(
         return NeighbourList(ag_env, zero_counts, empty_csr)
     if fr_idx:
         for pos_env, pos_cent, box in batches():
+            if pos_cent is None and engine.lens_direct_supported(
+                pos_env.shape[0], pos_env.shape[1], box, r_cut, respect_pbc
+            ):  # centres == environment, sparse cells: half-shell pair counts, no lists
+                counts.append(engine.lens_direct(pos_env, box, r_cut, 0, respect_pbc,
+                                                 want_lens=False)[1])  # fmt: skip
+                continue
             # counts only: the rows go to a scratch buffer and are dropped
             nr = engine.neighbor_rows_checked(pos_env, box, r_cut, pos_cent, respect_pbc)
             counts.append(nr.counts)

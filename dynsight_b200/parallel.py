@@ -94,20 +94,32 @@ def gather_columns(
     local: torch.Tensor, group: dist.ProcessGroup | None = None
 ) -> torch.Tensor | None:
     """Concatenate per-rank result slabs (n_centers, n_local_pairs) along the frame axis on
-    rank 0 (other ranks return ``None``).  Slab widths may differ between ranks."""
+    rank 0 (other ranks return ``None``).  Slab widths may differ between ranks.
+
+    Only the widths are all-gathered (one int64 per rank); the slabs travel point to point to
+    rank 0, which receives them one at a time straight behind each other -- no rank ever holds
+    more than its own slab, and rank 0 the result plus one slab in flight."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     width = torch.tensor([local.shape[1]], dtype=torch.int64, device=local.device)
     widths = [torch.zeros_like(width) for _ in range(world)]
     dist.all_gather(widths, width, group=group)
-    max_w = int(max(int(w.item()) for w in widths))
-    padded = torch.zeros((local.shape[0], max_w), dtype=local.dtype, device=local.device)
-    padded[:, : local.shape[1]] = local
-    out = [torch.zeros_like(padded) for _ in range(world)]
-    dist.all_gather(out, padded, group=group)
     if rank != 0:
+        if local.shape[1] > 0:
+            dist.send(local.contiguous(), dist.get_global_rank(group, 0) if group else 0,
+                      group=group)  # fmt: skip
         return None
-    return torch.cat([o[:, : int(w.item())] for o, w in zip(out, widths)], dim=1)
+    ws = [int(w.item()) for w in widths]
+    out = torch.empty((local.shape[0], sum(ws)), dtype=local.dtype, device=local.device)
+    out[:, : ws[0]] = local
+    col = ws[0]
+    for r in range(1, world):
+        if ws[r] > 0:
+            slab = torch.empty((local.shape[0], ws[r]), dtype=local.dtype, device=local.device)
+            dist.recv(slab, dist.get_global_rank(group, r) if group else r, group=group)
+            out[:, col : col + ws[r]] = slab
+            col += ws[r]
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

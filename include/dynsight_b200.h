@@ -132,6 +132,31 @@ int dsg_lens_pairs_rows(const int32_t* d_counts, const int64_t* d_row_start,
                         const int32_t* d_rows, int n_frames, int n_cent, int delay, double* d_out,
                         int64_t ld_out, int64_t col0, void* stream);
 
+/* Pair path: coordination numbers and LENS of a batch of frames WITHOUT neighbour lists.
+ * Replaces, for centers == selection (the default of compute_lens, lens.py:192-199), the whole
+ * chain neighbor_list_celllist_centers (lens.py:69-147) x 2 + lens_from_two_csr (lens.py:150-189)
+ * of one frame pair, and the counting loop of Trj.get_coord_number (trajectory.py:168-184).
+ * The neighbour relation of the reference is symmetric when centres and environment coincide,
+ * so every pair is tested once (half of the 27 cells) and credited to both atoms; a pair found
+ * in frame t is looked up directly in frame t + delay.  Same membership rule, bit for bit:
+ * dr2 < (r_cut - 1e-6)^2 on the minimum image (if respect_pbc), cells of the reference grid,
+ * atoms outside [0, box) binned by truncation + modulo like lens.py:52-54.
+ *   d_counts (n_frames, n_atoms) int32 or NULL;
+ *   d_lens or NULL: d_lens[i*lens_stride + col0 + t], t in [0, n_frames - delay), float64.
+ * dsg_lens_direct_supported: 1 if this path applies to the batch (sparse cells, i.e. one thread
+ * per atom is the right granularity; at least six reference cells per periodic axis), 0 if the
+ * caller has to use dsg_neigh_rows + dsg_lens_pairs_rows, < 0 on invalid arguments. */
+int dsg_lens_direct_supported(int n_frames, int n_atoms, const double* h_box, double r_cut,
+                              int respect_pbc);
+
+int dsg_lens_direct_workspace_bytes(int n_frames, int n_atoms, const double* h_box, double r_cut,
+                                    size_t* bytes_out);
+
+int dsg_lens_direct(const void* d_pos, int pos_dtype, int n_frames, int n_atoms,
+                    const double* h_box, double r_cut, int respect_pbc, int delay,
+                    void* d_workspace, size_t workspace_bytes, int32_t* d_counts, double* d_lens,
+                    int64_t lens_stride, int64_t col0, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * LENS (replaces lens/lens.py:150-189 lens_from_two_csr, batched over frame pairs).
  *

@@ -1,6 +1,6 @@
 """Small single-purpose launcher for ncu: runs one hot-path stage a few times.
 
-usage: python scripts/profile_target.py soap|soap3|neigh|neigh_fluid|tsoap|tcf|spavg|spavg324 [atoms] [frames]
+usage: python scripts/profile_target.py soap|soap3|neigh|neigh_fluid|pair|pair_fluid|tsoap|tcf|spavg|spavg324 [atoms] [frames]
 """
 import sys
 from pathlib import Path
@@ -19,7 +19,7 @@ g = torch.Generator(device=dev).manual_seed(0)
 if what == "soap3":  # cfg4-like: 3 species, l_max = 10, metal density
     box_l = (n / 0.0857) ** (1 / 3)
     r_cut = 5.0
-elif what in ("neigh_fluid", "spavg", "spavg324"):
+elif what in ("neigh_fluid", "pair_fluid", "spavg", "spavg324"):
     box_l = (n / 0.8) ** (1 / 3)
     r_cut = 1.5
 else:
@@ -38,6 +38,8 @@ for it in range(3):
     elif what == "soap3":
         sp3 = (torch.arange(n, device=dev, dtype=torch.int32) * 7919 % 3).to(torch.int32)
         out = engine.soap_power_spectrum(pos, sp3, cen, box, 5.0, 8, 10, n_species=3)
+    elif what in ("pair", "pair_fluid"):
+        out, _ = engine.lens_direct(pos, box, r_cut, 1, True)
     elif what in ("neigh", "neigh_fluid"):
         if len(sys.argv) > 4 and sys.argv[4] == "csr":
             nb = engine.neighbor_lists(pos, box, r_cut)

@@ -477,3 +477,181 @@ def test_clustered_atoms_overflow_retry_terminates():
     lens, nr = engine.lens_from_positions(_dev(pos), box, r_cut, 1, capacity=256 * 64)
     assert not nr.overflowed()
     assert np.array_equal(lens.cpu().numpy(), lo.compute_lens_arrays(pos, dims, r_cut))
+
+
+# ---------------------------------------------------------------------------------------------
+# pair path (dsg_lens_direct): half-shell pair search, partner-frame lookup, no lists
+# ---------------------------------------------------------------------------------------------
+def _dims(box, n_frames):
+    box = np.asarray(box, dtype=np.float32)
+    if box.ndim == 1:
+        box = np.tile(box, (n_frames, 1))
+    return np.concatenate([box, np.full((n_frames, 3), 90, np.float32)], axis=1)
+
+
+def _check_direct_vs_oracle(pos, box, r_cut, delay, pbc, dtype=None):
+    from dynsight_b200 import engine
+
+    n_frames = pos.shape[0]
+    assert engine.lens_direct_supported(n_frames, pos.shape[1], box, r_cut, pbc)
+    lens, counts = engine.lens_direct(_dev(pos, dtype), box, r_cut, delay, pbc)
+    dims = _dims(box, n_frames)
+    want = lo.compute_lens_arrays(pos, dims, r_cut, delay=delay, respect_pbc=pbc)
+    want_c = lo.coord_number_arrays(pos, dims, r_cut, respect_pbc=pbc)
+    assert np.array_equal(counts.cpu().numpy().T.astype(np.float64), want_c), "counts differ"
+    assert np.array_equal(lens.cpu().numpy(), want), "LENS differs"
+    # counts-only mode (Trj.get_coord_number)
+    _, counts0 = engine.lens_direct(_dev(pos, dtype), box, r_cut, 0, pbc, want_lens=False)
+    assert torch.equal(counts0, counts)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_pair_path_random_cases(dtype):
+    """Random boxes from 3 (pbc off) / 6 (pbc on) to 12 cells per axis, atoms inside and far outside
+    the box (the reference bins those by truncation + modulo), several delays, per-frame boxes."""
+    rng = np.random.default_rng(2024)
+    for case in range(36):
+        n = int(rng.integers(200, 1500))
+        n_frames = int(rng.integers(2, 7))
+        delay = int(rng.integers(1, n_frames))
+        pbc = bool(case % 2)
+        r_cut = float(rng.uniform(0.8, 1.7))
+        ncx = rng.integers(6 if pbc else 3, 13, size=3)
+        box = (ncx * r_cut * rng.uniform(1.0, 1.15, size=3)).astype(np.float32)
+        spread = (1.0, 1.0, 1.3, 3.0)[case % 4]
+        pos = ((rng.random((n_frames, n, 3)) - 0.5) * spread + 0.5) * box
+        pos[1:] = pos[0] + rng.normal(0, 0.2 * r_cut, (n_frames - 1, n, 3)).cumsum(axis=0)
+        pos = pos.astype(np.float32)
+        if spread == 1.0:
+            pos = np.clip(pos, 0, np.nextafter(box, np.float32(0))).astype(np.float32)
+        boxes = box
+        if case % 3 == 0:  # NPT-like: every frame has its own box (same cell counts or not)
+            boxes = (box[None, :] * rng.uniform(0.97, 1.03, (n_frames, 3))).astype(np.float32)
+        p = pos if dtype == torch.float32 else pos.astype(np.float64) + rng.normal(0, 1e-9, pos.shape)
+        from dynsight_b200 import engine
+
+        if not engine.lens_direct_supported(n_frames, n, boxes, r_cut, pbc):
+            continue  # too dense for one thread per atom: covered by the rows path tests
+        _check_direct_vs_oracle(p, boxes, r_cut, delay, pbc, dtype)
+
+
+def test_pair_path_near_threshold_pairs_in_both_frames():
+    """Adversarial for BOTH float32 guard bands of the pair path: thousands of pairs within a few
+    float32 ulps of the cutoff at coordinates ~100, a third of them across the periodic boundary;
+    frame 1 holds the same points moved rigidly by a random lattice of tiny shifts, so the
+    partner-frame test (plain float32 minimum image) sees near-threshold pairs too."""
+    rng = np.random.default_rng(77)
+    r_cut = 1.5
+    rc = r_cut - 1e-6
+    box = np.array([107.7, 96.3, 121.1], dtype=np.float32)
+    n_pairs = 6000
+    base = rng.random((n_pairs, 3)) * box
+    face = rng.integers(0, 3, n_pairs)
+    hug = rng.random(n_pairs) < 0.33
+    base[hug, face[hug]] = rng.random(hug.sum()) * 0.4
+    d = rng.normal(size=(n_pairs, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r = rc * (1.0 + rng.uniform(-4e-6, 4e-6, n_pairs))
+    partner = base - d * r[:, None]
+    pts = np.mod(np.concatenate([base, partner]), box).astype(np.float32)
+    # frame 1: every pair re-drawn at a fresh near-threshold distance around the same base point
+    r1 = rc * (1.0 + rng.uniform(-4e-6, 4e-6, n_pairs))
+    pts1 = np.mod(np.concatenate([base, base - d * r1[:, None]]), box).astype(np.float32)
+    top = np.nextafter(box, np.float32(0))
+    frames = np.minimum(np.stack([pts, pts1, pts]), top).astype(np.float32)
+    _check_direct_vs_oracle(frames, box, r_cut, 1, True)
+    _check_direct_vs_oracle(frames, box, r_cut, 2, True)
+
+
+def test_pair_path_dense_spot_settles_inline():
+    """A cluster whose half rows exceed the 32-entry staging tile in an otherwise dilute box: the
+    thread walks its cells a second time and settles every hit at once."""
+    rng = np.random.default_rng(8)
+    box = np.array([30.0, 31.0, 29.0], dtype=np.float32)
+    n = 4000
+    pos = (rng.random((3, n, 3)) * box).astype(np.float32)
+    pos[:, :90] = (np.array([14.2, 15.1, 13.9]) + rng.normal(0, 0.25, (3, 90, 3))).astype(np.float32)
+    _check_direct_vs_oracle(pos, box, 1.5, 1, True)
+    _check_direct_vs_oracle(pos, box, 1.5, 1, False)
+
+
+def test_pair_path_unsupported_and_fallback(balls7):
+    """Dense cells / few cells per axis are refused through the C ABI; the API falls back to the
+    rows path there (r_cut = 15 A in a 30 A box: the reference golden)."""
+    from dynsight_b200 import _lib, engine
+
+    pos = balls7["positions"][:3]
+    box = balls7["dims"][0, :3]
+    assert not engine.lens_direct_supported(3, pos.shape[1], box, 15.0, True)
+    with pytest.raises(_lib.DsgError, match="pair path"):
+        engine.lens_direct(_dev(pos), box, 15.0, 1, True)
+
+
+def test_cfg3_size_two_different_frames_vs_oracle():
+    """BASELINE.json configs[2] at its stated size: 1,000,000 particles, rho* = 0.8, r_cut = 1.5.
+    Three DIFFERENT frames through the public driver (pair path) and through the rows path
+    (neigh_rows_thread_kernel + lens_rows_thread_kernel); LENS and coordination numbers must match
+    the oracle bit for bit (about 10 s of CPU work)."""
+    from dynsight_b200 import engine
+    from dynsight_b200 import lens as dlens
+    from dynsight_b200.universe import ArrayUniverse
+
+    n_side = 100
+    n = n_side**3
+    box_l = np.float32((n / 0.8) ** (1 / 3))
+    rng = np.random.default_rng(3)
+    grid = (np.arange(n_side, dtype=np.float64) + 0.5) * (float(box_l) / n_side)
+    lat = np.stack(np.meshgrid(grid, grid, grid, indexing="ij"), axis=-1).reshape(-1, 3)
+    lat = lat[rng.permutation(n)]
+    cur = lat + rng.normal(0, 0.2, lat.shape)
+    frames = []
+    for _ in range(3):
+        cur = np.mod(cur + rng.normal(0, 0.07, lat.shape), float(box_l))
+        frames.append(np.minimum(cur.astype(np.float32), np.nextafter(box_l, np.float32(0))))
+    pos = np.stack(frames)
+    box = np.full(3, box_l, dtype=np.float32)
+    dims = _dims(box, 3)
+    want = lo.compute_lens_arrays(pos, dims, 1.5, delay=1)
+    want_c = lo.coord_number_arrays(pos, dims, 1.5)
+    assert 0.05 < want.mean() < 0.9  # the frames really differ
+    uni = ArrayUniverse(pos, dims)
+    got = dlens.compute_lens_device(uni, 1.5).cpu().numpy()
+    assert np.array_equal(got, want), "pair path LENS differs at 1M particles"
+    dpos = _dev(pos)
+    _, counts = engine.lens_direct(dpos, box, 1.5, 0, True, want_lens=False)
+    assert np.array_equal(counts.cpu().numpy().T.astype(np.float64), want_c)
+    res, nr = engine.lens_from_positions(dpos, box, 1.5, 1)
+    assert np.array_equal(res.cpu().numpy(), want), "rows path LENS differs at 1M particles"
+    assert np.array_equal(nr.counts.cpu().numpy().T.astype(np.float64), want_c)
+
+
+def test_cfg5_size_lens_vs_oracle():
+    """BASELINE.json configs[4] shape for LENS: 100,000 atoms at water-oxygen density, r_cut = 5 A
+    (k ~ 17.5), three frames of a random walk, pair path and rows path vs the oracle."""
+    from dynsight_b200 import engine
+
+    n = 100_000
+    rng = np.random.default_rng(12)
+    box_l = np.float32((n / 0.0334) ** (1 / 3))
+    cur = rng.random((n, 3)) * float(box_l)
+    frames = []
+    for _ in range(3):
+        cur = np.mod(cur + rng.normal(0, 0.1, cur.shape), float(box_l))
+        frames.append(np.minimum(cur.astype(np.float32), np.nextafter(box_l, np.float32(0))))
+    pos = np.stack(frames)
+    box = np.full(3, box_l, dtype=np.float32)
+    _check_direct_vs_oracle(pos, box, 5.0, 1, True)
+    want = lo.compute_lens_arrays(pos, _dims(box, 3), 5.0, delay=1)
+    res, _ = engine.lens_from_positions(_dev(pos), box, 5.0, 1)
+    assert np.array_equal(res.cpu().numpy(), want)
+
+
+def test_compute_lens_delay_zero_returns_zeros(balls7):
+    """delay = 0 pairs every frame with itself in the reference (lens.py:255-257): zeros."""
+    from dynsight_b200 import lens as dlens
+    from dynsight_b200.universe import ArrayUniverse
+
+    uni = ArrayUniverse(balls7["positions"][:5], balls7["dims"][:5])
+    got = dlens.compute_lens(uni, 10.0, delay=0)
+    assert got.shape == (7, 5)
+    assert not got.any()
