@@ -18,6 +18,7 @@
 // coordinate magnitudes); inside the band the reference's float64 expression is evaluated.
 #include <climits>
 #include <cmath>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -215,14 +216,21 @@ cell_assign_kernel(const T* __restrict__ pos, int n_atoms, FrameParams* __restri
         ay = fmaxf(ay, __shfl_xor_sync(kFull, ay, off));
         az = fmaxf(az, __shfl_xor_sync(kFull, az, off));
     }
-    if ((threadIdx.x & 31) == 0) {
-        // non-negative floats order like their bit patterns; the plain read skips the atomic once
-        // the running maximum is already at least this large (almost always)
-        const unsigned bx = __float_as_uint(ax), by = __float_as_uint(ay), bz = __float_as_uint(az);
-        volatile unsigned* cur = fp[f].amax_bits;
-        if (bx > cur[0]) atomicMax(&fp[f].amax_bits[0], bx);
-        if (by > cur[1]) atomicMax(&fp[f].amax_bits[1], by);
-        if (bz > cur[2]) atomicMax(&fp[f].amax_bits[2], bz);
+    // one RED.MAX per block and axis (non-negative floats order like their bit patterns); no value
+    // is read back, so no thread waits on the atomics
+    __shared__ float red[3][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        red[0][warp] = ax;
+        red[1][warp] = ay;
+        red[2][warp] = az;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float m = red[threadIdx.x][0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[threadIdx.x][w]);
+        atomicMax(&fp[f].amax_bits[threadIdx.x], __float_as_uint(m));
     }
 }
 
@@ -677,7 +685,7 @@ static int make_layout(int n_frames, int n_env, int n_cent, bool same, const dou
     L->off_cell_id_e = take(4 * fe);
     L->off_cnt_e = take(4 * (size_t)total);
     L->off_start_e = take(4 * ((size_t)total + 1));
-    L->off_sorted_e = take(16 * fe);
+    L->off_sorted_e = take(16 * (fe + 4));   // + 4: the pair kernel reads up to 3 slots past a run
     if (!same) {
         L->off_cell_id_c = take(4 * fc);
         L->off_cnt_c = take(4 * (size_t)total);
@@ -1440,11 +1448,11 @@ lens_pair_kernel(const PairArgs a) {
     }
     int own_inter = 0;
     // one hit (my_id, j) of frame t: count it for j and decide membership in frame t + delay
-    auto settle = [&](int j) {
+    auto settle = [&](int j, float xj, float yj, float zj) {
         unsigned long long inc = 1ull;
         if (paired) {
             const T* __restrict__ pj = pos_2 + (size_t)j * 3;
-            float dx = (float)pj[0] - x2, dy = (float)pj[1] - y2, dz = (float)pj[2] - z2;
+            float dx = xj - x2, dy = yj - y2, dz = zj - z2;
             dx = fmaf(-rintf(dx * i2x), b2x, dx);   // i2 = 0 without pbc: the raw difference
             dy = fmaf(-rintf(dy * i2y), b2y, dy);
             dz = fmaf(-rintf(dz * i2z), b2z, dz);
@@ -1469,103 +1477,187 @@ lens_pair_kernel(const PairArgs a) {
         atomicAdd(&acc_f[j], inc);
     };
 
-    int cnt = 0;
-    auto walk = [&](auto&& on_hit) {
-        // candidates of a contiguous run of cells, four loads in flight per step
-        auto scan_run = [&](int qb, int qe, float ox, float oy, float oz) {
-            for (int q0 = qb; q0 < qe; q0 += 4) {
-                float4 cd[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) cd[u] = a.sorted[min(q0 + u, qe - 1)];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int j = __float_as_int(cd[u].w);
-                    const float dx = cd[u].x + ox, dy = cd[u].y + oy, dz = cd[u].z + oz;
-                    const float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
-                    const bool valid = q0 + u < qe;
-                    bool hit = d2 < r2_lo;
-                    if (valid && !hit && !(d2 > r2_hi))   // inside the guard band: rare
-                        hit = exact_test<T>(pos_f + (size_t)j * 3, pos_f + (size_t)my_id * 3,
-                                            p->box, pbc, a.r2);
-                    on_hit(hit && valid, j);
-                }
-            }
-        };
-        // the cells (cx + ddx, cy + ddy, cz - 1 .. cz + 1): one run, or three at the z wrap
-        auto column = [&](int ddx, int ddy) {
+    // The half shell as five columns of cells: c = 0 is my own column (the slots behind mine in my
+    // cell, then the cell above), c = 1 the column (cx, cy + 1), c = 2..4 the columns (cx + 1,
+    // cy - 1 .. cy + 1), each with the cells cz - 1 .. cz + 1.  The z cells of a column are
+    // contiguous in the sorted array: one run per column, or one per cell at the z wrap.  One
+    // call site for everything (the kernel stays small enough for the instruction cache); hits
+    // number base .. base + kPairCap - 1 of the walk go to the staging tile, so a thread with more
+    // hits than the tile holds (rare) walks again with the next base.
+    // Hit number h of a walk goes to stage[h - base][tid]; sp points at the slot of the next hit
+    // (before or beyond the tile = not staged in this pass), so the hit counter and the store
+    // address are one register.
+    constexpr int kSlotBytes = kPairThreads * (int)sizeof(int);
+    // |d2 - mid| <= half  <=  d2 inside the guard band.  mid, half and d2 - mid are each rounded
+    // (an ulp of r2 apiece), so half is widened by 8 ulps of r2_hi: a candidate sent to the
+    // confirmation by mistake is still decided exactly, one that slipped past it would not be.
+    // A useless band (infinite) confirms everything.
+    const bool band_all = !(r2_hi < INFINITY);
+    const float r2_mid = band_all ? 0.f : 0.5f * (r2_lo + r2_hi);
+    const float r2_half =
+        band_all ? INFINITY : 0.5f * (r2_hi - r2_lo) + 8.f * 1.1920929e-7f * r2_hi;
+    char* const tile = reinterpret_cast<char*>(&stage[0][tid]);
+    int cnt = 0, base = 0;
+    do {
+        char* sp = tile - base * kSlotBytes;
+        // run bounds of column c, loaded one column ahead (they feed the candidate loads: two
+        // dependent round trips per column otherwise); only meaningful away from the z wrap
+        auto column_of = [&](int c, int& rowc, float& ox, float& oy) {
+            const int ddx = c >= 2 ? 1 : 0, ddy = c == 0 ? 0 : (c == 1 ? 1 : c - 3);
             const int ax = cx + ddx, ay = cy + ddy;
             const int wx = ax >= nx ? ax - nx : ax;
             const int wy = ay < 0 ? ay + ny : (ay >= ny ? ay - ny : ay);
-            const float ox = (ax >= nx ? bx : 0.f) - me.x;
-            const float oy = (ay < 0 ? -by : (ay >= ny ? by : 0.f)) - me.y;
-            const int rowc = base_cell + (wx * ny + wy) * nz;
-            if (cz >= 1 && cz <= nz - 2) {
-                scan_run(a.cell_start[rowc + cz - 1], a.cell_start[rowc + cz + 2], ox, oy, -me.z);
-            } else {
-                for (int ddz = -1; ddz <= 1; ++ddz) {
-                    const int az = cz + ddz;
-                    const int wz = az < 0 ? az + nz : (az >= nz ? az - nz : az);
-                    const float oz = (az < 0 ? -bz : (az >= nz ? bz : 0.f)) - me.z;
-                    scan_run(a.cell_start[rowc + wz], a.cell_start[rowc + wz + 1], ox, oy, oz);
+            ox = (ax >= nx ? bx : 0.f) - me.x;
+            oy = (ay < 0 ? -by : (ay >= ny ? by : 0.f)) - me.y;
+            rowc = base_cell + (wx * ny + wy) * nz;
+        };
+        const bool z_mid = cz >= 1 && cz + 1 < nz;   // every column is one run
+        int rowc_n, qb_n = 0, qe_n = 0;
+        float ox_n, oy_n;
+        column_of(0, rowc_n, ox_n, oy_n);
+        if (z_mid) {
+            qb_n = a.cell_start[rowc_n + cz];
+            qe_n = a.cell_start[rowc_n + cz + 2];
+        }
+#pragma unroll 1
+        for (int c = 0; c < 5; ++c) {
+            const int rowc = rowc_n, qb_pre = qb_n, qe_pre = qe_n;
+            const float ox = ox_n, oy = oy_n;
+            if (c < 4) {
+                column_of(c + 1, rowc_n, ox_n, oy_n);
+                if (z_mid) {
+                    qb_n = a.cell_start[rowc_n + cz - 1];
+                    qe_n = a.cell_start[rowc_n + cz + 2];
                 }
             }
-        };
-        // own column: the slots behind mine in my cell, then the cell above
-        const int col = base_cell + (cx * ny + cy) * nz;
-        if (cz + 1 < nz) {
-            scan_run((int)slot + 1, a.cell_start[col + cz + 2], -me.x, -me.y, -me.z);
-        } else {
-            scan_run((int)slot + 1, a.cell_start[col + cz + 1], -me.x, -me.y, -me.z);
-            scan_run(a.cell_start[col], a.cell_start[col + 1], -me.x, -me.y, bz - me.z);
+            const int z_lo = c == 0 ? cz : cz - 1, z_hi = cz + 1;
+            const bool one_run = z_lo >= 0 && z_hi < nz;
+            const int n_seg = one_run ? 1 : z_hi - z_lo + 1;
+#pragma unroll 1
+            for (int sg = 0; sg < n_seg; ++sg) {
+                int qb, qe;
+                float oz = -me.z;
+                if (z_mid) {
+                    qb = qb_pre;
+                    qe = qe_pre;
+                } else if (one_run) {
+                    qb = a.cell_start[rowc + z_lo];
+                    qe = a.cell_start[rowc + z_hi + 1];
+                } else {
+                    const int az = z_lo + sg;
+                    const int wz = az < 0 ? az + nz : (az >= nz ? az - nz : az);
+                    oz += az < 0 ? -bz : (az >= nz ? bz : 0.f);
+                    qb = a.cell_start[rowc + wz];
+                    qe = a.cell_start[rowc + wz + 1];
+                }
+                if (c == 0 && sg == 0) qb = (int)slot + 1;   // my own cell: only the slots behind me
+                // Four candidates per step.  The last step of a run reads up to three slots past
+                // it (the next cells; the sorted array is padded at its end) and masks them out.
+                // A run whose candidates all fit behind the hits staged so far needs no bounds
+                // check on the tile (CHECKED = false: almost always).
+                auto scan = [&](auto checked) {
+                    constexpr bool CHECKED = decltype(checked)::value;
+                    auto put = [&](bool hit, float w) {
+                        const bool room =
+                            !CHECKED || (unsigned)(sp - tile) < (unsigned)(kPairCap * kSlotBytes);
+                        if (hit && room) *reinterpret_cast<int*>(sp) = __float_as_int(w);
+                        if (hit) sp += kSlotBytes;
+                    };
+                    for (int q0 = qb; q0 < qe; q0 += 4) {
+                        const float4* __restrict__ cp = a.sorted + q0;
+                        float4 cd[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) cd[u] = cp[u];
+                        const int n_valid = qe - q0;
+                        float d2[4];
+                        bool band = false;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float dx = cd[u].x + ox, dy = cd[u].y + oy, dz = cd[u].z + oz;
+                            d2[u] = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+                            band = band || fabsf(d2[u] - r2_mid) <= r2_half;
+                            // j is never my_id (my own slot is in no run): lens.py:104 by construction
+                            put(d2[u] < r2_lo && u < n_valid, cd[u].w);
+                        }
+                        if (band) {   // a candidate of the step sits inside the guard band: rare
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (!(d2[u] < r2_lo) && !(d2[u] > r2_hi) && u < n_valid &&
+                                    exact_test<T>(pos_f + (size_t)__float_as_int(cd[u].w) * 3,
+                                                  pos_f + (size_t)my_id * 3, p->box, pbc, a.r2))
+                                    put(true, cd[u].w);
+                            }
+                        }
+                    }
+                };
+                const int soff = (int)(sp - tile);
+                if (soff >= 0 && soff + (qe - qb) * kSlotBytes <= kPairCap * kSlotBytes)
+                    scan(std::false_type{});
+                else
+                    scan(std::true_type{});
+            }
         }
-        column(0, 1);
-        column(1, -1);
-        column(1, 0);
-        column(1, 1);
-    };
-    // j is never my_id here (my own slot is not part of any run): lens.py:104 holds by construction
-    walk([&](bool hit, int j) {
-        if (hit) stage[min(cnt, kPairCap - 1)][tid] = j;   // branch-free staging
-        cnt += hit ? 1 : 0;
-    });
-    if (cnt <= kPairCap) {
-        for (int h = 0; h < cnt; ++h) settle(stage[h][tid]);
-    } else {   // more hits than the tile holds (rare): walk again and settle each hit at once
-        cnt = 0;
-        walk([&](bool hit, int j) {
-            if (hit) settle(j);
-            cnt += hit ? 1 : 0;
-        });
-    }
+        cnt = (int)(sp - tile) / kSlotBytes + base;
+        const int n_stage = min(cnt - base, kPairCap);
+        // four hits per step: their partner-frame coordinates are gathered together
+#pragma unroll 1
+        for (int h0 = 0; h0 < n_stage; h0 += 4) {
+            int jj[4];
+            float px[4], py[4], pz[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                jj[u] = stage[min(h0 + u, n_stage - 1)][tid];
+                if (paired) {
+                    const T* __restrict__ pj = pos_2 + (size_t)jj[u] * 3;
+                    px[u] = (float)pj[0];
+                    py[u] = (float)pj[1];
+                    pz[u] = (float)pj[2];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (h0 + u < n_stage) settle(jj[u], px[u], py[u], pz[u]);
+        }
+        base += kPairCap;
+    } while (base < cnt);
     atomicAdd(&acc_f[my_id], (unsigned long long)cnt | ((unsigned long long)own_inter << 32));
 }
 
-// acc -> counts (F, N) int32 and LENS (N, n_pairs) float64 (transposed through shared memory)
-__global__ void __launch_bounds__(1024)
+// acc -> counts (F, N) int32 and LENS (N, n_pairs) float64.  One thread owns one atom and a run
+// of eight consecutive frames: the 64-bit words of a frame are read coalesced across the atoms of
+// a warp, and every thread writes its eight results as one contiguous 64-byte piece of its output
+// row (two full sectors) -- no shared-memory transpose, no barrier.
+constexpr int kFinRun = 8;
+__global__ void __launch_bounds__(256)
 pair_finalize_kernel(const unsigned long long* __restrict__ acc, int n_frames, int n_atoms,
                      int delay, int* __restrict__ counts, double* __restrict__ lens,
                      long long ld, long long col0) {
-    __shared__ double tile[32][33];
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int i0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
-    {
-        const int t = t0 + ty, i = i0 + tx;
-        double v = 0.0;
-        if (t < n_frames && i < n_atoms) {
-            const unsigned long long w = acc[(size_t)t * n_atoms + i];
-            const int ca = (int)(unsigned)(w & 0xffffffffull);
-            if (counts) counts[(size_t)t * n_atoms + i] = ca;
-            if (lens && delay > 0 && t + delay < n_frames) {
-                const int cb = (int)(unsigned)(acc[(size_t)(t + delay) * n_atoms + i] & 0xffffffffull);
-                v = lens_value(ca, cb, (int)(unsigned)(w >> 32));
-            }
-        }
-        tile[ty][tx] = v;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t0 = blockIdx.y * kFinRun;
+    if (i >= n_atoms) return;
+    const bool with_lens = lens != nullptr && delay > 0;
+    unsigned long long w[kFinRun];
+#pragma unroll
+    for (int k = 0; k < kFinRun; ++k)
+        w[k] = t0 + k < n_frames ? acc[(size_t)(t0 + k) * n_atoms + i] : 0ull;
+    if (counts) {
+#pragma unroll
+        for (int k = 0; k < kFinRun; ++k)
+            if (t0 + k < n_frames) counts[(size_t)(t0 + k) * n_atoms + i] = (int)(unsigned)w[k];
     }
-    __syncthreads();
-    const int t = t0 + tx, i = i0 + ty;
-    if (lens && delay > 0 && t + delay < n_frames && i < n_atoms)
-        lens[(long long)i * ld + col0 + t] = tile[tx][ty];
+    if (!with_lens) return;
+    double* __restrict__ row = lens + (long long)i * ld + col0;
+#pragma unroll
+    for (int k = 0; k < kFinRun; ++k) {
+        const int t = t0 + k;
+        if (t + delay < n_frames) {
+            // the partner word is one of mine when the delay is shorter than the run
+            const unsigned long long w2 = (k + delay < kFinRun && delay < kFinRun)
+                                              ? w[(k + delay) & (kFinRun - 1)]
+                                              : acc[(size_t)(t + delay) * n_atoms + i];
+            row[t] = lens_value((int)(unsigned)w[k], (int)(unsigned)w2, (int)(unsigned)(w[k] >> 32));
+        }
+    }
 }
 
 // The pair path applies when one thread per atom is the right granularity (sparse cells, short
@@ -1668,9 +1760,9 @@ static int lens_direct_impl(const void* d_pos, int n_frames, int n_atoms, const 
     dim3 pgrid((n_atoms + kPairThreads - 1) / kPairThreads, n_frames);
     lens_pair_kernel<T><<<pgrid, kPairThreads, 0, st>>>(a);
     DSG_LAUNCH_CHECK("lens_pair_kernel");
-    dim3 fgrid((n_atoms + 31) / 32, (n_frames + 31) / 32);
-    pair_finalize_kernel<<<fgrid, dim3(32, 32), 0, st>>>(acc, n_frames, n_atoms, a.delay, d_counts,
-                                                         d_lens, lens_stride, col0);
+    dim3 fgrid((n_atoms + 255) / 256, (n_frames + kFinRun - 1) / kFinRun);
+    pair_finalize_kernel<<<fgrid, 256, 0, st>>>(acc, n_frames, n_atoms, a.delay, d_counts, d_lens,
+                                                lens_stride, col0);
     DSG_LAUNCH_CHECK("pair_finalize_kernel");
     return DSG_OK;
 }

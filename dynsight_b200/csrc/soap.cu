@@ -56,16 +56,16 @@ constexpr int kOpenCellsPerAxis = 32;
 #define DSG_SOAP_LIST 1            // neighbour rows from soap_list_kernel where the frames allow it
 #endif
 #ifndef DSG_SOAP_LIST_WARPS
-#define DSG_SOAP_LIST_WARPS 2      // warps per block of the list-mode kernel ...
+#define DSG_SOAP_LIST_WARPS 4      // warps per block of the list-mode kernel ...
 #endif
 #ifndef DSG_SOAP_LIST_BLOCKS
-#define DSG_SOAP_LIST_BLOCKS 6     // ... and its resident blocks per SM
+#define DSG_SOAP_LIST_BLOCKS 4     // ... and its resident blocks per SM (128 registers)
 #endif
 #ifndef DSG_SOAP_TILE_SPECTRUM
 #define DSG_SOAP_TILE_SPECTRUM 1   // fused epilogue: 2x2 register tiles for n_max = 8
 #endif
-#ifndef DSG_SOAP_EXP_HORNER
-#define DSG_SOAP_EXP_HORNER 0      // Horner instead of Estrin in exp_scaled
+#ifndef DSG_SOAP_EXP_ESTRIN
+#define DSG_SOAP_EXP_ESTRIN 0      // Estrin instead of Horner in exp_scaled (two more operations)
 #endif
 #ifndef DSG_SOAP_KO_HALFLOADS
 #define DSG_SOAP_KO_HALFLOADS 0    // timing probe: half of the harmonics loads of phase C (wrong results)
@@ -119,7 +119,7 @@ struct SoapArgs {
     double r2max;
     const double* gamma;    // (L+1, n)
     const double* bmat;     // (L+1, n, n)  beta * prefactor
-    const double* exp_tab;  // (64) 2^(j/64)
+    const double* exp_tab;  // (kExpTab) 2^(j/32)
     int bmat_smem_doubles;  // size of bmat if it is staged in shared memory, else 0
     int epi_smem_doubles;   // fused epilogue tables (swlm, lm_l, decode) in shared memory
     const double* swlm;     // (n_lm)  sqrt of the m-contraction weights
@@ -347,44 +347,53 @@ struct Acc {
     double v[N > 0 ? N : 1];
 };
 
-// exp(x) for x in [-690, 0], argument given pre-scaled: t = x * 16 log2(e).  2^n * 2^(j/16) * e^u
-// with 16 n + j = rint(t); 2^(j/16) from a shared-memory table, e^u by a degree-6 Taylor
-// polynomial in v = t - rint(t) (coefficients (ln2/16)^i / i! folded in; |u| <= ln2/32,
-// truncation 4.5e-16).  Relative error < 1e-15 + the rounding of t (<= 1e-14 for |x| < 100).
-// Branch-free, 13 fp64 operations.  16 entries * 8 bytes = one 128-byte row of shared memory:
-// every entry has its own bank pair, so the divergent table reads of a warp are conflict-free.
+// exp(x) for x in [-690, 0], argument given pre-scaled: t = x * 32 log2(e).  2^n * 2^(j/32) * e^u
+// with 32 n + j = rint(t); 2^(j/32) from a shared-memory table, e^u by a degree-5 Taylor
+// polynomial in v = t - rint(t) (coefficients (ln2/32)^i / i! folded in; |u| <= ln2/64,
+// truncation 2.2e-15).  Relative error < 5e-15.  Branch-free, 8 fp64 operations: the kernel is
+// issue-bound and an fp64 instruction holds the issue port for two cycles (DESIGN.md section
+// 3.4), so the exponential is built for the fewest instructions, not the shortest chain: Horner
+// with the coefficients read as constant-bank operands (no register or move is spent on them;
+// the literal constants of the former degree-6 Estrin form were re-materialised by 12 moves per
+// neighbour) and a 32-entry table instead of 16 (entries j and j + 16 share a bank: at worst a
+// two-way conflict on a load pipe that has slack).
 // The caller guarantees t >= -690 * kExpScale (2^n stays normal): soap_layout rejects cutoffs
 // for which gamma * r^2 could exceed 690.
-constexpr int kExpTab = 16;
-constexpr double kExpScale = 23.083120654223414;  // 16 * log2(e)
+constexpr int kExpTab = 32;
+constexpr int kExpTabLog2 = 5;
+constexpr double kExpScale = 46.166241308446828;  // 32 * log2(e)
+__constant__ double kExpPoly[5] = {
+    2.16608493924982901946e-02,   // (ln2/32)^1 / 1!
+    2.34596198202246771555e-04,   // (ln2/32)^2 / 2!
+    1.69385097243718189026e-06,   // (ln2/32)^3 / 3!
+    9.17256270182464301942e-09,   // (ln2/32)^4 / 4!
+    3.97370998454941544405e-11,   // (ln2/32)^5 / 5!
+};
 // g = gamma * kExpScale (negative), s = r^2.  The product enters only through two FMAs: rint(g s)
 // by the magic-constant trick and the remainder v = g s - rint(g s) with a single rounding, so
 // the argument is never rounded to float64 (one operation fewer and v exact to 1e-17).
 __device__ __forceinline__ double exp_scaled(double g, double s, const double* __restrict__ tab) {
     const double magic = 6755399441055744.0;                     // 1.5 * 2^52
     const double tn = fma(g, s, magic);
-    const int kq = __double2loint(tn);                           // 16 n + j
+    const int kq = __double2loint(tn);                           // 32 n + j
     const double v = fma(g, s, magic - tn);                      // [-1/2, 1/2]
-#if DSG_SOAP_EXP_HORNER
-    double p = fma(9.18121957384443806176e-12, v, 1.27158719505581314889e-09);
-    p = fma(p, v, 1.46761003229194288311e-07);
-    p = fma(p, v, 1.35508077794974568162e-05);
-    p = fma(p, v, 9.38384792808987194639e-04);
-    p = fma(p, v, 4.33216987849965803892e-02);
-    p = fma(p, v, 1.0);
-#else
-    // Estrin scheme: two more operations than Horner, dependency depth 4 instead of 6
+#if DSG_SOAP_EXP_ESTRIN   // 7 operations at depth 3 instead of 5 at depth 5
     const double v2 = v * v;
-    const double t0 = fma(4.33216987849965803892e-02, v, 1.0);
-    const double t1 = fma(1.35508077794974568162e-05, v, 9.38384792808987194639e-04);
-    double t2 = fma(1.27158719505581314889e-09, v, 1.46761003229194288311e-07);
-    t2 = fma(9.18121957384443806176e-12, v2, t2);
+    const double t0 = fma(kExpPoly[0], v, 1.0);
+    const double t1 = fma(kExpPoly[2], v, kExpPoly[1]);
+    const double t2 = fma(kExpPoly[4], v, kExpPoly[3]);
     const double v4 = v2 * v2;
     double p = fma(t1, v2, t0);
     p = fma(t2, v4, p);
+#else
+    double p = fma(kExpPoly[4], v, kExpPoly[3]);
+    p = fma(p, v, kExpPoly[2]);
+    p = fma(p, v, kExpPoly[1]);
+    p = fma(p, v, kExpPoly[0]);
+    p = fma(p, v, 1.0);
 #endif
     const double r = tab[kq & (kExpTab - 1)] * p;
-    return __hiloint2double(__double2hiint(r) + ((kq >> 4) << 20), __double2loint(r));
+    return __hiloint2double(__double2hiint(r) + ((kq >> kExpTabLog2) << 20), __double2loint(r));
 }
 
 // Layout of one neighbour's harmonics row: the block of angular momentum l (2l+1 values, padded
@@ -682,10 +691,9 @@ __device__ __forceinline__ void mix_and_spectrum(const SoapArgs& a, const double
 // soap_spectrum_kernel finishes the centres.  No per-warp coefficient buffer is needed, so the
 // occupancy is the single-species one whatever the number of species.
 // List mode needs neither the prefetch registers nor the batch tables of the in-kernel search, so
-// it also fits 4 blocks of 4 warps per SM at 128 registers (DSG_SOAP_LIST_WARPS=4,
-// DSG_SOAP_LIST_BLOCKS=4).  Measured on the 100 000-atom box: 4.30e7 centre-frames/s for 4 x 4
-// against 4.38e7 for 6 x 2 at 168 registers -- the tighter register budget costs the schedule what
-// the four extra warps bring, so the default stays 6 x 2.
+// it also fits 4 blocks of 4 warps per SM at 128 registers.  With the 8-operation exponential
+// (round 2) that is the faster shape: 4.68e7 centre-frames/s for 4 x 4 against 4.52e7 for 6 x 2 at
+// 168 registers on the 100 000-atom box (round 1, 13-operation exponential: 4.30e7 vs 4.38e7).
 constexpr int kListWarps = DSG_SOAP_LIST_WARPS;
 template <int LT, int S0, int S1, int S2, int S3, bool SPLIT, bool LIST>
 __global__ void __launch_bounds__(
@@ -699,7 +707,7 @@ soap_kernel(const SoapArgs a) {
     extern __shared__ __align__(16) double smem_all[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warps = blockDim.x >> 5;
-    // block-wide tables: 2^(j/16) and (if small enough) the Loewdin matrices
+    // block-wide tables: 2^(j/32) and (if small enough) the Loewdin matrices
     double* exp_tab = smem_all;
     double* bmat_s = smem_all + kExpTab;
     const int bmat_stage = SPLIT ? 0 : a.bmat_smem_doubles;
@@ -819,7 +827,9 @@ soap_kernel(const SoapArgs a) {
 #pragma unroll kUnrollC
                 for (int jj = 0; jj < nh; ++jj) {   // phase C
                     const double r2 = r2_next;
-                    r2_next = nbuf[(h0 + min(jj + 1, nh - 1)) * 4 + 3];
+                    // the entry behind the last neighbour is read too and never used (at worst
+                    // nbuf[32]: the first words of this warp's cell table) -- no clamp in the loop
+                    r2_next = nbuf[(h0 + jj + 1) * 4 + 3];
                     const double* __restrict__ rt = rbuf + jj * P;
                     if constexpr (PK) {
                         const double e0 = exp_scaled(gam[0], r2, exp_tab);
@@ -1423,7 +1433,7 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     DSG_CUDA_CHECK(cudaMemcpyAsync(d_frames, frames.data(), sizeof(SoapFrame) * n_frames,
                                    cudaMemcpyHostToDevice, st));
     double exp_tab[kExpTab];
-    for (int j = 0; j < kExpTab; ++j) exp_tab[j] = std::exp2((double)j / kExpTab);  // 2^(j/16)
+    for (int j = 0; j < kExpTab; ++j) exp_tab[j] = std::exp2((double)j / kExpTab);  // 2^(j/32)
     DSG_CUDA_CHECK(cudaMemcpyAsync(ws + L.off_exptab, exp_tab, sizeof(exp_tab),
                                    cudaMemcpyHostToDevice, st));
 

@@ -36,12 +36,22 @@ def _device_csr(neigh_list_per_frame: Any, n_atoms: int) -> engine.NeighborBatch
     dev = frames.device()
     if isinstance(neigh_list_per_frame, NeighbourList):
         nb = neigh_list_per_frame.device_batch()  # stays on the device: no host round trip
-        if nb.n_cent != n_atoms:
+        cent = neigh_list_per_frame.centre_indices
+        if nb.n_cent != n_atoms or (cent is not None and not np.array_equal(cent, np.arange(n_atoms))):
             msg = "the neighbour list must hold one entry per atom of the universe (centers='all')"
             raise ValueError(msg)
-        if nb.indices.numel() == 0:
-            nb = engine.NeighborBatch(nb.counts, nb.indptr, nb.frame_off,
-                                      torch.zeros(1, dtype=torch.int32, device=dev), nb.n_frames,
+        indices = nb.indices
+        env = neigh_list_per_frame.env_indices
+        if env is not None and indices.numel() and not (
+            env.size == n_atoms and np.array_equal(env, np.arange(n_atoms))
+        ):
+            # rows hold positions inside the environment selection; the reference reads
+            # ``neigh[t][i].indices`` = universe indices (misc.py:60-66, 180-190)
+            indices = torch.as_tensor(env.astype(np.int32), device=dev)[indices.long()]
+        if indices.numel() == 0:
+            indices = torch.zeros(1, dtype=torch.int32, device=dev)
+        if indices is not nb.indices:
+            nb = engine.NeighborBatch(nb.counts, nb.indptr, nb.frame_off, indices, nb.n_frames,
                                       nb.n_cent)  # fmt: skip
         return nb
     rows = [[np.asarray(ag.indices, dtype=np.int32) for ag in fr] for fr in neigh_list_per_frame]

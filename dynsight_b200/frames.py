@@ -212,3 +212,39 @@ def to_host(t: torch.Tensor) -> np.ndarray:
         torch.cuda.current_stream(t.device).synchronize()
         return host.numpy()
     return t.cpu().numpy()
+
+
+class PendingHostCopy:
+    """A device -> host copy in flight on the side stream (:func:`to_host_async`)."""
+
+    def __init__(self, host: torch.Tensor | None, done: torch.cuda.Event | None,
+                 fallback: torch.Tensor | None = None) -> None:  # fmt: skip
+        self._host, self._done, self._fallback = host, done, fallback
+
+    def result(self) -> np.ndarray:
+        if self._host is None:
+            return to_host(self._fallback)
+        self._done.synchronize()
+        return self._host.numpy()
+
+
+def to_host_async(t: torch.Tensor) -> PendingHostCopy:
+    """Start copying a device result to page-locked host memory on the copy stream, behind the
+    work already enqueued on the current stream; ``result()`` waits for the copy only."""
+    n_bytes = t.numel() * t.element_size()
+    if t.device.type != "cuda" or not 0 < n_bytes <= _PINNED_RESULT_LIMIT:
+        return PendingHostCopy(None, None, t)
+    try:
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    except RuntimeError:
+        return PendingHostCopy(None, None, t)
+    side = _copy_stream(t.device)
+    ready = torch.cuda.Event()
+    ready.record(torch.cuda.current_stream(t.device))
+    with torch.cuda.stream(side):
+        side.wait_event(ready)
+        host.copy_(t, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(side)
+    t.record_stream(side)
+    return PendingHostCopy(host, done)

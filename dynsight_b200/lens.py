@@ -19,12 +19,119 @@ from dynsight_b200 import engine, frames
 if TYPE_CHECKING:
     from numpy.typing import NDArray
 
-__all__ = ["compute_lens", "compute_lens_device", "list_neighbours_along_trajectory"]
+__all__ = ["LensJob", "compute_lens", "compute_lens_device", "list_neighbours_along_trajectory"]
 
 
 def _mean_neighbours_estimate(n_env: int, box: np.ndarray, r_cut: float) -> float:
     vol = float(np.prod(np.maximum(box[0], 1e-12)))
     return min(float(n_env), n_env / vol * 4.18879 * float(r_cut) ** 3)
+
+
+class LensJob:
+    """LENS (and, on request, coordination numbers) of a trajectory, fed one device batch at a
+    time: ``job.process(fb)`` for every batch of ``frames.iter_batches(..., overlap=delay)``, then
+    ``job.finish()``.  ``compute_lens_device`` runs it alone; ``pipeline.descriptors_from_trajectory``
+    feeds the same batches to the SOAP / timeSOAP job as well (one ingest for all descriptors)."""
+
+    def __init__(self, universe: Any, r_cut: float, delay: int = 1, centers: str = "all",
+                 selection: str = "all", trajslice: slice | None = None, respect_pbc: bool = True,
+                 want_counts: bool = False) -> None:  # fmt: skip
+        ag_env = universe.select_atoms(selection)
+        ag_cent = universe.select_atoms(centers)
+        self.universe = universe
+        self.r_cut, self.delay, self.respect_pbc = r_cut, delay, respect_pbc
+        self.fr_idx = frames.frame_sequence(universe.trajectory.n_frames, trajslice)
+        n_pairs = len(self.fr_idx) - delay
+        if delay < 0 or n_pairs < 1:  # "pairs" would be empty (lens.py:255-260)
+            msg = "No valid pairs found."
+            raise RuntimeError(msg)
+        self.n_all = len(universe.atoms)
+        self.ix_env = np.asarray(ag_env.indices)
+        self.ix_cent = np.asarray(ag_cent.indices)
+        self.same = self.ix_env.shape == self.ix_cent.shape and bool(
+            np.array_equal(self.ix_env, self.ix_cent)
+        )
+        dev = frames.device()
+        self.out = torch.empty((self.ix_cent.size, n_pairs), dtype=torch.float64, device=dev)
+        self.counts_out = (
+            torch.zeros((self.ix_cent.size, len(self.fr_idx)), dtype=torch.float64, device=dev)
+            if want_counts else None
+        )  # fmt: skip
+        # no centres: empty result; no environment atoms: every row is empty and
+        # lens_from_two_csr returns 0.0 for a + b == 0 (lens.py:171-173); delay = 0 pairs every
+        # frame with itself (lens.py:255-257): identical lists, LENS = 0.0 everywhere
+        self.trivial = self.ix_cent.size == 0 or self.ix_env.size == 0 or delay == 0
+        if self.trivial:
+            self.out.zero_()
+        self.sel_env = frames.Selection(self.ix_env, self.n_all)
+        self.sel_cent = frames.Selection(self.ix_cent, self.n_all)
+        self._pending: tuple | None = None
+
+    @property
+    def needs_batches(self) -> bool:
+        return not self.trivial or (self.counts_out is not None and self.ix_cent.size > 0
+                                    and self.ix_env.size > 0)  # fmt: skip
+
+    def default_batch_frames(self) -> int:
+        """Frames per batch from a 4 GB budget.  Rows path: 1.3 k int32 row entries + counts / row
+        starts / cell-sorted copies per atom-frame (k from the density of the first frame); the
+        pair path needs 44 B."""
+        host, dims = frames._load_host(self.universe, self.fr_idx[:1])  # noqa: SLF001
+        box0 = (dims[:, :3].astype(np.float64) if dims is not None else
+                (host.amax(dim=1) - host.amin(dim=1)).numpy().astype(np.float64) * 1.01)  # fmt: skip
+        k_est = _mean_neighbours_estimate(max(1, self.ix_env.size), box0, self.r_cut)
+        return frames.pick_batch_frames(max(self.ix_env.size, self.ix_cent.size, 1),
+                                        60.0 + 5.2 * k_est, self.delay + 1)  # fmt: skip
+
+    def _settle(self) -> None:
+        """The one host sync per rows-path batch: a reservation overflow (rare) reruns it."""
+        job, self._pending = self._pending, None
+        if job is None:
+            return
+        fb, box, pos_env, pos_cent, nr = job
+        if nr.overflowed():
+            warp = nr.needs_warp_kernel()
+            _, nr2 = engine.lens_from_positions(
+                pos_env, box, self.r_cut, max(self.delay, 1), pos_cent, self.respect_pbc,
+                out=self.out if not self.trivial else None, col0=fb.seq0,
+                capacity=None if warp else engine._next_capacity(nr, None),  # noqa: SLF001
+                force_warp=warp,
+            )
+            if self.counts_out is not None:
+                engine.coordination_numbers(nr2.counts, out=self.counts_out, col0=fb.seq0)
+
+    def process(self, fb: frames.FrameBatch) -> None:
+        """Enqueue the kernels of one batch.  The status of a rows-path batch is read only after
+        the kernels of the next one are enqueued (software pipeline, one sync per batch)."""
+        if not self.needs_batches:
+            return
+        n_fb = len(fb.frames)
+        with_lens = not self.trivial and n_fb > self.delay
+        box = frames.lens_boxes(fb, 1.01)
+        pos_env = fb.select(self.sel_env, self.n_all)
+        if self.same and engine.lens_direct_supported(n_fb, pos_env.shape[1], box, self.r_cut,
+                                                      self.respect_pbc):  # fmt: skip
+            # centres == environment, sparse cells: pair path, no lists and nothing to retry
+            _, counts = engine.lens_direct(
+                pos_env, box, self.r_cut, self.delay, self.respect_pbc, out=self.out,
+                col0=fb.seq0, want_lens=with_lens, want_counts=self.counts_out is not None,
+            )
+            if counts is not None:
+                engine.coordination_numbers(counts, out=self.counts_out, col0=fb.seq0)
+            self._settle()
+            return
+        pos_cent = None if self.same else fb.select(self.sel_cent, self.n_all)
+        nr = engine.neighbor_rows(pos_env, box, self.r_cut, pos_cent, self.respect_pbc)
+        if with_lens:
+            engine.lens_pairs_rows(nr, self.delay, out=self.out, col0=fb.seq0)
+        if self.counts_out is not None:
+            engine.coordination_numbers(nr.counts, out=self.counts_out, col0=fb.seq0)
+        self._settle()
+        self._pending = (fb, box, pos_env, pos_cent, nr)
+
+    def finish(self) -> torch.Tensor:
+        self._settle()
+        return self.out
 
 
 def compute_lens_device(
@@ -38,72 +145,15 @@ def compute_lens_device(
     batch_frames: int | None = None,
 ) -> torch.Tensor:
     """:func:`compute_lens` that leaves the (n_centers, n_pairs) float64 result on the device."""
-    ag_env = universe.select_atoms(selection)
-    ag_cent = universe.select_atoms(centers)
-    fr_idx = frames.frame_sequence(universe.trajectory.n_frames, trajslice)
-    n_pairs = len(fr_idx) - delay
-    if delay < 0 or n_pairs < 1:  # "pairs" would be empty (lens.py:255-260)
-        msg = "No valid pairs found."
-        raise RuntimeError(msg)
-    n_all = len(universe.atoms)
-    ix_env = np.asarray(ag_env.indices)
-    ix_cent = np.asarray(ag_cent.indices)
-    same = ix_env.shape == ix_cent.shape and bool(np.array_equal(ix_env, ix_cent))
-    dev = frames.device()
-    out = torch.empty((ix_cent.size, n_pairs), dtype=torch.float64, device=dev)
-    if ix_cent.size == 0 or ix_env.size == 0 or delay == 0:
-        # no centres: empty result; no environment atoms: every row is empty and
-        # lens_from_two_csr returns 0.0 for a + b == 0 (lens.py:171-173); delay = 0 pairs every
-        # frame with itself (lens.py:255-257): identical lists, LENS = 0.0 everywhere
-        return out.zero_()
-    k_est = 0.0
+    job = LensJob(universe, r_cut, delay, centers, selection, trajslice, respect_pbc)
+    if not job.needs_batches:
+        return job.out
     if batch_frames is None:
-        # rows path: 1.3 k int32 row entries + counts / row starts / cell-sorted copies per
-        # atom-frame; the pair path needs 44 B.  k from the density of the first frame.
-        host, dims = frames._load_host(universe, fr_idx[:1])  # noqa: SLF001
-        box0 = (dims[:, :3].astype(np.float64) if dims is not None else
-                (host.amax(dim=1) - host.amin(dim=1)).numpy().astype(np.float64) * 1.01)  # fmt: skip
-        k_est = _mean_neighbours_estimate(ix_env.size, box0, r_cut)
-        batch_frames = frames.pick_batch_frames(max(ix_env.size, ix_cent.size),
-                                                60.0 + 5.2 * k_est, delay + 1)  # fmt: skip
+        batch_frames = job.default_batch_frames()
     batch_frames = max(batch_frames, delay + 1)
-
-    def settle(job: tuple | None) -> None:
-        """The one host sync per batch: a reservation overflow (rare) reruns that batch."""
-        if job is None:
-            return
-        fb, box, pos_env, pos_cent, nr = job
-        if nr.overflowed():
-            warp = nr.needs_warp_kernel()
-            engine.lens_from_positions(
-                pos_env, box, r_cut, delay, pos_cent, respect_pbc, out=out, col0=fb.seq0,
-                capacity=None if warp else engine._next_capacity(nr, None),  # noqa: SLF001
-                force_warp=warp,
-            )
-
-    # Software pipeline over batches: asking the iterator for batch k issues its host -> device
-    # copy on the side stream while the kernels of batch k-1 (already enqueued) run; the status
-    # of batch k-1 is read only after the kernels of batch k are enqueued.
-    pending = None
-    sel_env, sel_cent = frames.Selection(ix_env, n_all), frames.Selection(ix_cent, n_all)
-    for fb in frames.iter_batches(universe, fr_idx, batch_frames, overlap=delay):
-        box = frames.lens_boxes(fb, 1.01)
-        pos_env = fb.select(sel_env, n_all)
-        if same and engine.lens_direct_supported(pos_env.shape[0], pos_env.shape[1], box, r_cut,
-                                                 respect_pbc):  # fmt: skip
-            # centres == environment, sparse cells: pair path, no lists and nothing to retry
-            engine.lens_direct(pos_env, box, r_cut, delay, respect_pbc, out=out, col0=fb.seq0,
-                               want_counts=False)  # fmt: skip
-            settle(pending)
-            pending = None
-            continue
-        pos_cent = None if same else fb.select(sel_cent, n_all)
-        nr = engine.neighbor_rows(pos_env, box, r_cut, pos_cent, respect_pbc)
-        engine.lens_pairs_rows(nr, delay, out=out, col0=fb.seq0)
-        settle(pending)
-        pending = (fb, box, pos_env, pos_cent, nr)
-    settle(pending)
-    return out
+    for fb in frames.iter_batches(universe, job.fr_idx, batch_frames, overlap=delay):
+        job.process(fb)
+    return job.finish()
 
 
 def compute_lens(
@@ -169,9 +219,15 @@ class NeighbourList(Sequence):
     is accessed.
     """
 
-    def __init__(self, ag_env: Any, counts: torch.Tensor,
-                 build_csr: Any) -> None:  # fmt: skip
+    def __init__(self, ag_env: Any, counts: torch.Tensor, build_csr: Any,
+                 env_indices: np.ndarray | None = None, centre_indices: np.ndarray | None = None,
+                 ) -> None:  # fmt: skip
         self._ag_env = ag_env
+        # universe indices of the environment / centre atoms: the CSR ``indices`` are positions
+        # inside ``ag_env`` (what the numba kernel returns), consumers that index the universe's
+        # arrays (psi / phi kernels) translate through these
+        self.env_indices = env_indices
+        self.centre_indices = centre_indices
         self.counts_device = counts  # (F, M) int32 CUDA
         self._build_csr = build_csr  # () -> engine.NeighborBatch covering all frames (device)
         self._batch: engine.NeighborBatch | None = None
@@ -289,7 +345,7 @@ def list_neighbours_along_trajectory(
                 torch.zeros(0, dtype=torch.int32, device=dev), len(fr_idx), ix_cent.size,
             )  # fmt: skip
 
-        return NeighbourList(ag_env, zero_counts, empty_csr)
+        return NeighbourList(ag_env, zero_counts, empty_csr, ix_env, ix_cent)
     if fr_idx:
         for pos_env, pos_cent, box in batches():
             if pos_cent is None and engine.lens_direct_supported(
@@ -303,4 +359,4 @@ def list_neighbours_along_trajectory(
             counts.append(nr.counts)
     dev_counts = (torch.cat(counts, dim=0) if counts else
                   torch.empty((0, ix_cent.size), dtype=torch.int32, device=frames.device()))  # fmt: skip
-    return NeighbourList(ag_env, dev_counts, build_csr)
+    return NeighbourList(ag_env, dev_counts, build_csr, ix_env, ix_cent)

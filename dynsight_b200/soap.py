@@ -23,6 +23,7 @@ __all__ = [
     "normalize_soap",
     "saponify_trajectory",
     "saponify_trajectory_device",
+    "TimesoapJob",
     "soap_distance",
     "timesoap",
     "timesoap_from_trajectory",
@@ -239,6 +240,55 @@ def timesoap(soap: NDArray[np.float64], delay: int = 1) -> NDArray[np.float64]:
     return frames.to_host(engine.timesoap_device(_to_device(soap), delay))
 
 
+class TimesoapJob:
+    """timeSOAP straight from positions, fed one device batch at a time (batches overlap by
+    ``delay`` frames): SOAP of the batch, reduced to timeSOAP on the device.  The (N, F, C) SOAP
+    tensor of the trajectory never exists."""
+
+    def __init__(self, universe: Any, soaprcut: float, soapnmax: int = 8, soaplmax: int = 8,
+                 delay: int = 1, selection: str = "all", soap_respectpbc: bool = True,
+                 centers: str = "all", trajslice: slice | None = None) -> None:  # fmt: skip
+        sel = universe.select_atoms(selection)
+        self.universe = universe
+        self.sel_ix = np.asarray(sel.indices)
+        centers_list = _centre_positions(sel, centers)
+        sp_idx, self.n_species = _species_indices(np.asarray(sel.atoms.types))
+        self.fr_idx = frames.frame_sequence(universe.trajectory.n_frames, trajslice)
+        if delay < 1 or delay >= len(self.fr_idx):
+            msg = "delay value outside bounds"
+            raise ValueError(msg)
+        self.r_cut, self.n_max, self.l_max = float(soaprcut), int(soapnmax), int(soaplmax)
+        self.delay, self.periodic = int(delay), bool(soap_respectpbc)
+        dev = frames.device()
+        self.n_cent = len(centers_list)
+        self.n_feat = soap_basis.n_features(self.n_species, self.n_max, self.l_max)
+        self.out = torch.empty((self.n_cent, len(self.fr_idx) - delay), dtype=torch.float64,
+                               device=dev)  # fmt: skip
+        self.species_t = torch.as_tensor(sp_idx, device=dev)
+        self.centres_t = torch.as_tensor(centers_list, device=dev)
+        self.n_all = len(universe.atoms)
+        self.sel_all = frames.Selection(self.sel_ix, self.n_all)
+
+    def default_batch_frames(self) -> int:
+        scratch = soap_basis.scratch_doubles(self.n_species, self.n_max, self.l_max)
+        per_frame = max(1, self.n_cent) * (self.n_feat + scratch) * 8.0
+        return int(max(self.delay + 1, min(512, 16e9 // per_frame)))
+
+    def process(self, fb: frames.FrameBatch) -> None:
+        if self.n_cent == 0:
+            return
+        box = frames.soap_boxes(fb, self.periodic)
+        pos = fb.select(self.sel_all, self.n_all)
+        spectra = engine.soap_power_spectrum(
+            pos, self.species_t, self.centres_t, box, self.r_cut, self.n_max, self.l_max,
+            n_species=self.n_species,
+        )  # fmt: skip
+        engine.timesoap_device(spectra, self.delay, out=self.out, col0=fb.seq0)
+
+    def finish(self) -> torch.Tensor:
+        return self.out
+
+
 def timesoap_from_trajectory(
     universe: Any,
     soaprcut: float,
@@ -259,35 +309,12 @@ def timesoap_from_trajectory(
     device.  Returns a CUDA float64 tensor (n_centers, n_frames - delay), or the same values as a
     numpy array (like ``timesoap``) with ``as_numpy=True``.
     """
-    if trajslice is None:
-        trajslice = slice(None)
-    sel = universe.select_atoms(selection)
-    sel_ix = np.asarray(sel.indices)
-    centers_list = _centre_positions(sel, centers)
-    sp_idx, n_species = _species_indices(np.asarray(sel.atoms.types))
-    fr_idx = frames.frame_sequence(universe.trajectory.n_frames, trajslice)
-    if delay < 1 or delay >= len(fr_idx):
-        msg = "delay value outside bounds"
-        raise ValueError(msg)
-    dev = frames.device()
-    n_cent = len(centers_list)
-    n_feat = soap_basis.n_features(n_species, soapnmax, soaplmax)
-    out = torch.empty((n_cent, len(fr_idx) - delay), dtype=torch.float64, device=dev)
-    species_t = torch.as_tensor(sp_idx, device=dev)
-    centres_t = torch.as_tensor(centers_list, device=dev)
-    n_all = len(universe.atoms)
+    job = TimesoapJob(universe, soaprcut, soapnmax, soaplmax, delay, selection, soap_respectpbc,
+                      centers, trajslice)  # fmt: skip
     if batch_frames is None:
-        scratch = soap_basis.scratch_doubles(n_species, soapnmax, soaplmax)
-        per_frame = max(1, n_cent) * (n_feat + scratch) * 8.0
-        batch_frames = int(max(delay + 1, min(512, 16e9 // per_frame)))
+        batch_frames = job.default_batch_frames()
     batch_frames = max(batch_frames, delay + 1)
-    sel_all = frames.Selection(sel_ix, n_all)
-    for fb in frames.iter_batches(universe, fr_idx, batch_frames, overlap=delay):
-        box = frames.soap_boxes(fb, bool(soap_respectpbc))
-        pos = fb.select(sel_all, n_all)
-        spectra = engine.soap_power_spectrum(
-            pos, species_t, centres_t, box, float(soaprcut), int(soapnmax), int(soaplmax),
-            n_species=n_species,
-        )  # fmt: skip
-        engine.timesoap_device(spectra, delay, out=out, col0=fb.seq0)
+    for fb in frames.iter_batches(universe, job.fr_idx, batch_frames, overlap=delay):
+        job.process(fb)
+    out = job.finish()
     return frames.to_host(out) if as_numpy else out

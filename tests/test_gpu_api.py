@@ -335,3 +335,63 @@ def test_psi_phi_lane_groups_vs_oracle(scale):
                                do.orientational_order_param(pos, csr, 6), rtol=1e-5, atol=1e-6)  # fmt: skip
     np.testing.assert_allclose(descriptors.velocity_alignment(u, neig),
                                do.velocity_alignment(pos, csr), rtol=1e-5, atol=1e-6)  # fmt: skip
+
+
+def test_psi_phi_with_a_subset_selection_match_the_plain_list_path():
+    """The lazy NeighbourList stores positions inside the environment selection; the psi / phi
+    kernels index the universe's arrays, so rows are translated to universe indices like the
+    reference's ``neigh[t][i].indices`` (misc.py:79-88, 190-205)."""
+    from dynsight_b200 import descriptors
+    from dynsight_b200.trajectory import Trj
+    from dynsight_b200.universe import ArrayUniverse
+    from golden_cases import fluid_case
+
+    pos, box, r_cut = fluid_case(n_side=7, n_frames=4)
+    n = pos.shape[1]
+    dims = np.tile(np.concatenate([box, [90, 90, 90]]).astype(np.float32), (4, 1))
+    types = np.where(np.arange(n) % 3 == 0, "C", "O")
+    u = ArrayUniverse(pos, dims, names=types, types=types)
+    tr = Trj(u)
+    neig, _ = tr.get_coord_number(r_cut=r_cut, centers="all", selection="type O")
+    plain = [list(fr) for fr in neig]   # list[list[AtomGroup]]: .indices are universe indices
+    assert not np.array_equal(neig.env_indices, np.arange(n))
+    for order in (4, 6):
+        lazy = descriptors.orientational_order_param(u, neig, order=order)
+        assert np.array_equal(lazy, descriptors.orientational_order_param(u, plain, order=order))
+    assert np.array_equal(descriptors.velocity_alignment(u, neig),
+                          descriptors.velocity_alignment(u, plain))  # fmt: skip
+
+
+def test_pipeline_one_pass_equals_the_separate_calls(balls7):
+    """pipeline.descriptors_from_trajectory feeds every device batch to the LENS and the timeSOAP
+    job: same values as compute_lens / Trj.get_coord_number / timesoap_from_trajectory, for the
+    pair path, the rows path and explicit centres, with small batches that overlap."""
+    from dynsight_b200 import lens as dlens
+    from dynsight_b200 import pipeline
+    from dynsight_b200 import soap as dsoap
+    from dynsight_b200.trajectory import Trj
+    from dynsight_b200.universe import ArrayUniverse
+
+    rng = np.random.default_rng(4)
+    n, nf = 700, 9
+    box = np.array([28.0, 29.0, 27.5], dtype=np.float32)
+    pos = (rng.random((1, n, 3)) * box + rng.normal(0, 0.2, (nf, n, 3)).cumsum(0)).astype(np.float32)
+    dims = np.tile(np.concatenate([box, [90, 90, 90]]).astype(np.float32), (nf, 1))
+    types = np.where(np.arange(n) % 4 == 0, "C", "O")
+    uni = ArrayUniverse(pos, dims, names=types, types=["O"] * n)
+    for kw, r_lens in ((dict(), 4.0), (dict(), 9.5), (dict(centers="name C"), 4.0)):
+        for delay in (1, 2):
+            res = pipeline.descriptors_from_trajectory(
+                uni, lens_r_cut=r_lens, soap_r_cut=4.5, soapnmax=4, soaplmax=4, delay=delay,
+                coord_number=True, batch_frames=4, **kw,
+            )
+            assert np.array_equal(res["lens"], dlens.compute_lens(uni, r_lens, delay=delay, **kw))
+            _, nc = Trj(uni).get_coord_number(r_cut=r_lens, **kw)
+            assert np.array_equal(res["coord_number"], nc.dataset)
+            want_ts = dsoap.timesoap_from_trajectory(uni, 4.5, 4, 4, delay=delay, as_numpy=True,
+                                                     **kw)  # fmt: skip
+            # SOAP sums run in cell order, and the order of atoms inside a cell (atomic scatter)
+            # differs from launch to launch: equal to rounding, not bit for bit
+            assert np.abs(res["timesoap"] - want_ts).max() < 1e-12
+    with pytest.raises(ValueError, match="nothing to compute"):
+        pipeline.descriptors_from_trajectory(uni)

@@ -655,3 +655,33 @@ def test_compute_lens_delay_zero_returns_zeros(balls7):
     got = dlens.compute_lens(uni, 10.0, delay=0)
     assert got.shape == (7, 5)
     assert not got.any()
+
+
+def test_pair_path_dense_sampling_across_the_guard_band():
+    """300,000 pairs whose squared distance is spread evenly over r2 +- 1.5e-3, i.e. across the whole
+    float32 guard band INCLUDING its edges (a few pairs per float32 ulp): catches a pre-test of the
+    band that is a rounding error too narrow.  Both frames, pair path and rows path."""
+    from dynsight_b200 import engine
+
+    rng = np.random.default_rng(31)
+    r_cut = 1.5
+    r2 = (r_cut - 1e-6) ** 2
+    box = np.array([107.7, 96.3, 121.1], dtype=np.float32)
+    n_pairs = 300_000
+    frames = []
+    base = rng.random((n_pairs, 3)) * box
+    for _ in range(2):
+        d = rng.normal(size=(n_pairs, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        r = np.sqrt(r2 + rng.uniform(-1.5e-3, 1.5e-3, n_pairs))
+        pts = np.mod(np.concatenate([base, base - d * r[:, None]]), box).astype(np.float32)
+        frames.append(np.minimum(pts, np.nextafter(box, np.float32(0))))
+    pos = np.stack(frames).astype(np.float32)
+    dims = _dims(box, 2)
+    want = lo.compute_lens_arrays(pos, dims, r_cut, delay=1)
+    want_c = lo.coord_number_arrays(pos, dims, r_cut)
+    lens, counts = engine.lens_direct(_dev(pos), box, r_cut, 1, True)
+    assert np.array_equal(counts.cpu().numpy().T.astype(np.float64), want_c)
+    assert np.array_equal(lens.cpu().numpy(), want)
+    res, nr = engine.lens_from_positions(_dev(pos), box, r_cut, 1)
+    assert np.array_equal(res.cpu().numpy(), want)

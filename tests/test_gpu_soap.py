@@ -263,3 +263,111 @@ def test_cfg2_full_size_materialised_equals_streamed():
     assert full.shape == streamed.shape == (n, nf - 2)
     assert float((full - streamed).abs().max()) < 1e-9
     assert 0.0 < float(full.mean()) < 1.5
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-species layout: pins DERIVED from single-species runs (no reference golden has S > 1;
+# DScribe is called at saponify.py:96-122 with species = set(types))
+# ---------------------------------------------------------------------------------------------
+def _blocks(spec, n_species, n_max, l_max):
+    """Split a multi-species spectrum (..., C) into {(zi, zj): (..., l+1, n, n)} full matrices
+    (diagonal blocks symmetrised from their upper triangle)."""
+    out, pos = {}, 0
+    iu = np.triu_indices(n_max)
+    for zi in range(n_species):
+        for zj in range(zi, n_species):
+            if zi == zj:
+                size = (l_max + 1) * iu[0].size
+                tri = spec[..., pos : pos + size].reshape(*spec.shape[:-1], l_max + 1, -1)
+                full = np.zeros((*spec.shape[:-1], l_max + 1, n_max, n_max))
+                full[..., iu[0], iu[1]] = tri
+                full[..., iu[1], iu[0]] = tri
+            else:
+                size = (l_max + 1) * n_max * n_max
+                full = spec[..., pos : pos + size].reshape(*spec.shape[:-1], l_max + 1, n_max, n_max)
+            out[(zi, zj)] = full
+            pos += size
+    assert pos == spec.shape[-1]
+    return out
+
+
+def test_multi_species_blocks_sum_to_the_single_species_spectrum():
+    """Relabelling the atoms of a one-species system into three species must not change
+    c_nlm = sum_Z c^Z_nlm, hence p_lnn' = sum_Z p^ZZ_lnn' + sum_{Z<Z'} (p^ZZ'_lnn' + p^ZZ'_ln'n):
+    pins the content and the (l, n, n') layout of every block against the single-species kernel
+    (itself pinned by the seven DScribe goldens)."""
+    from dynsight_b200 import soap as dsoap
+    from dynsight_b200.universe import ArrayUniverse
+
+    rng = np.random.default_rng(21)
+    n, n_max, l_max = 300, 5, 4
+    box = np.array([27.0, 28.5, 26.2], dtype=np.float32)
+    pos = (rng.random((2, n, 3)) * box).astype(np.float32)
+    dims = np.tile(np.concatenate([box, [90, 90, 90]]).astype(np.float32), (2, 1))
+    one = dsoap.saponify_trajectory(ArrayUniverse(pos, dims, names=["O"] * n, types=["O"] * n),
+                                    4.5, n_max, l_max)  # fmt: skip
+    types = np.array(["Cu", "H", "O"])[rng.integers(0, 3, n)]
+    three = dsoap.saponify_trajectory(ArrayUniverse(pos, dims, names=types, types=types), 4.5,
+                                      n_max, l_max)  # fmt: skip
+    blk = _blocks(three, 3, n_max, l_max)
+    total = sum(blk[(z, z)] for z in range(3))
+    for zi in range(3):
+        for zj in range(zi + 1, 3):
+            total = total + blk[(zi, zj)] + np.swapaxes(blk[(zi, zj)], -1, -2)
+    iu = np.triu_indices(n_max)
+    got = total[..., iu[0], iu[1]].reshape(n, 2, -1)
+    scale = np.abs(one).max(axis=-1, keepdims=True)
+    assert (np.abs(got - one) / scale).max() < 1e-10
+
+
+def test_multi_species_block_order_and_orientation_derived():
+    """Which block is (Z, Z') and which index of a cross block belongs to which species, derived
+    from single-species runs.  All neighbours sit on the z axis through the centre, so only m = 0
+    survives and p^ZZ'_lnn' = u_n v_n' factorises for l >= 1; u and v follow (up to a sign) from the
+    single-species spectra of {centre + near atoms} and {centre + far atoms}.  Near and far atoms
+    excite different radial functions, so u v^T != v u^T.  Species order = ascending atomic number:
+    swapping the labels swaps the diagonal blocks and transposes the cross block."""
+    from dynsight_b200 import soap as dsoap
+    from dynsight_b200.universe import ArrayUniverse
+
+    n_max, l_max, r_cut = 4, 2, 5.0
+    box = np.array([60.0, 60.0, 60.0], dtype=np.float32)
+    c0 = np.array([30.0, 30.0, 30.0])
+    near = c0 + np.array([[0, 0, 1.0], [0, 0, -1.3]])
+    far = c0 + np.array([[0, 0, 4.2], [0, 0, -3.9]])
+    dims = np.concatenate([box, [90, 90, 90]]).astype(np.float32)[None]
+
+    def run(points, types):
+        pos = np.asarray(points, dtype=np.float32)[None]
+        u = ArrayUniverse(pos, dims, names=list(types), types=list(types))
+        return dsoap.saponify_trajectory(u, r_cut, n_max, l_max)[0, 0]   # centre = atom 0
+
+    iu = np.triu_indices(n_max)
+
+    def factor(spec, l):
+        tri = spec.reshape(l_max + 1, -1)[l]
+        m = np.zeros((n_max, n_max))
+        m[iu] = tri
+        m = m + m.T - np.diag(np.diag(m))
+        k = int(np.argmax(np.diag(m)))
+        return m[k] / np.sqrt(m[k, k])
+
+    p_near = run(np.vstack([c0, near]), ["O"] * 3)
+    p_far = run(np.vstack([c0, far]), ["O"] * 3)
+    pts = np.vstack([c0, near, far])
+    # centre + near atoms are hydrogen (Z = 1), far atoms copper (Z = 29): H is species 0
+    lo = _blocks(run(pts, ["H", "H", "H", "Cu", "Cu"]), 2, n_max, l_max)
+    # the other way round: centre + near atoms copper, far atoms hydrogen: H (far) is species 0
+    hi = _blocks(run(pts, ["Cu", "Cu", "Cu", "H", "H"]), 2, n_max, l_max)
+    for l in (1, 2):
+        u, v = factor(p_near, l), factor(p_far, l)
+        uv = np.outer(u, v)
+        scale = np.abs(uv).max()
+        assert np.abs(uv - uv.T).max() > 0.05 * scale          # the configuration is polarised
+        for blocks, a, b in ((lo, u, v), (hi, v, u)):         # species 0 = the hydrogen atoms
+            cross = blocks[(0, 1)][l]
+            want = np.outer(a, b)
+            err = min(np.abs(cross - want).max(), np.abs(cross + want).max())
+            assert err < 1e-9 * scale, (l, err)
+            assert np.abs(blocks[(0, 0)][l] - np.outer(a, a)).max() < 1e-9 * scale
+            assert np.abs(blocks[(1, 1)][l] - np.outer(b, b)).max() < 1e-9 * scale

@@ -126,3 +126,23 @@ def write_frame(coords: np.ndarray, box_nm: np.ndarray, step: int, time: float, 
     head += struct.pack(">i", smallidx)
     head += struct.pack(">i", len(payload))
     return head + payload + b"\0" * (-len(payload) % 4)
+
+
+def write_synthetic_waters(path, n_mol: int, n_frames: int, seed: int = 0) -> int:
+    """A compressed XTC of ``n_mol`` water-like triples x ``n_frames`` frames for throughput
+    measurements (bench.py): one frame is encoded and repeated with increasing step numbers (the
+    decoder does the same work for every frame).  Returns the file size in bytes."""
+    rng = np.random.default_rng(seed)
+    smallidx = 21
+    half = MAGICINTS[smallidx] // 2
+    p0 = rng.integers(0, 40_000, size=(n_mol, 3))
+    p1 = p0 + rng.integers(-half + 1, half - 1, size=(n_mol, 3)) // 2
+    p2 = p0 + rng.integers(-half + 1, half - 1, size=(n_mol, 3)) // 2
+    coords = np.stack([p0, p1, p2], axis=1).reshape(-1, 3).astype(np.int64)
+    layout = [("water", 0)] * n_mol
+    box = np.diag([40.0, 40.0, 40.0]).astype(np.float32)
+    frame = write_frame(coords, box, 0, 0.0, 1000.0, smallidx, layout)
+    with open(path, "wb") as fh:
+        for f in range(n_frames):
+            fh.write(frame[:8] + struct.pack(">if", f, 0.5 * f) + frame[16:])
+    return len(frame) * n_frames
