@@ -269,10 +269,12 @@ def traffic_for(kernel: str, atoms: int, frames: int) -> tuple[float | None, str
     return float(entry["dram_bytes_per_launch"]), f"{path.name}: {entry['source']}"
 
 
-def parity_check(engine, block, box, lens_out, nc_out, soap_buf, ts_out, n_sample: int) -> dict:
+def parity_check(engine, block, box, lens_out, nc_out, species, ts_out, n_sample: int) -> dict:
     """The outputs of the last timed step against the CPU oracle (the checker, not the product):
-    LENS and coordination numbers of the first two frame pairs for ALL atoms, bit for bit; SOAP
-    and timeSOAP on ``n_sample`` evenly spaced centres (1e-8 max|p| and 1e-5 t + 1e-7)."""
+    LENS and coordination numbers of the first two frame pairs for ALL atoms, bit for bit;
+    timeSOAP of the first pair on ``n_sample`` evenly spaced centres (1e-5 t + 1e-7), and -- the
+    timed step writes no spectra -- the SOAP vectors of those centres from one extra call of the
+    same kernels (1e-8 max|p|)."""
     from oracle import lens_oracle, soap_oracle, timesoap_oracle
 
     n_atoms = block.shape[1]
@@ -291,8 +293,12 @@ def parity_check(engine, block, box, lens_out, nc_out, soap_buf, ts_out, n_sampl
                                   L_MAX, basis, n_threads=os.cpu_count() or 1) for f in range(2)],
         axis=1,
     )  # fmt: skip
-    idx = __import__("torch").as_tensor(sample.astype(np.int64), device=soap_buf.device)
-    got_soap = soap_buf[idx, :2].cpu().numpy()
+    torch = __import__("torch")
+    idx = torch.as_tensor(sample.astype(np.int64), device=ts_out.device)
+    got_soap = engine.soap_power_spectrum(
+        block[:2].contiguous(), species, torch.as_tensor(sample, device=ts_out.device), box,
+        R_CUT_SOAP, N_MAX, L_MAX, n_species=1,
+    ).cpu().numpy()  # fmt: skip
     rel = float((np.abs(got_soap - want_soap) / np.abs(want_soap).max(axis=-1, keepdims=True)).max())
     want_ts = timesoap_oracle.timesoap(want_soap, DELAY)[:, 0]
     got_ts = ts_out[idx, 0].cpu().numpy()
@@ -349,7 +355,6 @@ def run_b200(args: argparse.Namespace) -> None:
     species = torch.zeros(n_atoms, dtype=torch.int32, device=dev)
     centres = torch.arange(n_atoms, dtype=torch.int32, device=dev)
     n_feat = 324
-    soap_buf = torch.empty((n_atoms, bsz + 1, n_feat), dtype=torch.float64, device=dev)
     lens_out = torch.empty((n_atoms, bsz), dtype=torch.float64, device=dev)
     ts_out = torch.empty((n_atoms, bsz), dtype=torch.float64, device=dev)
     nc_out = torch.empty((n_atoms, bsz + 1), dtype=torch.float64, device=dev)
@@ -358,7 +363,7 @@ def run_b200(args: argparse.Namespace) -> None:
     if not engine.lens_direct_supported(bsz + 1, n_atoms, box, R_CUT_LENS, True):
         raise SystemExit("bench.py: this shape is outside the pair path of the LENS kernels")
 
-    ev = {k: [] for k in ("lens", "soap", "tsoap")}
+    ev = {k: [] for k in ("lens", "soap_timesoap")}
 
     def step(b: int, record: bool) -> None:
         lo = (b % args.pool_blocks) * bsz
@@ -375,7 +380,7 @@ def run_b200(args: argparse.Namespace) -> None:
             block[bsz:].copy_(halo_recv)
         else:
             block[bsz:].copy_(pool[nxt : nxt + DELAY])
-        marks = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record else None
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if record else None
         if marks:
             marks[0].record()
         # LENS + coordination numbers: pair path (half-shell search, partner-frame lookup)
@@ -383,14 +388,13 @@ def run_b200(args: argparse.Namespace) -> None:
         engine.coordination_numbers(counts, out=nc_out, col0=0)
         if marks:
             marks[1].record()
-        engine.soap_power_spectrum(block, species, centres, box, R_CUT_SOAP, N_MAX, L_MAX,
-                                   n_species=1, out=soap_buf, frame0=0)  # fmt: skip
+        # SOAP fused with timeSOAP: every spectrum is folded into the distance to the previous
+        # frame's inside the spectrum epilogue; no (N, F, C) tensor is written
+        engine.soap_timesoap(block, species, centres, box, R_CUT_SOAP, N_MAX, L_MAX, delay=DELAY,
+                             n_species=1, out=ts_out, col0=0)  # fmt: skip
         if marks:
             marks[2].record()
-        engine.timesoap_device(soap_buf, DELAY, out=ts_out, col0=0)
-        if marks:
-            marks[3].record()
-            for k, name in enumerate(("lens", "soap", "tsoap")):
+            for k, name in enumerate(("lens", "soap_timesoap")):
                 ev[name].append((marks[k], marks[k + 1]))
 
     def barrier() -> None:
@@ -425,7 +429,7 @@ def run_b200(args: argparse.Namespace) -> None:
     # ---- parity of what was just timed (rank 0; the oracle is the checker only) ----
     parity = None
     if rank == 0 and not args.no_parity:
-        parity = parity_check(engine, block, box, lens_out, nc_out, soap_buf, ts_out, 1024)
+        parity = parity_check(engine, block, box, lens_out, nc_out, species, ts_out, 1024)
 
     # ---- fp64 FMA peak of this device ("builder must measure") ----
     scratch = torch.empty(148 * 8 * 256, dtype=torch.float64, device=dev)
@@ -448,18 +452,19 @@ def run_b200(args: argparse.Namespace) -> None:
     k_soap = RHO * 4.0 / 3.0 * math.pi * r_soap**3 + 1.0
     fl, ex = soap_flops_per_pf(k_soap)
     soap_pf = n_atoms * (bsz + 1)
+    part_ms["soap"] = part_ms["soap_timesoap"]   # one fused kernel chain
     soap_tflops = fl * soap_pf / (part_ms["soap"] * 1e-3) / 1e12
     # second view: every exponential is 8 fp64 operations (2 range reduction, 5 polynomial, 1 table)
     soap_tflops_exp = (fl + 2.0 * 8.0 * ex) * soap_pf / (part_ms["soap"] * 1e-3) / 1e12
-    soap_bytes = (12 + 8 * n_feat) * soap_pf
     lens_bytes_pf = 20 + 8 * (k_mean_lens + 1)
     lens_gbs = lens_bytes_pf * pf_per_step / (part_ms["lens"] * 1e-3) / 1e9
-    ts_gbs = (8 * n_feat + 8) * pf_per_step / (part_ms["tsoap"] * 1e-3) / 1e9
+    del part_ms["soap"]
+    soap_ms = part_ms["soap_timesoap"]
     soap_traffic, soap_traffic_src = traffic_for("soap_kernel", n_atoms, bsz + 1)
     lens_traffic, lens_traffic_src = traffic_for("lens_pair_pipeline", n_atoms, bsz + 1)
-    ts_traffic, ts_traffic_src = traffic_for("timesoap_stream_kernel", n_atoms, bsz + 1)
     roofline = {
-        "kernel": "soap_kernel<8,20,0,0,0,false,LIST=true> (+ soap_list_kernel, binning)",
+        "kernel": "soap_kernel<8,20,0,0,0,false,LIST=true,SEQ=true> (SOAP with the timeSOAP distance "
+                  "folded into the spectrum epilogue; + soap_list_kernel, binning)",
         "bound": "fp64",
         "achieved": soap_tflops,
         "peak": fp64_peak_tflops,
@@ -475,10 +480,12 @@ def run_b200(args: argparse.Namespace) -> None:
         "frac_counting_exps_as_16_flops": (soap_tflops_exp / fp64_peak_tflops
                                            if fp64_peak_tflops else None),
         "mean_neighbours_incl_self": k_soap,
-        "share_of_step": part_ms["soap"] / sum(part_ms.values()),
+        "share_of_step": soap_ms / sum(part_ms.values()),
         "hbm_view": {
-            "achieved_gbs": soap_bytes / (part_ms["soap"] * 1e-3) / 1e9, "peak_gbs": hbm_peak,
-            "algorithmic_bytes_per_pf": 12 + 8 * n_feat,
+            "note": "fused: 12 B of positions in, 8 B of timeSOAP out per particle-frame; the "
+                    "2592 B spectrum goes to the warp's ring (L2) instead of HBM",
+            "unfused_bytes_per_pf": 12 + 2 * 8 * n_feat + 8, "fused_bytes_per_pf": 20,
+            "peak_gbs": hbm_peak,
         },
     }  # fmt: skip
     rooflines_hbm = [
@@ -490,13 +497,6 @@ def run_b200(args: argparse.Namespace) -> None:
             "traffic_source": lens_traffic_src,
             "algorithmic_bytes_per_pf": lens_bytes_pf, "mean_neighbours": k_mean_lens,
             "ms_per_step": part_ms["lens"], "peak_source": hbm_src,
-        },
-        {
-            "kernel": "timesoap_stream_kernel<12>",
-            "bound": "hbm", "achieved": ts_gbs, "peak": hbm_peak, "unit": "GB/s",
-            "frac": ts_gbs / hbm_peak, "traffic": ts_traffic, "traffic_source": ts_traffic_src,
-            "algorithmic_bytes_per_pf": 8 * n_feat + 8, "ms_per_step": part_ms["tsoap"],
-            "peak_source": hbm_src,
         },
     ]  # fmt: skip
 
@@ -549,7 +549,7 @@ def run_b200(args: argparse.Namespace) -> None:
     cfg4 = None
     small = None
     if rank == 0 and not args.no_extra:
-        del pool, soap_buf
+        del pool
         torch.cuda.empty_cache()
         extra = lens_cfg3_section(engine, dev, hbm_peak, hbm_src)
         cfg4 = soap_cfg4_section(engine, dev, hbm_peak, fp64_peak_tflops, args.no_parity)
@@ -599,8 +599,7 @@ def run_b200(args: argparse.Namespace) -> None:
             "breakdown_ms_per_step": part_ms,
             "breakdown_pf_per_s": {
                 "lens_from_positions": pf_per_step / (part_ms["lens"] * 1e-3),
-                "soap": soap_pf / (part_ms["soap"] * 1e-3),
-                "timesoap": pf_per_step / (part_ms["tsoap"] * 1e-3),
+                "soap_timesoap_fused": soap_pf / (soap_ms * 1e-3),
             },
             "cpu_baseline": cpu_baseline,
             "strong_scaling": strong,
@@ -785,21 +784,18 @@ def soap_cfg4_section(engine, dev, hbm_peak: float, fp64_peak_tflops: float, no_
     cen = torch.arange(n, dtype=torch.int32, device=dev)
     box3 = np.full(3, np.float32(box_l), dtype=np.float32)
     ts_out = torch.empty((n, n_frames - DELAY), dtype=torch.float64, device=dev)
-    batch = 5   # 4 new frames per batch: 33 GB of spectra + 29 GB of primitive sums in flight
-    keep = {}
+    # primitive sums between the accumulate and the spectrum kernel: 23 KB per centre-frame; the
+    # spectra (26.4 KB per centre-frame) only ever exist in the warps' rings
+    batch = 12
 
     def run() -> int:
         done = 0
         start = 0
         while start < n_frames - DELAY:
             stop = min(n_frames, start + batch)
-            spectra = engine.soap_power_spectrum(pos[start:stop], sp3, cen, box3, R_CUT_SOAP, N_MAX,
-                                                 l_max4, n_species=n_sp)  # fmt: skip
-            engine.timesoap_device(spectra, DELAY, out=ts_out, col0=start)
-            if start == 0:
-                keep["first"] = spectra[:: n // 48, :2].clone()
+            engine.soap_timesoap(pos[start:stop], sp3, cen, box3, R_CUT_SOAP, N_MAX, l_max4,
+                                 delay=DELAY, n_species=n_sp, out=ts_out, col0=start)  # fmt: skip
             done += stop - start
-            del spectra
             start = stop - DELAY
         return done
 
@@ -830,7 +826,8 @@ def soap_cfg4_section(engine, dev, hbm_peak: float, fp64_peak_tflops: float, no_
                                       N_MAX, l_max4, basis, n_threads=os.cpu_count() or 1)
              for f in range(2)], axis=1,
         )  # fmt: skip
-        got = keep["first"].cpu().numpy()
+        got = engine.soap_power_spectrum(pos[:2], sp3, torch.as_tensor(sample, device=dev), box3,
+                                         R_CUT_SOAP, N_MAX, l_max4, n_species=n_sp).cpu().numpy()  # fmt: skip
         rel = float((np.abs(got - want) / np.abs(want).max(axis=-1, keepdims=True)).max())
         want_t = timesoap_oracle.timesoap(want, DELAY)[:, 0]
         got_t = ts_out[:: n // 48, 0].cpu().numpy()
@@ -841,10 +838,12 @@ def soap_cfg4_section(engine, dev, hbm_peak: float, fp64_peak_tflops: float, no_
     return {
         "workload": f"cfg4 (BASELINE.json configs[3]): {n} atoms, {n_sp} species, rho={rho4}/A^3, "
                     f"r_cut={R_CUT_SOAP}, n_max={N_MAX}, l_max={l_max4} ({n_feat4} features, "
-                    f"K={k4:.0f}), {n_frames} frames streamed into timeSOAP in batches of {batch}",
+                    f"K={k4:.0f}), {n_frames} frames through the fused SOAP -> timeSOAP kernels in "
+                    f"batches of {batch} frames (the 218 GB of spectra never exist)",
         "value": n * (n_frames - DELAY) / (ms * 1e-3), "unit": UNIT,
         "value_note": "timeSOAP particle-frames per second including the SOAP of every frame "
-                      "(batches overlap by one frame: 40 SOAP frames for 32 pairs)",
+                      f"(batches overlap by one frame: {soap_frames} SOAP frames for "
+                      f"{n_frames - DELAY} pairs)",
         "soap_pf_per_s": n * soap_frames / (ms * 1e-3), "ms_total": ms,
         "roofline": {"bound": "fp64", "achieved": tfl, "peak": fp64_peak_tflops,
                      "unit": "TFLOP/s",

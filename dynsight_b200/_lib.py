@@ -92,6 +92,17 @@ SIGNATURES: dict[str, tuple] = {
         [_c_ptr, _c_int, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_int, _c_ptr, _c_dbl, _c_int,
          _c_int, _c_ptr, _c_ptr, _c_ptr, _c_size, _c_ptr, _c_i64, _c_i64, _c_ptr],
     ),
+    "dsg_soap_timesoap_workspace_bytes": (
+        _c_int,
+        [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_ptr, _c_dbl, _c_int,
+         ctypes.POINTER(_c_size)],
+    ),
+    "dsg_soap_timesoap": (
+        _c_int,
+        [_c_ptr, _c_int, _c_ptr, _c_ptr, _c_int, _c_int, _c_int, _c_int, _c_ptr, _c_dbl, _c_int,
+         _c_int, _c_ptr, _c_ptr, _c_int, _c_ptr, _c_size, _c_ptr, _c_i64, _c_i64, _c_ptr, _c_i64,
+         _c_i64, _c_ptr],
+    ),
     "dsg_rows_csr_workspace_bytes": (_c_int, [_c_int, _c_int, ctypes.POINTER(_c_size)]),
     "dsg_rows_csr_offsets": (
         _c_int, [_c_ptr, _c_int, _c_int, _c_ptr, _c_size, _c_ptr, _c_ptr, _c_ptr],

@@ -66,6 +66,23 @@ __host__ __device__ inline double lens_value(int a, int b, int inter) {
     return (double)numer / (double)denom;    // lens.py:188 (IEEE float64 division)
 }
 
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// timeSOAP of one pair from the squared norms and the dot product of the two SOAP vectors
+// (timesoap.py:54-58 + :118-127).  A zero-norm vector normalises to the zero vector => cos = 0.
+__device__ __forceinline__ double soap_dist_from_sums(double n1sq, double n2sq, double dot) {
+    double c = 0.0;
+    if (n1sq > 0.0 && n2sq > 0.0) c = dot / (sqrt(n1sq) * sqrt(n2sq));
+    c = fmin(1.0, fmax(-1.0, c));
+    return sqrt(fmax(0.0, 2.0 - 2.0 * c));
+}
+#endif
+
 __host__ __device__ inline int wrap_cell(int c, int n) {
     c %= n;
     return c < 0 ? c + n : c;

@@ -1651,9 +1651,9 @@ pair_finalize_kernel(const unsigned long long* __restrict__ acc, int n_frames, i
     for (int k = 0; k < kFinRun; ++k) {
         const int t = t0 + k;
         if (t + delay < n_frames) {
-            // the partner word is one of mine when the delay is shorter than the run
-            const unsigned long long w2 = (k + delay < kFinRun && delay < kFinRun)
-                                              ? w[(k + delay) & (kFinRun - 1)]
+            // delay 1: the partner word is the next one of my own run (static register index)
+            const unsigned long long w2 = (delay == 1 && k + 1 < kFinRun)
+                                              ? w[k + 1 < kFinRun ? k + 1 : 0]
                                               : acc[(size_t)(t + delay) * n_atoms + i];
             row[t] = lens_value((int)(unsigned)w[k], (int)(unsigned)w2, (int)(unsigned)(w[k] >> 32));
         }

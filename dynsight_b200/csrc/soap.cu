@@ -73,6 +73,10 @@ constexpr int kOpenCellsPerAxis = 32;
 #ifndef DSG_SOAP_EXTRA_SMEM
 #define DSG_SOAP_EXTRA_SMEM 0      // occupancy probe: dummy dynamic shared memory per block
 #endif
+#ifndef DSG_SOAP_SEQ_GROUP
+#define DSG_SOAP_SEQ_GROUP 1
+#endif
+constexpr int kSeqGroup = DSG_SOAP_SEQ_GROUP;  // centres a warp of the frame-sequential kernels walks per frame
 constexpr int kListCap = 32;     // displacement list entries per warp
 constexpr int kCellTab = 32;     // (cell range, shift) entries resolved per pass
 constexpr int kBatchCap = 64;    // 32-candidate batches listed per pass
@@ -135,6 +139,16 @@ struct SoapArgs {
     int row_cap;
     int* list_flag;         // != 0: some row overflowed row_cap -> the in-kernel gather runs instead
     int list_role;          // 0 no lists; 1 consumer of the lists; 2 fallback (runs iff the flag is set)
+    // frame-sequential mode (SEQ kernels, dsg_soap_timesoap): a warp owns one centre and a run of
+    // seq_run frame pairs; the spectrum of frame f is compared with the one of frame f - delay,
+    // which the same warp left in its ring (global memory, rewritten every `delay` frames, so it
+    // lives in L2), and only the timeSOAP value is written (the spectra too if out != NULL)
+    const int* slot_of_atom;   // (F, N) sorted slot of an atom
+    const int* centres;        // (n_cent) atom index of a centre (unused by the kernels so far)
+    int n_frames, delay, seq_run;
+    double* ring;              // (n_runs, n_cent, delay, n_feat + 1): vectors + squared norms
+    double* ts_out;
+    long long ts_ld, ts_col0;
     SoapPlan plan;
 };
 constexpr int kListEntryShift = 26;
@@ -251,7 +265,7 @@ soap_scatter_kernel(const double* __restrict__ wpos, int n_atoms,
                     const SoapFrame* __restrict__ fr, const unsigned* __restrict__ cell_id,
                     int* __restrict__ cell_cnt, const int* __restrict__ cell_start,
                     double* __restrict__ sx, double* __restrict__ sy, double* __restrict__ sz,
-                    int* __restrict__ sid) {
+                    int* __restrict__ sid, int* __restrict__ slot_of) {
     const int f = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_atoms) return;
@@ -262,6 +276,7 @@ soap_scatter_kernel(const double* __restrict__ wpos, int n_atoms,
     sy[slot] = wpos[a * 3 + 1];
     sz[slot] = wpos[a * 3 + 2];
     sid[slot] = i;
+    if (slot_of) slot_of[a] = slot;
 }
 
 __global__ void __launch_bounds__(256)
@@ -571,13 +586,47 @@ __device__ __forceinline__ void store_item(const Acc<S>& a, int l, int k, int n,
 // memory; the mixed coefficients c[z][lm][n'] = sqrt(w_lm) * sum_k bmat[l][n'][k] G[z][lm][k] go to
 // the shared buffer `mix`, then one lane per output contracts over m and the warp writes the
 // spectrum coalesced.
+// Where the features of one (centre, frame) go: the spectrum row (out, may be NULL) and/or the
+// timeSOAP sums against the vector the same warp computed `delay` frames earlier (ring, may be
+// NULL; it is overwritten with the new vector).  Lane `lane` handles the features c = lane (mod 32)
+// in ascending order with the same fma sequence as timesoap_stream_kernel, so the fused value equals
+// the two-kernel one.
+struct SpectrumSink {
+    double* out;
+    double* ring;
+    double csq, dot;
+    // staged spectrum (shared memory): the ring loads of a lane are independent of its ring
+    // stores only if they all come first -- one L2 round trip per frame instead of eleven
+    __device__ __forceinline__ void put_staged(const double* __restrict__ stage, int n_feat,
+                                               int lane) {
+        if (ring) {
+            for (int c = lane; c < n_feat; c += 32) {
+                const double v = stage[c];
+                csq = fma(v, v, csq);
+                dot = fma(v, ring[c], dot);
+            }
+            for (int c = lane; c < n_feat; c += 32) ring[c] = stage[c];
+        }
+        if (out)
+            for (int c = lane; c < n_feat; c += 32) out[c] = stage[c];
+    }
+    __device__ __forceinline__ void put(int c, double v) {
+        if (out) out[c] = v;
+        if (ring) {
+            csq = fma(v, v, csq);
+            dot = fma(v, ring[c], dot);
+            ring[c] = v;
+        }
+    }
+};
+
 __device__ __forceinline__ void mix_and_spectrum(const SoapArgs& a, const double* __restrict__ gsum,
                                                  double* __restrict__ mix,
                                                  const double* __restrict__ bmat,
                                                  const double* __restrict__ swlm,
                                                  const unsigned char* __restrict__ lm_l,
                                                  const unsigned short* __restrict__ decode,
-                                                 double* __restrict__ out, int lane) {
+                                                 SpectrumSink& sink, int lane) {
     const SoapPlan& pl = a.plan;
     const int n = pl.n_max, n_lm = pl.n_lm;
     const int n_out = pl.n_species * n_lm * n;
@@ -664,7 +713,7 @@ __device__ __forceinline__ void mix_and_spectrum(const SoapArgs& a, const double
             if (nb0 > na0) ob[r1 + nb0] = o10;        // below the diagonal inside a diagonal tile
         }
         __syncwarp();
-        for (int c = lane; c < pl.n_feat; c += 32) out[c] = stage[c];
+        sink.put_staged(stage, pl.n_feat, lane);
         __syncwarp();
         return;
     }
@@ -679,7 +728,7 @@ __device__ __forceinline__ void mix_and_spectrum(const SoapArgs& a, const double
             s0 = fma(ca[mi * n], cb[mi * n], s0);
             s1 = fma(ca[(mi + 1) * n], cb[(mi + 1) * n], s1);
         }
-        out[c] = s0 + s1;
+        sink.put(c, s0 + s1);
     }
     __syncwarp();
 }
@@ -695,12 +744,18 @@ __device__ __forceinline__ void mix_and_spectrum(const SoapArgs& a, const double
 // (round 2) that is the faster shape: 4.68e7 centre-frames/s for 4 x 4 against 4.52e7 for 6 x 2 at
 // 168 registers on the 100 000-atom box (round 1, 13-operation exponential: 4.30e7 vs 4.38e7).
 constexpr int kListWarps = DSG_SOAP_LIST_WARPS;
-template <int LT, int S0, int S1, int S2, int S3, bool SPLIT, bool LIST>
+// SEQ = frame-sequential: warp w of the grid owns centre w and the frame pairs
+// [blockIdx.y * seq_run, ...) -- it walks the frames of its run in order (plus the `delay` frames
+// before its first output), finds its centre in each frame's sorted order through slot_of_atom,
+// and hands every spectrum to the timeSOAP sums against its ring.  Not combined with SPLIT (there
+// soap_spectrum_kernel is the frame-sequential one).
+template <int LT, int S0, int S1, int S2, int S3, bool SPLIT, bool LIST, bool SEQ = false>
 __global__ void __launch_bounds__(
     (LIST && S0 <= 20) ? 32 * kListWarps : 64,
     (S0 <= 20) ? (LIST ? DSG_SOAP_LIST_BLOCKS : DSG_SOAP_MIN_BLOCKS)
                : (S0 <= 21 ? DSG_SOAP_MIN_BLOCKS_L10 : 4))
 soap_kernel(const SoapArgs a) {
+    static_assert(!(SEQ && SPLIT), "frame-sequential accumulation is only the fused kernel");
     constexpr bool PK = LT == 8 && S0 == kPackSlots;  // packed l_max = 8 rows (see hoff)
     // list mode: the consumer runs unless a row overflowed, the fallback only if one did
     if (a.list_role != 0 && ((*a.list_flag != 0) != (a.list_role == 2))) return;
@@ -733,13 +788,29 @@ soap_kernel(const SoapArgs a) {
     __syncthreads();
     const double* __restrict__ bmat = bmat_stage > 0 ? bmat_s : a.bmat;
     double* smem = smem_all + kExpTab + bmat_stage + epi_stage;
-    const int f = blockIdx.y;
-    // each warp walks a run of consecutive slots of the frame's (species, cell)-sorted order:
-    // consecutive centres share their candidate cells (L1 reuse, cached cell table) and the
-    // block-wide tables are loaded once
-    const int first = (blockIdx.x * warps + warp) * a.slots_per_warp;
-    const int last = min(a.n_atoms, first + a.slots_per_warp);
-    if (first >= last) return;  // warps are independent from here: only __syncwarp below
+    // non-SEQ: each warp walks a run of consecutive slots of the frame's (species, cell)-sorted
+    // order: consecutive centres share their candidate cells (L1 reuse, cached cell table) and
+    // the block-wide tables are loaded once
+    int first = 0, last = 0, seq_t0 = 0, seq_frames = 1, seq_first = 0;
+    if (SEQ) {
+        // warp w takes the kSeqGroup atoms that sit at the sorted slots [w * kSeqGroup, ...) of the
+        // run's FIRST frame (neighbours in space, so the warps of a block keep sharing lines).
+        // Measured on 100 000 atoms x 33 frames: groups of 1 / 2 / 4 / 8 / 16 / 32 centres per warp
+        // give 69.3 / 72.1 / 73.6 / 76.1 / 77.6 / 80.2 ms -- more, shorter-lived warps balance the
+        // SMs better than longer walks reuse L1, so a warp owns ONE centre (69.0 ms + 1.3 ms for
+        // the two-kernel path).
+        seq_first = (blockIdx.x * warps + warp) * kSeqGroup;
+        if (seq_first >= a.n_atoms) return;   // warps are independent from here: only __syncwarp below
+        seq_t0 = blockIdx.y * a.seq_run;                       // first frame pair of the run
+        const int t1 = min(a.n_frames - a.delay, seq_t0 + a.seq_run);
+        seq_frames = t1 - seq_t0 + a.delay;                    // frames seq_t0 .. t1 + delay - 1
+        first = 0;
+        last = min(kSeqGroup, a.n_atoms - seq_first);
+    } else {
+        first = (blockIdx.x * warps + warp) * a.slots_per_warp;
+        last = min(a.n_atoms, first + a.slots_per_warp);
+        if (first >= last) return;
+    }
 
     const SoapPlan& pl = a.plan;
     const int n = pl.n_max, P = pl.row_stride, n_lm = pl.n_lm;
@@ -754,6 +825,18 @@ soap_kernel(const SoapArgs a) {
     int* bl_e = reinterpret_cast<int*>(bl_q + kBatchCap);             // [64] batch -> table entry
     double* rbuf = nbuf + kWarpFixed;  // [kChunk][P] harmonics; later G / mixed
 
+    const int g = lane >> 3, kk = lane & 7;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int il[kMaxItems], ioff[kMaxItems];
+#pragma unroll
+    for (int t = 0; t < kMaxItems; ++t) {
+        il[t] = pl.item_l[g][t];
+        ioff[t] = pl.item_off[g][t];
+    }
+
+    const int n_pass = SPLIT ? pl.n_species * pl.kblocks : 1;
+    for (int fo = 0; fo < seq_frames; ++fo) {   // one trip unless SEQ
+    const int f = SEQ ? seq_t0 + fo : (int)blockIdx.y;
     const SoapFrame* __restrict__ fr = a.frames + f;
     int ne[3], mode[3], nc[3], nimg[3];
     double box[3];
@@ -766,17 +849,6 @@ soap_kernel(const SoapArgs a) {
         ne[k] = mode[k] == kNarrow ? 2 * nimg[k] + 1 : 3;
     }
     const int spec_stride = fr->spec_stride;
-
-    const int g = lane >> 3, kk = lane & 7;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    int il[kMaxItems], ioff[kMaxItems];
-#pragma unroll
-    for (int t = 0; t < kMaxItems; ++t) {
-        il[t] = pl.item_l[g][t];
-        ioff[t] = pl.item_off[g][t];
-    }
-
-    const int n_pass = SPLIT ? pl.n_species * pl.kblocks : 1;
     for (int pass = 0; pass < n_pass; ++pass) {
     const int z_sp = SPLIT ? pass / pl.kblocks : 0;
     const int kb = SPLIT ? pass - z_sp * pl.kblocks : 0;
@@ -785,8 +857,12 @@ soap_kernel(const SoapArgs a) {
     const bool kact = k < n;
     int cached_cell = -1, n_batches = -1;
 
-    for (int slot_local = first; slot_local < last; ++slot_local) {
-        const size_t slot = (size_t)f * a.n_atoms + slot_local;
+    for (int walk = first; walk < last; ++walk) {
+        // SEQ: the walk-th atom of the warp's group, wherever this frame's order has put it
+        const size_t slot =
+            SEQ ? (size_t)a.slot_of_atom[(size_t)f * a.n_atoms +
+                                         a.sid[(size_t)seq_t0 * a.n_atoms + seq_first + walk]]
+                : (size_t)f * a.n_atoms + walk;
         const int ci = a.centre_of_atom[a.sid[slot]];
         if (ci < 0) continue;
         const double xc = a.sx[slot], yc = a.sy[slot], zc = a.sz[slot];
@@ -1050,12 +1126,38 @@ soap_kernel(const SoapArgs a) {
         __syncwarp();
         if (!SPLIT) {
             // the harmonics buffer is free now: G sits at its start, the mixed coefficients follow
+            SpectrumSink sink;
+            sink.out = a.out ? a.out + (long long)ci * a.stride_i + (long long)f * a.stride_f
+                             : nullptr;
+            sink.ring = nullptr;
+            sink.csq = sink.dot = 0.0;
+            double* ring_sq = nullptr;
+            if (SEQ) {
+                // ring slot f mod delay still holds frame f - delay (if the run got that far)
+                double* base = a.ring + (((size_t)blockIdx.y * a.n_cent + ci) * a.delay +
+                                         (size_t)(f % a.delay)) * (size_t)(pl.n_feat + 1);
+                sink.ring = base;
+                ring_sq = base + pl.n_feat;
+                // runs overlap by `delay` frames: the spectrum row of a frame (if wanted) is
+                // written by the run its index falls into
+                if (min(f / a.seq_run, (int)gridDim.y - 1) != (int)blockIdx.y) sink.out = nullptr;
+            }
             mix_and_spectrum(a, rbuf, rbuf + ((c_doubles + 1) & ~1), bmat, swlm_s, lm_l_s,
-                             decode_s,
-                             a.out + (long long)ci * a.stride_i + (long long)f * a.stride_f, lane);
+                             decode_s, sink, lane);
+            if (SEQ) {
+                const double csq = warp_sum(sink.csq), dot = warp_sum(sink.dot);
+                if (lane == 0) {
+                    if (fo >= a.delay)
+                        a.ts_out[(long long)ci * a.ts_ld + a.ts_col0 + (f - a.delay)] =
+                            soap_dist_from_sums(*ring_sq, csq, dot);
+                    *ring_sq = csq;
+                }
+                __syncwarp();
+            }
         }
     }  // slot loop
     }  // pass loop
+    }  // frame loop (SEQ)
 }
 
 // Split mode, second kernel: one warp per (centre, frame), one angular momentum at a time.  The
@@ -1070,6 +1172,7 @@ struct SpecTask {
     int pad;
 };
 
+template <bool SEQ>
 __global__ void __launch_bounds__(128)
 soap_spectrum_kernel(const SoapArgs a, const SpecTask* __restrict__ tasks, int n_tasks) {
     extern __shared__ __align__(16) double smem_all[];
@@ -1081,12 +1184,52 @@ soap_spectrum_kernel(const SoapArgs a, const SpecTask* __restrict__ tasks, int n
     const SoapPlan& pl = a.plan;
     const int n = pl.n_max, n_lm = pl.n_lm, l_max = pl.l_max, S = pl.n_species;
     const int np_stride = (n + 1) & ~1;
-    double* mix = smem_all + a.bmat_smem_doubles + (size_t)warp * S * (2 * l_max + 1) * np_stride;
-    const int f = blockIdx.y;
+    // per warp: mixed coefficients of one l + the outputs of that l (all species pairs, in
+    // feature order); block-wide: feature index at l = 0 and per-l stride of every output
+    const int n_l = pl.n_feat / (l_max + 1);
+    const int mix_doubles = S * (2 * l_max + 1) * np_stride;
+    const int warp_doubles = (mix_doubles + n_l + 1) & ~1;
+    double* mix = smem_all + a.bmat_smem_doubles + (size_t)warp * warp_doubles;
+    double* lst = mix + mix_doubles;
+    int* c0_s = reinterpret_cast<int*>(smem_all + a.bmat_smem_doubles +
+                                       (size_t)(blockDim.x >> 5) * warp_doubles);
+    int* blk_s = c0_s + n_l;
+    for (int t = threadIdx.x; t < n_tasks; t += blockDim.x) {
+        const SpecTask tk = tasks[t];
+        const bool diag = (tk.code & 15) == ((tk.code >> 4) & 15);
+        const int na0 = (tk.code >> 8) & 255, nb0 = (tk.code >> 16) & 255;
+        const int seg = tk.base / (l_max + 1);   // start of the pair inside one l
+        for (int q = 0; q < 4; ++q) {
+            const int na = na0 + (q >> 1), nb = nb0 + (q & 1);
+            if (na < n && nb < n && (!diag || nb >= na)) {
+                const int off = diag ? na * n - (na * (na - 1)) / 2 + nb - na : na * n + nb;
+                c0_s[seg + off] = tk.base + off;
+                blk_s[seg + off] = tk.blk;
+            }
+        }
+    }
+    __syncthreads();
     const int ci = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (ci >= a.n_cent) return;
+    if (ci >= a.n_cent) return;   // warps are independent from here: only __syncwarp below
+    // SEQ: the warp walks the frames of its run in order and folds every spectrum into the
+    // timeSOAP sums against its ring (see soap_kernel); else one (centre, frame) per warp
+    const int t0 = SEQ ? blockIdx.y * a.seq_run : 0;
+    const int n_fr = SEQ ? min(a.n_frames - a.delay, t0 + a.seq_run) - t0 + a.delay : 1;
+    for (int fo = 0; fo < n_fr; ++fo) {
+    const int f = SEQ ? t0 + fo : (int)blockIdx.y;
     const double* __restrict__ gsum = a.gscr + ((size_t)f * a.n_cent + ci) * S * n_lm * n;
-    double* __restrict__ out = a.out + (long long)ci * a.stride_i + (long long)f * a.stride_f;
+    SpectrumSink sink;
+    sink.out = a.out ? a.out + (long long)ci * a.stride_i + (long long)f * a.stride_f : nullptr;
+    sink.ring = nullptr;
+    sink.csq = sink.dot = 0.0;
+    double* ring_sq = nullptr;
+    if (SEQ) {
+        double* base = a.ring + (((size_t)blockIdx.y * a.n_cent + ci) * a.delay +
+                                 (size_t)(f % a.delay)) * (size_t)(pl.n_feat + 1);
+        sink.ring = base;
+        ring_sq = base + pl.n_feat;
+        if (min(f / a.seq_run, (int)gridDim.y - 1) != (int)blockIdx.y) sink.out = nullptr;
+    }
 
     for (int l = 0; l <= l_max; ++l) {
         const int nm = 2 * l + 1, ncol = S * nm;
@@ -1148,7 +1291,7 @@ soap_spectrum_kernel(const SoapArgs a, const SpecTask* __restrict__ tasks, int n
                 o10 = fma(u.y, v.x, o10);
                 o11 = fma(u.y, v.y, o11);
             }
-            double* __restrict__ ob = out + tk.base + (size_t)l * tk.blk;
+            double* __restrict__ ob = lst + tk.base / (l_max + 1);
             const bool diag = zi == zj;
             const double res[4] = {o00, o01, o10, o11};
 #pragma unroll
@@ -1161,7 +1304,32 @@ soap_spectrum_kernel(const SoapArgs a, const SpecTask* __restrict__ tasks, int n
             }
         }
         __syncwarp();
+        // flush the staged outputs of this l in feature order (coalesced); ring loads first
+        if (sink.ring) {
+            for (int idx = lane; idx < n_l; idx += 32) {
+                const double v = lst[idx];
+                sink.csq = fma(v, v, sink.csq);
+                sink.dot = fma(v, sink.ring[c0_s[idx] + l * blk_s[idx]], sink.dot);
+            }
+            for (int idx = lane; idx < n_l; idx += 32)
+                sink.ring[c0_s[idx] + l * blk_s[idx]] = lst[idx];
+        }
+        if (sink.out)
+            for (int idx = lane; idx < n_l; idx += 32)
+                sink.out[c0_s[idx] + l * blk_s[idx]] = lst[idx];
+        __syncwarp();
     }
+    if (SEQ) {
+        const double csq = warp_sum(sink.csq), dot = warp_sum(sink.dot);
+        if (lane == 0) {
+            if (fo >= a.delay)
+                a.ts_out[(long long)ci * a.ts_ld + a.ts_col0 + (f - a.delay)] =
+                    soap_dist_from_sums(*ring_sq, csq, dot);
+            *ring_sq = csq;
+        }
+        __syncwarp();
+    }
+    }  // frame loop (SEQ)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1178,6 +1346,9 @@ struct SoapLayout {
     // list mode (soap_list_kernel): fused single-species kernel, periodic, >= 3 cells per axis
     int row_cap = 0;  // 0 = the main kernel searches by itself
     size_t off_rows = 0, off_rowcnt = 0, off_listflag = 0;
+    // frame-sequential mode (fused timeSOAP): sorted slot of every atom, per-warp rings
+    int seq_run = 0, n_runs = 0;
+    size_t off_slot_of = 0, off_ring = 0;
     size_t bytes = 0;
 };
 
@@ -1188,9 +1359,10 @@ static bool soap_split(int n_species, int n_max) {
 
 static double soap_radius(double r_cut) { return r_cut + std::sqrt(-2.0 * std::log(1e-3)); }
 
+// delay > 0: layout of the fused SOAP -> timeSOAP call (dsg_soap_timesoap)
 static int soap_layout(int n_frames, int n_atoms, int n_cent, int n_species, int n_max, int l_max,
                        const double* h_box, double r_cut, SoapLayout* L,
-                       std::vector<SoapFrame>* frames) {
+                       std::vector<SoapFrame>* frames, int delay = 0) {
     if (n_frames < 1 || n_frames > 65535)
         return set_error(DSG_ERR_INVALID_ARGUMENT, "n_frames=%d must be in [1, 65535] per batch",
                          n_frames);
@@ -1311,6 +1483,22 @@ static int soap_layout(int n_frames, int n_atoms, int n_cent, int n_species, int
         L->off_rowcnt = take(4 * fa * (size_t)(n_species + 1));
         L->off_listflag = take(4);
     }
+    if (delay > 0) {
+        if (delay >= n_frames)
+            return set_error(DSG_ERR_INVALID_ARGUMENT, "delay=%d must be below n_frames=%d", delay,
+                             n_frames);
+        // frame pairs per warp: long runs (the `delay` frames a run shares with the next one are
+        // computed twice) as long as the grid still has ~4 generations of resident warps
+        const long long pairs = n_frames - delay;
+        long long run = pairs * n_cent / kSeqGroup / (148LL * 16 * 4);
+        if (run > 64) run = 64;
+        if (run < 8LL * delay) run = 8LL * delay;
+        if (run > pairs) run = pairs;
+        L->seq_run = (int)run;
+        L->n_runs = (int)((pairs + run - 1) / run);
+        L->off_slot_of = take(4 * fa);
+        L->off_ring = take(8 * (size_t)L->n_runs * n_cent * delay * ((size_t)n_feat + 1));
+    }
     L->bytes = o;
     return DSG_OK;
 }
@@ -1358,16 +1546,19 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
                      int n_frames, int n_atoms, int n_cent, int n_species, const double* h_box,
                      double r_cut, int n_max, int l_max, const double* h_alphas,
                      const double* h_betas, void* d_ws, size_t ws_bytes, double* d_out,
-                     int64_t stride_i, int64_t stride_f, cudaStream_t st) {
+                     int64_t stride_i, int64_t stride_f, cudaStream_t st, int delay = 0,
+                     double* d_ts = nullptr, int64_t ts_ld = 0, int64_t ts_col0 = 0) {
     SoapLayout L;
     std::vector<SoapFrame> frames;
     int rc = soap_layout(n_frames, n_atoms, n_cent, n_species, n_max, l_max, h_box, r_cut, &L,
-                         &frames);
+                         &frames, delay);
     if (rc) return rc;
+    const bool seq = delay > 0;
+    if (seq && !d_ts) return set_error(DSG_ERR_INVALID_ARGUMENT, "d_timesoap is NULL");
     if (!d_ws || ws_bytes < L.bytes)
         return set_error(DSG_ERR_WORKSPACE_TOO_SMALL, "workspace has %zu bytes, %zu needed",
                          ws_bytes, L.bytes);
-    if (!d_pos || !d_species || !d_centres || !d_out || !h_alphas || !h_betas)
+    if (!d_pos || !d_species || !d_centres || (!d_out && !seq) || !h_alphas || !h_betas)
         return set_error(DSG_ERR_INVALID_ARGUMENT, "NULL pointer argument");
     char* ws = (char*)d_ws;
     SoapFrame* d_frames = (SoapFrame*)(ws + L.off_frames);
@@ -1381,6 +1572,7 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     int* sid = (int*)(ws + L.off_sid);
     int* cmap = (int*)(ws + L.off_cmap);
     int* tile = (int*)(ws + L.off_tile);
+    int* slot_of = seq ? (int*)(ws + L.off_slot_of) : nullptr;
 
     // ---- basis tables (host float64) ----
     const double eta = 0.5;
@@ -1457,7 +1649,7 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     rc = run_scan(cnt, L.total_cells, 1, start, tile, nullptr, st);
     if (rc) return rc;
     soap_scatter_kernel<<<agrid, 256, 0, st>>>(wpos, n_atoms, d_frames, cell_id, cnt, start, sx,
-                                               sy, sz, sid);
+                                               sy, sz, sid, slot_of);
     DSG_LAUNCH_CHECK("soap_scatter_kernel");
 
     // ---- main kernel ----
@@ -1485,6 +1677,15 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     a.out = d_out;
     a.stride_i = stride_i;
     a.stride_f = stride_f;
+    a.slot_of_atom = slot_of;
+    a.centres = d_centres;
+    a.n_frames = n_frames;
+    a.delay = delay;
+    a.seq_run = L.seq_run;
+    a.ring = seq ? (double*)(ws + L.off_ring) : nullptr;
+    a.ts_out = d_ts;
+    a.ts_ld = ts_ld;
+    a.ts_col0 = ts_col0;
     a.rows = nullptr;
     a.rowcnt = nullptr;
     a.row_cap = L.row_cap;
@@ -1533,8 +1734,13 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     while (warps_l > 1 && per_warp_l * warps_l + shared_tables > 227 * 1024) warps_l >>= 1;
     const size_t smem_l = per_warp_l * warps_l + shared_tables + DSG_SOAP_EXTRA_SMEM;
     // spectrum kernel: mixed coefficients of one l per warp
-    const size_t spec_bytes = 8 * (size_t)n_species * (2 * l_max + 1) * ((n_max + 1) & ~1);
-    if (smem > 227 * 1024 || (split && spec_bytes + 8 * (size_t)a.bmat_smem_doubles > 227 * 1024))
+    const size_t n_l_feat = (size_t)n_feat / (l_max + 1);   // outputs of one l, staged per warp
+    const size_t spec_bytes =
+        8 * ((((size_t)n_species * (2 * l_max + 1) * ((n_max + 1) & ~1)) + n_l_feat + 1) &
+             ~(size_t)1);
+    const size_t spec_block_bytes = 8 * n_l_feat;           // feature index + stride tables
+    if (smem > 227 * 1024 ||
+        (split && spec_bytes + spec_block_bytes + 8 * (size_t)a.bmat_smem_doubles > 227 * 1024))
         return set_error(DSG_ERR_UNSUPPORTED, "%zu bytes of shared memory per warp needed",
                          split ? spec_bytes : per_warp);
     // about 16 resident-block generations over the 148 SMs; runs of >= 1 slot per warp
@@ -1546,32 +1752,39 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     const int warps_needed = (n_atoms + spw - 1) / spw;
     dim3 grid((warps_needed + warps - 1) / warps, n_frames);
     dim3 grid_l((warps_needed + warps_l - 1) / warps_l, n_frames);
+    // frame-sequential grids (fused timeSOAP): one warp per (centre, run of frame pairs)
+    dim3 grid_q((n_atoms + warps * kSeqGroup - 1) / (warps * kSeqGroup), seq ? L.n_runs : 1);
+    dim3 grid_ql((n_atoms + warps_l * kSeqGroup - 1) / (warps_l * kSeqGroup), seq ? L.n_runs : 1);
+#define DSG_SOAP_LAUNCH_ONE(KERNEL, GRID, WARPS, SMEM)                                           \
+    do {                                                                                         \
+        DSG_CUDA_CHECK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            (int)(SMEM)));                                       \
+        KERNEL<<<GRID, (WARPS) * 32, SMEM, st>>>(a);                                             \
+    } while (0)
 #define DSG_SOAP_LAUNCH(LT, A, B, C, D)                                                          \
     do {                                                                                         \
         if (split) {                                                                             \
             if (a.list_role == 1) {                                                              \
-                DSG_CUDA_CHECK(cudaFuncSetAttribute(soap_kernel<LT, A, B, C, D, true, true>,     \
-                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                                    (int)smem_l));                               \
-                soap_kernel<LT, A, B, C, D, true, true><<<grid_l, warps_l * 32, smem_l, st>>>(a); \
+                DSG_SOAP_LAUNCH_ONE((soap_kernel<LT, A, B, C, D, true, true>), grid_l, warps_l,  \
+                                    smem_l);                                                     \
                 a.list_role = 2;                                                                 \
             }                                                                                    \
-            DSG_CUDA_CHECK(cudaFuncSetAttribute(soap_kernel<LT, A, B, C, D, true, false>,        \
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                                (int)smem));                                     \
-            soap_kernel<LT, A, B, C, D, true, false><<<grid, warps * 32, smem, st>>>(a);         \
+            DSG_SOAP_LAUNCH_ONE((soap_kernel<LT, A, B, C, D, true, false>), grid, warps, smem);  \
+        } else if (seq) {                                                                        \
+            if (a.list_role == 1) {                                                              \
+                DSG_SOAP_LAUNCH_ONE((soap_kernel<LT, A, B, C, D, false, true, true>), grid_ql,   \
+                                    warps_l, smem_l);                                            \
+                a.list_role = 2;                                                                 \
+            }                                                                                    \
+            DSG_SOAP_LAUNCH_ONE((soap_kernel<LT, A, B, C, D, false, false, true>), grid_q,       \
+                                warps, smem);                                                    \
         } else {                                                                                 \
             if (a.list_role == 1) {                                                              \
-                DSG_CUDA_CHECK(cudaFuncSetAttribute(soap_kernel<LT, A, B, C, D, false, true>,    \
-                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                                    (int)smem_l));                               \
-                soap_kernel<LT, A, B, C, D, false, true><<<grid_l, warps_l * 32, smem_l, st>>>(a); \
+                DSG_SOAP_LAUNCH_ONE((soap_kernel<LT, A, B, C, D, false, true>), grid_l, warps_l, \
+                                    smem_l);                                                     \
                 a.list_role = 2;   /* the same centres by the in-kernel search iff a row overflowed */ \
             }                                                                                    \
-            DSG_CUDA_CHECK(cudaFuncSetAttribute(soap_kernel<LT, A, B, C, D, false, false>,       \
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                                (int)smem));                                     \
-            soap_kernel<LT, A, B, C, D, false, false><<<grid, warps * 32, smem, st>>>(a);        \
+            DSG_SOAP_LAUNCH_ONE((soap_kernel<LT, A, B, C, D, false, false>), grid, warps, smem); \
         }                                                                                        \
     } while (0)
     if (l_max <= 4) DSG_SOAP_LAUNCH(4, 9, 0, 0, 0);
@@ -1587,6 +1800,7 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     else if (l_max <= 10) DSG_SOAP_LAUNCH(10, 21, 13, 5, 0);
     else DSG_SOAP_LAUNCH(12, 25, 17, 9, 0);
 #undef DSG_SOAP_LAUNCH
+#undef DSG_SOAP_LAUNCH_ONE
     DSG_LAUNCH_CHECK("soap_kernel");
     if (split) {
         std::vector<SpecTask> tasks;
@@ -1607,12 +1821,23 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
         DSG_CUDA_CHECK(cudaMemcpyAsync(d_tasks, tasks.data(), sizeof(SpecTask) * tasks.size(),
                                        cudaMemcpyHostToDevice, st));
         int sw = 4;  // warps per block, fewer if the coefficients of one l are large
-        while (sw > 1 && sw * spec_bytes + 8 * (size_t)a.bmat_smem_doubles > 227 * 1024) --sw;
-        const size_t ssm = sw * spec_bytes + 8 * (size_t)a.bmat_smem_doubles;
-        DSG_CUDA_CHECK(cudaFuncSetAttribute(soap_spectrum_kernel,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
-        dim3 sgrid((n_cent + sw - 1) / sw, n_frames);
-        soap_spectrum_kernel<<<sgrid, sw * 32, ssm, st>>>(a, d_tasks, L.n_tasks);
+        while (sw > 1 &&
+               sw * spec_bytes + spec_block_bytes + 8 * (size_t)a.bmat_smem_doubles > 227 * 1024)
+            --sw;
+        const size_t ssm = sw * spec_bytes + spec_block_bytes + 8 * (size_t)a.bmat_smem_doubles;
+        if (seq) {
+            DSG_CUDA_CHECK(cudaFuncSetAttribute(soap_spectrum_kernel<true>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)ssm));
+            dim3 sgrid((n_cent + sw - 1) / sw, L.n_runs);
+            soap_spectrum_kernel<true><<<sgrid, sw * 32, ssm, st>>>(a, d_tasks, L.n_tasks);
+        } else {
+            DSG_CUDA_CHECK(cudaFuncSetAttribute(soap_spectrum_kernel<false>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)ssm));
+            dim3 sgrid((n_cent + sw - 1) / sw, n_frames);
+            soap_spectrum_kernel<false><<<sgrid, sw * 32, ssm, st>>>(a, d_tasks, L.n_tasks);
+        }
         DSG_LAUNCH_CHECK("soap_spectrum_kernel");
     }
     return DSG_OK;
@@ -1656,6 +1881,44 @@ extern "C" int dsg_soap(const void* d_pos, int pos_dtype, const int32_t* d_speci
         return soap_impl<double>((const double*)d_pos, d_species, d_centres, n_frames, n_atoms,
                                  n_cent, n_species, h_box, r_cut, n_max, l_max, h_alphas, h_betas,
                                  d_workspace, workspace_bytes, d_out, stride_i, stride_f, st);
+    return set_error(DSG_ERR_INVALID_ARGUMENT, "pos_dtype=%d is neither DSG_F32 nor DSG_F64",
+                     pos_dtype);
+}
+
+extern "C" int dsg_soap_timesoap_workspace_bytes(int n_frames, int n_atoms, int n_cent,
+                                                 int n_species, int n_max, int l_max,
+                                                 const double* h_box, double r_cut, int delay,
+                                                 size_t* bytes_out) {
+    if (!bytes_out) return set_error(DSG_ERR_INVALID_ARGUMENT, "bytes_out is NULL");
+    if (delay < 1) return set_error(DSG_ERR_INVALID_ARGUMENT, "delay=%d must be >= 1", delay);
+    SoapLayout L;
+    int rc = soap_layout(n_frames, n_atoms, n_cent, n_species, n_max, l_max, h_box, r_cut, &L,
+                         nullptr, delay);
+    if (rc) return rc;
+    *bytes_out = L.bytes;
+    return DSG_OK;
+}
+
+extern "C" int dsg_soap_timesoap(const void* d_pos, int pos_dtype, const int32_t* d_species,
+                                 const int32_t* d_centres, int n_frames, int n_atoms, int n_cent,
+                                 int n_species, const double* h_box, double r_cut, int n_max,
+                                 int l_max, const double* h_alphas, const double* h_betas,
+                                 int delay, void* d_workspace, size_t workspace_bytes,
+                                 double* d_timesoap, int64_t ts_ld, int64_t ts_col0,
+                                 double* d_soap_out, int64_t stride_i, int64_t stride_f,
+                                 void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (delay < 1) return set_error(DSG_ERR_INVALID_ARGUMENT, "delay=%d must be >= 1", delay);
+    if (pos_dtype == DSG_F32)
+        return soap_impl<float>((const float*)d_pos, d_species, d_centres, n_frames, n_atoms,
+                                n_cent, n_species, h_box, r_cut, n_max, l_max, h_alphas, h_betas,
+                                d_workspace, workspace_bytes, d_soap_out, stride_i, stride_f, st,
+                                delay, d_timesoap, ts_ld, ts_col0);
+    if (pos_dtype == DSG_F64)
+        return soap_impl<double>((const double*)d_pos, d_species, d_centres, n_frames, n_atoms,
+                                 n_cent, n_species, h_box, r_cut, n_max, l_max, h_alphas, h_betas,
+                                 d_workspace, workspace_bytes, d_soap_out, stride_i, stride_f, st,
+                                 delay, d_timesoap, ts_ld, ts_col0);
     return set_error(DSG_ERR_INVALID_ARGUMENT, "pos_dtype=%d is neither DSG_F32 nor DSG_F64",
                      pos_dtype);
 }

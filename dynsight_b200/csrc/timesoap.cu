@@ -10,22 +10,7 @@
 
 namespace dsg {
 
-constexpr unsigned kFullTs = 0xffffffffu;
 constexpr int kTsWarps = 4;
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFullTs, v, off);
-    return v;
-}
-
-// timesoap.py:54-58 + :118-127.  A zero-norm vector normalises to the zero vector => cos = 0.
-__device__ __forceinline__ double soap_dist_from_sums(double n1sq, double n2sq, double dot) {
-    double c = 0.0;
-    if (n1sq > 0.0 && n2sq > 0.0) c = dot / (sqrt(n1sq) * sqrt(n2sq));
-    c = fmin(1.0, fmax(-1.0, c));
-    return sqrt(fmax(0.0, 2.0 - 2.0 * c));
-}
 
 struct TsArgs {
     const double* soap;

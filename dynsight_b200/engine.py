@@ -681,6 +681,77 @@ def soap_power_spectrum(
     return out
 
 
+def soap_timesoap(
+    pos: torch.Tensor,
+    species: torch.Tensor,
+    centres: torch.Tensor,
+    box: np.ndarray | torch.Tensor | None,
+    r_cut: float,
+    n_max: int,
+    l_max: int,
+    delay: int = 1,
+    n_species: int | None = None,
+    out: torch.Tensor | None = None,
+    col0: int = 0,
+    soap_out: torch.Tensor | None = None,
+    frame0: int = 0,
+) -> torch.Tensor:
+    """timeSOAP of a batch of frames straight from positions (``dsg_soap_timesoap``): the SOAP
+    spectrum of every frame is folded into the distance to the spectrum ``delay`` frames earlier
+    inside the spectrum epilogue; the spectra are not written unless ``soap_out`` is given.
+
+    Returns / fills ``out[:, col0 : col0 + F - delay]`` (n_centres, >= col0 + F - delay) float64.
+    Arguments as :func:`soap_power_spectrum`."""
+    from dynsight_b200 import soap_basis
+
+    lib = _lib.load()
+    _require_cuda(pos, "pos")
+    _require_cuda(species, "species")
+    _require_cuda(centres, "centres")
+    if species.dtype != torch.int32 or centres.dtype != torch.int32:
+        msg = "species and centres must be int32"
+        raise TypeError(msg)
+    n_frames, n_atoms, _ = pos.shape
+    n_cent = centres.numel()
+    if delay < 1 or delay >= n_frames:
+        msg = "delay value outside bounds"
+        raise ValueError(msg)
+    if n_species is None:
+        n_species = int(species.max().item()) + 1
+    alphas, betas = soap_basis.gto_basis(float(r_cut), int(n_max), int(l_max))
+    n_feat = soap_basis.n_features(n_species, n_max, l_max)
+    h_box = None if box is None else _host_box(box, n_frames)
+    box_ptr = None if h_box is None else h_box.ctypes.data
+    ws_bytes = ctypes.c_size_t(0)
+    _lib.check(
+        lib.dsg_soap_timesoap_workspace_bytes(
+            n_frames, n_atoms, n_cent, n_species, n_max, l_max, box_ptr, float(r_cut), int(delay),
+            ctypes.byref(ws_bytes),
+        )
+    )  # fmt: skip
+    workspace = torch.empty(ws_bytes.value, dtype=torch.uint8, device=pos.device)
+    if out is None:
+        out = torch.empty((n_cent, n_frames - delay), dtype=torch.float64, device=pos.device)
+        col0 = 0
+    soap_ptr, s_i, s_f = None, 0, 0
+    if soap_out is not None:
+        view = soap_out[:, frame0 : frame0 + n_frames]
+        if view.shape != (n_cent, n_frames, n_feat) or view.stride(2) != 1:
+            msg = f"soap_out has shape {tuple(soap_out.shape)}; expected (n_centres, >= F, {n_feat})"
+            raise ValueError(msg)
+        soap_ptr, s_i, s_f = view.data_ptr(), view.stride(0), view.stride(1)
+    _lib.check(
+        lib.dsg_soap_timesoap(
+            pos.data_ptr(), _dtype_code(pos), species.data_ptr(), centres.data_ptr(), n_frames,
+            n_atoms, n_cent, n_species, box_ptr, float(r_cut), int(n_max), int(l_max),
+            alphas.ctypes.data, betas.ctypes.data, int(delay), workspace.data_ptr(),
+            ws_bytes.value, out.data_ptr(), out.stride(0), int(col0), soap_ptr, s_i, s_f,
+            _stream_ptr(),
+        )
+    )  # fmt: skip
+    return out
+
+
 def _mean_row_len(batch: NeighborBatch) -> int:
     """Mean neighbours per (atom, frame) from sizes already known on the host (0 = unknown)."""
     cells = batch.n_frames * batch.n_cent

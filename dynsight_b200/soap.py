@@ -242,8 +242,8 @@ def timesoap(soap: NDArray[np.float64], delay: int = 1) -> NDArray[np.float64]:
 
 class TimesoapJob:
     """timeSOAP straight from positions, fed one device batch at a time (batches overlap by
-    ``delay`` frames): SOAP of the batch, reduced to timeSOAP on the device.  The (N, F, C) SOAP
-    tensor of the trajectory never exists."""
+    ``delay`` frames) through the fused SOAP -> timeSOAP kernels (``engine.soap_timesoap``).  No
+    SOAP tensor exists, neither of the trajectory nor of a batch."""
 
     def __init__(self, universe: Any, soaprcut: float, soapnmax: int = 8, soaplmax: int = 8,
                  delay: int = 1, selection: str = "all", soap_respectpbc: bool = True,
@@ -270,20 +270,27 @@ class TimesoapJob:
         self.sel_all = frames.Selection(self.sel_ix, self.n_all)
 
     def default_batch_frames(self) -> int:
+        # per frame: the primitive sums of split mode (several species / n_max > 8) or the
+        # neighbour rows of list mode (~1 KB per atom); the spectra themselves are never stored
         scratch = soap_basis.scratch_doubles(self.n_species, self.n_max, self.l_max)
-        per_frame = max(1, self.n_cent) * (self.n_feat + scratch) * 8.0
-        return int(max(self.delay + 1, min(512, 16e9 // per_frame)))
+        per_frame = max(1, self.n_cent) * scratch * 8.0 + len(self.sel_ix) * 1100.0
+        free, _total = torch.cuda.mem_get_info(frames.device())
+        ring = max(1, self.n_cent) * self.delay * (self.n_feat + 1) * 8.0
+        budget = max(0.45 * free - ring, 1e9)
+        # batches overlap by `delay` frames (computed twice): at least 8 pairs per batch if they fit
+        return int(max(self.delay + 1, min(512, budget // per_frame)))
 
     def process(self, fb: frames.FrameBatch) -> None:
         if self.n_cent == 0:
             return
         box = frames.soap_boxes(fb, self.periodic)
         pos = fb.select(self.sel_all, self.n_all)
-        spectra = engine.soap_power_spectrum(
+        # fused: every spectrum is folded into the distance to the one `delay` frames earlier in
+        # the spectrum epilogue (ring in L2); nothing of size (N, F, C) is written
+        engine.soap_timesoap(
             pos, self.species_t, self.centres_t, box, self.r_cut, self.n_max, self.l_max,
-            n_species=self.n_species,
+            delay=self.delay, n_species=self.n_species, out=self.out, col0=fb.seq0,
         )  # fmt: skip
-        engine.timesoap_device(spectra, self.delay, out=self.out, col0=fb.seq0)
 
     def finish(self) -> torch.Tensor:
         return self.out

@@ -255,6 +255,27 @@ int dsg_soap(const void* d_pos, int pos_dtype, const int32_t* d_species, const i
              void* d_workspace, size_t workspace_bytes, double* d_out, int64_t stride_i,
              int64_t stride_f, void* stream);
 
+/* SOAP fused with timeSOAP (replaces the chain Trj.get_soap -> Insight.get_angular_velocity ->
+ * timesoap, trajectory.py:267-320 / insight.py:136-155 / timesoap.py:130-179, for callers that want
+ * timeSOAP only): the spectrum of frame f is folded into the distance to the spectrum of frame
+ * f - delay inside the spectrum epilogue.  A warp owns one centre and a run of frame pairs; the
+ * `delay` previous vectors live in its ring (a workspace region rewritten every `delay` frames, i.e.
+ * L2 traffic), so the (n_cent, n_frames, n_feat) spectra never exist:
+ *   d_timesoap[i*ts_ld + ts_col0 + t] = timesoap value of the pair (t, t + delay), t in
+ *   [0, n_frames - delay), float64 -- the (n_centers, n_frames - delay) layout of timesoap().
+ * d_soap_out may be NULL; if given, the spectra are written as well (same layout as dsg_soap).
+ * Same arithmetic as dsg_soap followed by dsg_timesoap (equal to rounding). */
+int dsg_soap_timesoap_workspace_bytes(int n_frames, int n_atoms, int n_cent, int n_species,
+                                      int n_max, int l_max, const double* h_box, double r_cut,
+                                      int delay, size_t* bytes_out);
+
+int dsg_soap_timesoap(const void* d_pos, int pos_dtype, const int32_t* d_species,
+                      const int32_t* d_centres, int n_frames, int n_atoms, int n_cent,
+                      int n_species, const double* h_box, double r_cut, int n_max, int l_max,
+                      const double* h_alphas, const double* h_betas, int delay, void* d_workspace,
+                      size_t workspace_bytes, double* d_timesoap, int64_t ts_ld, int64_t ts_col0,
+                      double* d_soap_out, int64_t stride_i, int64_t stride_f, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Spatial average (replaces analysis/spatial_average.py:31-63, processframe: FastNS pairs, then
  * np.mean over each particle's neighbours and itself -- SURVEY.md section 8f row 1).

@@ -16,7 +16,7 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
 nf = int(sys.argv[3]) if len(sys.argv) > 3 else 8
 dev = torch.device("cuda")
 g = torch.Generator(device=dev).manual_seed(0)
-if what == "soap3":  # cfg4-like: 3 species, l_max = 10, metal density
+if what in ("soap3", "fused3"):  # cfg4-like: 3 species, l_max = 10, metal density
     box_l = (n / 0.0857) ** (1 / 3)
     r_cut = 5.0
 elif what in ("neigh_fluid", "pair_fluid", "spavg", "spavg324"):
@@ -26,6 +26,9 @@ else:
     box_l = (n / 0.0334) ** (1 / 3)
     r_cut = 5.0
 pos = (torch.rand((nf, n, 3), device=dev, generator=g, dtype=torch.float64) * box_l).float()
+if what.startswith("fused"):   # the fused kernels walk a trajectory: frames must be continuous
+    step = 0.1 * torch.randn((nf, n, 3), device=dev, generator=g, dtype=torch.float64).cumsum(0)
+    pos = torch.remainder(pos[:1].double() + step, box_l).float()
 pos.clamp_(max=float(np.nextafter(np.float32(box_l), np.float32(0))))
 box = np.full(3, np.float32(box_l), dtype=np.float32)
 sp = torch.zeros(n, dtype=torch.int32, device=dev)
@@ -35,6 +38,11 @@ for it in range(3):
     e0.record()
     if what == "soap":
         out = engine.soap_power_spectrum(pos, sp, cen, box, 5.0, 8, 8)
+    elif what == "fused":
+        out = engine.soap_timesoap(pos, sp, cen, box, 5.0, 8, 8, delay=1)
+    elif what == "fused3":
+        sp3 = (torch.arange(n, device=dev, dtype=torch.int32) * 7919 % 3).to(torch.int32)
+        out = engine.soap_timesoap(pos, sp3, cen, box, 5.0, 8, 10, delay=1, n_species=3)
     elif what == "soap3":
         sp3 = (torch.arange(n, device=dev, dtype=torch.int32) * 7919 % 3).to(torch.int32)
         out = engine.soap_power_spectrum(pos, sp3, cen, box, 5.0, 8, 10, n_species=3)

@@ -371,3 +371,67 @@ def test_multi_species_block_order_and_orientation_derived():
             assert err < 1e-9 * scale, (l, err)
             assert np.abs(blocks[(0, 0)][l] - np.outer(a, a)).max() < 1e-9 * scale
             assert np.abs(blocks[(1, 1)][l] - np.outer(b, b)).max() < 1e-9 * scale
+
+
+# ---------------------------------------------------------------------------------------------
+# fused SOAP -> timeSOAP (dsg_soap_timesoap): frame-sequential warps, ring of `delay` vectors
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize(
+    ("n_species", "n_max", "l_max", "periodic"),
+    [(1, 8, 8, True), (1, 4, 4, True), (1, 6, 6, False), (3, 8, 10, True), (2, 4, 3, True),
+     (1, 12, 5, True)],
+)
+def test_fused_timesoap_equals_two_kernel_path(n_species, n_max, l_max, periodic):
+    """engine.soap_timesoap == soap_power_spectrum + timesoap_device (to rounding) for the fused
+    single-species kernels (list mode and in-kernel search), split mode (several species,
+    n_max > 8), delays 1..3, runs that split the frame axis, a subset of centres, and with the
+    spectra requested as well."""
+    from dynsight_b200 import engine
+
+    rng = np.random.default_rng(17 + n_species + n_max)
+    n, n_frames = 260, 23
+    box = np.array([27.0, 28.5, 26.5], dtype=np.float32)
+    pos = (rng.random((1, n, 3)) * box + rng.normal(0, 0.15, (n_frames, n, 3)).cumsum(0)).astype(
+        np.float32)
+    dpos = torch.as_tensor(pos).cuda()
+    species = torch.as_tensor(rng.integers(0, n_species, n).astype(np.int32)).cuda()
+    centres = torch.as_tensor(np.sort(rng.choice(n, 37, replace=False)).astype(np.int32)).cuda()
+    bx = box if periodic else None
+    ref = engine.soap_power_spectrum(dpos, species, centres, bx, 4.5, n_max, l_max,
+                                     n_species=n_species)
+    for delay in (1, 2, 3):
+        want = engine.timesoap_device(ref, delay)
+        got = engine.soap_timesoap(dpos, species, centres, bx, 4.5, n_max, l_max, delay=delay,
+                                   n_species=n_species)
+        assert got.shape == want.shape == (37, n_frames - delay)
+        # two launches sum the neighbours in different orders (atomic scatter inside a cell), and
+        # sqrt(2 - 2 cos) amplifies 1e-13 on the spectra to ~1e-10 on a distance of 0.05
+        assert float((got - want).abs().max()) < 2e-9
+    spectra = torch.full_like(ref, float("nan"))
+    got = engine.soap_timesoap(dpos, species, centres, bx, 4.5, n_max, l_max, delay=2,
+                               n_species=n_species, soap_out=spectra)
+    scale = ref.abs().amax(dim=-1, keepdim=True)
+    assert float(((spectra - ref).abs() / scale).max()) < 1e-9   # summation order, see above
+    assert float((got - engine.timesoap_device(ref, 2)).abs().max()) < 2e-9
+
+
+def test_fused_timesoap_vs_oracle_and_api():
+    """The fused path against the oracle chain (SOAP restatement -> timesoap.py restatement) and
+    through timesoap_from_trajectory with small overlapping batches."""
+    from dynsight_b200 import soap as dsoap
+    from dynsight_b200.universe import ArrayUniverse
+
+    rng = np.random.default_rng(5)
+    n, n_frames = 150, 9
+    box = np.array([26.5, 27.0, 28.0], dtype=np.float32)
+    pos = (rng.random((1, n, 3)) * box + rng.normal(0, 0.2, (n_frames, n, 3)).cumsum(0)).astype(
+        np.float32)
+    dims = np.tile(np.concatenate([box, [90, 90, 90]]).astype(np.float32), (n_frames, 1))
+    uni = ArrayUniverse(pos, dims, names=["O"] * n, types=["O"] * n)
+    cent = np.arange(0, n, 5)
+    want_soap = so.soap_trajectory(pos, np.full(n, 8), cent, dims[:, :3].astype(float), 5.0, 8, 8)
+    for delay, batch in ((1, 4), (2, 5), (1, None)):
+        want = to.timesoap(want_soap, delay)
+        got = dsoap.timesoap_from_trajectory(uni, 5.0, 8, 8, delay=delay, batch_frames=batch,
+                                             as_numpy=True)[cent]
+        assert np.all(np.abs(got - want) <= 1e-5 * np.abs(want) + 1e-7)
