@@ -274,7 +274,9 @@ class TimesoapJob:
         # neighbour rows of list mode (~1 KB per atom); the spectra themselves are never stored
         scratch = soap_basis.scratch_doubles(self.n_species, self.n_max, self.l_max)
         per_frame = max(1, self.n_cent) * scratch * 8.0 + len(self.sel_ix) * 1100.0
-        free, _total = torch.cuda.mem_get_info(frames.device())
+        # memory not held by torch's allocator (cudaMemGetInfo costs ~10 ms per call: not here)
+        dev = frames.device()
+        free = torch.cuda.get_device_properties(dev).total_memory - torch.cuda.memory_reserved(dev)
         ring = max(1, self.n_cent) * self.delay * (self.n_feat + 1) * 8.0
         budget = max(0.45 * free - ring, 1e9)
         # batches overlap by `delay` frames (computed twice): at least 8 pairs per batch if they fit

@@ -1,29 +1,39 @@
-"""Wall-clock breakdown of the public-API calls the bench's e2e leg makes."""
-import sys, time
+"""Where the end-to-end time of pipeline.descriptors_from_trajectory goes (run alone or under
+torchrun: python -m torch.distributed.run --nproc-per-node N scripts/e2e_breakdown.py)."""
+import os, sys, time
 from pathlib import Path
 import numpy as np, torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-from dynsight_b200 import lens as dlens, soap as dsoap
+from dynsight_b200 import pipeline, frames
 from dynsight_b200.universe import ArrayUniverse
 
-n, bsz = 100_000, 32
+rank = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(rank)
+n, nf = 100_000, 33
 box_l = (n / 0.0334) ** (1 / 3)
-rng = np.random.default_rng(0)
-host = torch.empty((bsz + 1, n, 3), dtype=torch.float32, pin_memory=True)
+rng = np.random.default_rng(rank)
+pos = torch.empty((nf, n, 3), dtype=torch.float32, pin_memory=True)
 cur = rng.random((n, 3)) * box_l
-for f in range(bsz + 1):
+for f in range(nf):
     cur = np.mod(cur + rng.normal(0, 0.1, cur.shape), box_l)
-    host[f] = torch.from_numpy(cur.astype(np.float32))
-host.clamp_(max=float(np.nextafter(np.float32(box_l), np.float32(0))))
-dims = np.tile(np.array([box_l] * 3 + [90] * 3, dtype=np.float32), (bsz + 1, 1))
-uni = ArrayUniverse(host.numpy(), dims, names=["O"] * n, types=["O"] * n)
-def t(label, fn):
-    torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize()
-    print(f"{label:40s} {1e3 * (time.perf_counter() - t0):8.2f} ms"); return r
-for it in range(3):
-    print("--- iteration", it)
-    d = t("compute_lens_device", lambda: dlens.compute_lens_device(uni, 5.0, 1))
-    t("  lens .cpu().numpy()", lambda: d.cpu().numpy())
-    s = t("timesoap_from_trajectory (device)", lambda: dsoap.timesoap_from_trajectory(uni, 5.0, 8, 8, delay=1))
-    t("  tsoap .cpu().numpy()", lambda: s.cpu().numpy())
-    t("compute_lens (numpy out)", lambda: dlens.compute_lens(uni, 5.0, 1))
+    pos[f] = torch.from_numpy(np.minimum(cur, np.nextafter(np.float32(box_l), np.float32(0))).astype(np.float32))
+dims = np.tile(np.asarray([box_l] * 3 + [90] * 3, dtype=np.float32), (nf, 1))
+uni = ArrayUniverse(pos.numpy(), dims, names=["O"] * n, types=["O"] * n)
+def call():
+    return pipeline.descriptors_from_trajectory(uni, lens_r_cut=5.0, soap_r_cut=5.0, coord_number=True)
+for _ in range(2): call()
+torch.cuda.synchronize()
+for it in range(4):
+    t0 = time.perf_counter(); res = call(); t1 = time.perf_counter()
+    print(f"rank {rank} pipeline {1e3*(t1-t0):.2f} ms", flush=True)
+# pieces
+d = torch.empty((nf, n, 3), dtype=torch.float32, device="cuda")
+torch.cuda.synchronize(); t0 = time.perf_counter(); d.copy_(pos, non_blocking=True); torch.cuda.synchronize(); t1 = time.perf_counter()
+print(f"rank {rank} h2d 39.6MB {1e3*(t1-t0):.2f} ms")
+r = torch.empty((n, 32), dtype=torch.float64, device="cuda")
+torch.cuda.synchronize(); t0 = time.perf_counter(); h = frames.to_host(r); t1 = time.perf_counter()
+print(f"rank {rank} d2h 25.6MB {1e3*(t1-t0):.2f} ms")
+import cProfile, pstats
+pr = cProfile.Profile(); pr.enable(); call(); pr.disable()
+if rank == 0:
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
