@@ -49,6 +49,9 @@ constexpr int kOpenCellsPerAxis = 32;
 #define DSG_SOAP_MIN_BLOCKS_L10 4
 #endif
 // Build-time switches of the measured variants (defaults = what ships)
+#ifndef DSG_SOAP_MMA
+#define DSG_SOAP_MMA 1             // phase C on the fp64 tensor path (DMMA.8x8x4), see soap_kernel
+#endif
 #ifndef DSG_SOAP_PACK
 #define DSG_SOAP_PACK 1            // l_max = 8: packed rows, 20 accumulator slots per lane
 #endif
@@ -59,7 +62,11 @@ constexpr int kOpenCellsPerAxis = 32;
 #define DSG_SOAP_LIST_WARPS 4      // warps per block of the list-mode kernel ...
 #endif
 #ifndef DSG_SOAP_LIST_BLOCKS
+#if DSG_SOAP_MMA
+#define DSG_SOAP_LIST_BLOCKS 3     // ... and its resident blocks per SM (168 registers)
+#else
 #define DSG_SOAP_LIST_BLOCKS 4     // ... and its resident blocks per SM (128 registers)
+#endif
 #endif
 #ifndef DSG_SOAP_TILE_SPECTRUM
 #define DSG_SOAP_TILE_SPECTRUM 1   // fused epilogue: 2x2 register tiles for n_max = 8
@@ -76,6 +83,7 @@ constexpr int kOpenCellsPerAxis = 32;
 #ifndef DSG_SOAP_SEQ_GROUP
 #define DSG_SOAP_SEQ_GROUP 1
 #endif
+
 constexpr int kSeqGroup = DSG_SOAP_SEQ_GROUP;  // centres a warp of the frame-sequential kernels walks per frame
 constexpr int kListCap = 32;     // displacement list entries per warp
 constexpr int kCellTab = 32;     // (cell range, shift) entries resolved per pass
@@ -411,6 +419,38 @@ __device__ __forceinline__ double exp_scaled(double g, double s, const double* _
     return __hiloint2double(__double2hiint(r) + ((kq >> kExpTabLog2) << 20), __double2loint(r));
 }
 
+// NE exponentials of the same s, written stage by stage: ptxas keeps roughly the source order, so
+// the NE dependency chains advance together (each stage is NE independent fp64 operations) instead
+// of two at a time -- the tensor-path loop is bound by the latency of these chains, not by a pipe.
+template <int NE>
+__device__ __forceinline__ void exp_scaled_batch(const double (&g)[NE], double s,
+                                                 const double* __restrict__ tab, double (&e)[NE]) {
+    const double magic = 6755399441055744.0;
+    double tn[NE], v[NE], p[NE], tv[NE];
+#pragma unroll
+    for (int i = 0; i < NE; ++i) tn[i] = fma(g[i], s, magic);
+#pragma unroll
+    for (int i = 0; i < NE; ++i) v[i] = fma(g[i], s, magic - tn[i]);
+#pragma unroll
+    for (int i = 0; i < NE; ++i) tv[i] = tab[__double2loint(tn[i]) & (kExpTab - 1)];
+#pragma unroll
+    for (int i = 0; i < NE; ++i) p[i] = fma(kExpPoly[4], v[i], kExpPoly[3]);
+#pragma unroll
+    for (int i = 0; i < NE; ++i) p[i] = fma(p[i], v[i], kExpPoly[2]);
+#pragma unroll
+    for (int i = 0; i < NE; ++i) p[i] = fma(p[i], v[i], kExpPoly[1]);
+#pragma unroll
+    for (int i = 0; i < NE; ++i) p[i] = fma(p[i], v[i], kExpPoly[0]);
+#pragma unroll
+    for (int i = 0; i < NE; ++i) p[i] = fma(p[i], v[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+        const double r = tv[i] * p[i];
+        const int kq = __double2loint(tn[i]);
+        e[i] = __hiloint2double(__double2hiint(r) + ((kq >> kExpTabLog2) << 20), __double2loint(r));
+    }
+}
+
 // Layout of one neighbour's harmonics row: the block of angular momentum l (2l+1 values, padded
 // to even length) starts at harm_off(LT, l); element (l, m) sits at harm_off + l + m.  l = 0 is
 // not used (its single value is 1 and that channel is accumulated separately).  For LT = 8 the
@@ -450,17 +490,29 @@ __host__ __device__ constexpr int harm_len(int lt) {
 // groups never share a bank) and every lane accumulates exactly 20 slots instead of 17 + 9.
 constexpr int kPackSlots = 20;
 __host__ __device__ constexpr int pack_size0(int g) { return 17 - 2 * g; }
-template <int LT, bool PK>
+// Row layouts: natural / bank-ordered blocks (kRowBlocks), packed l_max = 8 rows (kRowPacked), and
+// the dense rows of the tensor path (kRowDense: block l at l^2 - 1, no padding, l = 0 not stored)
+enum RowLayout : int { kRowBlocks = 0, kRowPacked = 1, kRowDense = 2 };
+template <int LT, int LAY>
 __host__ __device__ constexpr int hoff(int l) {
-    if (!PK) return harm_off(LT, l);
+    if (LAY == kRowDense) return l * l - 1;
+    if (LAY == kRowBlocks) return harm_off(LT, l);
     return l >= 5 ? (8 - l) * kPackSlots : (l - 1) * kPackSlots + pack_size0(l - 1);
 }
+// tensor path: 8-column tiles of the (2l+1) values of one l
+__host__ __device__ constexpr int mma_tiles(int l) { return (2 * l + 1 + 7) / 8; }
+__host__ __device__ constexpr int mma_tile_base(int l) {
+    int b = 0;
+    for (int i = 1; i < l; ++i) b += mma_tiles(i);
+    return b;
+}
+__host__ __device__ constexpr int mma_row_stride(int lt) { return (lt * (lt + 2)) | 1; }
 
 // Phase B: un-normalised regular solid harmonics of one displacement:
 //   rt[off(l) + l + m] = S_l^m(z, r2) * A_m(x, y),   rt[off(l) + l - m] = S_l^m * B_m   (m > 0)
 //   A_m + i B_m = (x + i y)^m ;  S_m^m = (2m-1)!!, S_{m+1}^m = (2m+1) z S_m^m,
 //   S_l^m = ((2l-1) z S_{l-1}^m - (l+m-1) r2 S_{l-2}^m) / (l-m)
-template <int LT, bool PK>
+template <int LT, int LAY>
 __device__ __forceinline__ void solid_harmonics(double x, double y, double z, double r2,
                                                 double* __restrict__ rt) {
     double am = 1.0, bm = 0.0, dfact = 1.0;
@@ -474,13 +526,13 @@ __device__ __forceinline__ void solid_harmonics(double x, double y, double z, do
         }
         double s0 = dfact;  // S_m^m
         if (m > 0) {
-            rt[hoff<LT, PK>(m) + 2 * m] = s0 * am;
-            rt[hoff<LT, PK>(m)] = s0 * bm;
+            rt[hoff<LT, LAY>(m) + 2 * m] = s0 * am;
+            rt[hoff<LT, LAY>(m)] = s0 * bm;
         }
         if (m + 1 <= LT) {
             double s1 = (double)(2 * m + 1) * z * s0;  // S_{m+1}^m
             {
-                const int o = hoff<LT, PK>(m + 1) + m + 1;
+                const int o = hoff<LT, LAY>(m + 1) + m + 1;
                 rt[o + m] = s1 * am;
                 if (m > 0) rt[o - m] = s1 * bm;
             }
@@ -489,7 +541,7 @@ __device__ __forceinline__ void solid_harmonics(double x, double y, double z, do
                 const double inv = 1.0 / (double)(l - m);  // compile-time constant after unrolling
                 const double s2 =
                     ((double)(2 * l - 1) * z * s1 - (double)(l + m - 1) * r2 * s0) * inv;
-                const int o = hoff<LT, PK>(l) + l;
+                const int o = hoff<LT, LAY>(l) + l;
                 rt[o + m] = s2 * am;
                 if (m > 0) rt[o - m] = s2 * bm;
                 s0 = s1;
@@ -559,6 +611,14 @@ __device__ __forceinline__ void accumulate_packed(Acc<kPackSlots>& a, double e0,
     a.v[18] = fma(e1, v.x, a.v[18]);
     a.v[19] = fma(e1, v.y, a.v[19]);
 #endif
+}
+
+// C (8x8) += A (8x4) * B (4x8) on the fp64 tensor path.  Fragments (PTX m8n8k4): A[row = lane >> 2]
+// [col = lane & 3], B[row = lane & 3][col = lane >> 2], C[row = lane >> 2][cols 2 (lane & 3) + {0, 1}].
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
 }
 
 __device__ __forceinline__ void store_packed(const Acc<kPackSlots>& a, int g, int k, int n,
@@ -756,7 +816,17 @@ __global__ void __launch_bounds__(
                : (S0 <= 21 ? DSG_SOAP_MIN_BLOCKS_L10 : 4))
 soap_kernel(const SoapArgs a) {
     static_assert(!(SEQ && SPLIT), "frame-sequential accumulation is only the fused kernel");
-    constexpr bool PK = LT == 8 && S0 == kPackSlots;  // packed l_max = 8 rows (see hoff)
+    // MM: phase C as tensor-core products G_l (8 radial x 2l+1) += E_l (8 x 4 neighbours) * Y_l
+    // (4 x 2l+1): lane (k = lane >> 2, j = lane & 3) evaluates the Gaussians of radial index k on
+    // neighbour j of each group of four -- every needed exponential exactly once, as before --
+    // and they go straight into the A fragment; the harmonics are the B fragment (one 64-bit
+    // shared load per 8x8x4 tile and lane instead of one 128-bit load per two FMAs: the scalar
+    // loop moved 20 doubles per lane and neighbour through the shared-memory pipe, which ran at
+    // 82 % of its peak).  2l+1 is padded to 8-column tiles (the pad columns read the next block
+    // of the row and are discarded), l = 0 stays a scalar sum.
+    constexpr bool MM = DSG_SOAP_MMA != 0;
+    [[maybe_unused]] constexpr bool PK = !MM && LT == 8 && S0 == kPackSlots;  // packed rows (see hoff)
+    constexpr int kTiles = mma_tile_base(LT + 1);
     // list mode: the consumer runs unless a row overflowed, the fallback only if one did
     if (a.list_role != 0 && ((*a.list_flag != 0) != (a.list_role == 2))) return;
     extern __shared__ __align__(16) double smem_all[];
@@ -773,6 +843,28 @@ soap_kernel(const SoapArgs a) {
     unsigned short* decode_s = reinterpret_cast<unsigned short*>(swlm_s + a.plan.n_lm);
     unsigned char* lm_l_s = reinterpret_cast<unsigned char*>(decode_s + a.plan.n_feat);
     for (int i = threadIdx.x; i < kExpTab; i += blockDim.x) exp_tab[i] = a.exp_tab[i];
+    if (MM && !SPLIT) {
+        // tensor-path epilogue: Loewdin matrices padded to 8 x 8 (zero rows / columns behind
+        // n_max), and per 8-column tile the squared m-weights (zero in the pad columns)
+        const int nm = a.plan.n_max;
+        for (int i = threadIdx.x; i < bmat_stage; i += blockDim.x) {
+            const int l = i >> 6, np = (i >> 3) & 7, kq = i & 7;
+            bmat_s[i] = (l <= a.plan.l_max && np < nm && kq < nm)
+                            ? a.bmat[((size_t)l * nm + np) * nm + kq] : 0.0;
+        }
+        for (int i = threadIdx.x; i < 8 * (kTiles + 1); i += blockDim.x) {
+            const int tt = i >> 3, c = i & 7;   // tile 0 = l = 0, then the tiles of l = 1, 2, ...
+            int l = 0, t = 0;
+            if (tt > 0) {
+                l = 1;
+                while (l < LT && mma_tile_base(l + 1) <= tt - 1) ++l;
+                t = tt - 1 - mma_tile_base(l);
+            }
+            const int col = 8 * t + c;
+            const double w = (l <= a.plan.l_max && col < 2 * l + 1) ? a.swlm[l * l + col] : 0.0;
+            swlm_s[i] = w * w;
+        }
+    } else {
     for (int i = threadIdx.x; i < bmat_stage; i += blockDim.x) bmat_s[i] = a.bmat[i];
     if (!SPLIT) {
         for (int i = threadIdx.x; i < a.plan.n_lm; i += blockDim.x) {
@@ -784,6 +876,7 @@ soap_kernel(const SoapArgs a) {
             decode_s[i] = (unsigned short)(((code >> 8) & 15) | (((code >> 12) & 31) << 4) |
                                            (((code >> 17) & 31) << 9));
         }
+    }
     }
     __syncthreads();
     const double* __restrict__ bmat = bmat_stage > 0 ? bmat_s : a.bmat;
@@ -813,7 +906,8 @@ soap_kernel(const SoapArgs a) {
     }
 
     const SoapPlan& pl = a.plan;
-    const int n = pl.n_max, P = pl.row_stride, n_lm = pl.n_lm;
+    const int n = pl.n_max, n_lm = pl.n_lm;
+    [[maybe_unused]] const int P = pl.row_stride;
     const int c_doubles = pl.n_species * n_lm * n;
     // per-warp fixed part: displacement list + cell table (+ batch list of the in-kernel search)
     constexpr int kWarpFixed = soap_warp_fixed(LIST);
@@ -824,8 +918,19 @@ soap_kernel(const SoapArgs a) {
     int2* bl_q = reinterpret_cast<int2*>(tab_sh + kCellTab * 4);   // [64] batch (start, count)
     int* bl_e = reinterpret_cast<int*>(bl_q + kBatchCap);             // [64] batch -> table entry
     double* rbuf = nbuf + kWarpFixed;  // [kChunk][P] harmonics; later G / mixed
+    // tensor path: the pad columns of the last row's last tile read up to 8 doubles behind the rows;
+    // they must be finite (their products are multiplied by a zero weight)
+    if (MM) {
+        if (lane < 8) rbuf[kChunk * mma_row_stride(LT) + lane] = 0.0;
+        // ... and so must the words between the LT (LT + 2) values of a row and its odd stride
+        for (int i = lane; i < kChunk * (mma_row_stride(LT) - LT * (LT + 2)); i += 32) {
+            constexpr int kPad = mma_row_stride(LT) - LT * (LT + 2);
+            rbuf[(i / kPad) * mma_row_stride(LT) + LT * (LT + 2) + i % kPad] = 0.0;
+        }
+    }
 
-    const int g = lane >> 3, kk = lane & 7;
+    const int g = lane >> 3, kk = MM ? lane >> 2 : lane & 7;
+    const int ji = lane & 3;   // tensor path: neighbour of the lane inside a group of four
     const unsigned lt_mask = (1u << lane) - 1u;
     int il[kMaxItems], ioff[kMaxItems];
 #pragma unroll
@@ -874,9 +979,15 @@ soap_kernel(const SoapArgs a) {
         double gam[kMaxItems];
 #pragma unroll
         for (int t = 0; t < kMaxItems; ++t)
-            gam[t] = (kact && il[t] >= 0) ? -a.gamma[il[t] * n + k] * kExpScale : 0.0;
+            gam[t] = (!MM && kact && il[t] >= 0) ? -a.gamma[il[t] * n + k] * kExpScale : 0.0;
+        double gm[LT + 1], ct[2 * kTiles];   // tensor path: exponents of the lane, C fragments
+#pragma unroll
+        for (int l = 0; l <= LT; ++l)
+            gm[l] = (MM && kact && l <= pl.l_max) ? -a.gamma[l * n + k] * kExpScale : 0.0;
+#pragma unroll
+        for (int t = 0; t < 2 * kTiles; ++t) ct[t] = 0.0;
         // l = 0: lane (jq, k) sums exp(-gamma_0k r^2) over the neighbours jj = jq (mod 4)
-        const double gam0 = kact ? -a.gamma[k] * kExpScale : 0.0;
+        [[maybe_unused]] const double gam0 = kact ? -a.gamma[k] * kExpScale : 0.0;
         double acc00 = 0.0;
         Acc<S0> a0;
         Acc<S1> a1;
@@ -892,11 +1003,50 @@ soap_kernel(const SoapArgs a) {
         for (int s = 0; s < S3; ++s) a3.v[s] = 0.0;
 
         auto process = [&](int fill) {
+            if constexpr (MM) {
+                constexpr int PM = mma_row_stride(LT);
+                for (int h0 = 0; h0 < fill; h0 += kChunk) {
+                    const int nh = min(kChunk, fill - h0);
+                    if (lane < kChunk) {   // phase B; the rows behind the last neighbour are zero
+                        const double* d = nbuf + (h0 + lane) * 4;
+                        const bool on = lane < nh;
+                        const double x = on ? d[0] : 0.0, y = on ? d[1] : 0.0;
+                        const double z = on ? d[2] : 0.0, r2 = on ? d[3] : 0.0;
+                        // neighbour 4 q + i -> row 4 i + q: with an odd stride the 16 stores of
+                        // phase B and the 16 (neighbour, column) loads of a half-warp below each
+                        // hit 16 different bank pairs
+                        solid_harmonics<LT, kRowDense>(x, y, z, r2,
+                                                       rbuf + ((lane & 3) * 4 + (lane >> 2)) * PM);
+                    }
+                    __syncwarp();
+                    const int ngrp = (nh + 3) >> 2;
+                    for (int q = 0; q < ngrp; ++q) {   // phase C, four neighbours per trip
+                        const bool on = 4 * q + ji < nh;
+                        const double r2 = on ? nbuf[(h0 + 4 * q + ji) * 4 + 3] : 0.0;
+                        const double* __restrict__ rt = rbuf + (ji * 4 + q) * PM + (lane >> 2);
+                        // no branch on l <= l_max: one basic block (the results for l > l_max are
+                        // dropped at the end)
+                        double e[LT + 1];
+                        exp_scaled_batch<LT + 1>(gm, r2, exp_tab, e);
+                        acc00 += on ? e[0] : 0.0;
+#pragma unroll
+                        for (int l = 1; l <= LT; ++l) {
+#pragma unroll
+                            for (int t = 0; t < mma_tiles(l); ++t)
+                                dmma_8x8x4(ct[2 * (mma_tile_base(l) + t)],
+                                           ct[2 * (mma_tile_base(l) + t) + 1],
+                                           rt[l * l - 1 + 8 * t], e[l]);
+                        }
+                    }
+                    __syncwarp();
+                }
+            } else {
             for (int h0 = 0; h0 < fill; h0 += kChunk) {
                 const int nh = min(kChunk, fill - h0);
                 if (lane < nh) {   // phase B
                     const double* d = nbuf + (h0 + lane) * 4;
-                    solid_harmonics<LT, PK>(d[0], d[1], d[2], d[3], rbuf + lane * P);
+                    solid_harmonics<LT, PK ? kRowPacked : kRowBlocks>(d[0], d[1], d[2], d[3],
+                                                                        rbuf + lane * P);
                 }
                 __syncwarp();
                 double r2_next = nbuf[h0 * 4 + 3];   // one neighbour ahead: hides the shared load
@@ -924,6 +1074,7 @@ soap_kernel(const SoapArgs a) {
                     if (jj < nh) acc00 += exp_scaled(gam0, nbuf[(h0 + jj) * 4 + 3], exp_tab);
                 }
                 __syncwarp();
+            }
             }
         };
 
@@ -1110,12 +1261,124 @@ soap_kernel(const SoapArgs a) {
         }
 
         // ---- registers -> G[z][lm][k] (shared: fused epilogue; global: split mode) ----
-        acc00 += __shfl_xor_sync(kFullS, acc00, 8);
-        acc00 += __shfl_xor_sync(kFullS, acc00, 16);
+        acc00 += __shfl_xor_sync(kFullS, acc00, MM ? 1 : 8);
+        acc00 += __shfl_xor_sync(kFullS, acc00, MM ? 2 : 16);
         double* cz = SPLIT ? a.gscr + ((size_t)f * a.n_cent + ci) * c_doubles +
                                  (size_t)z_sp * n_lm * n
                            : rbuf;
-        if (kact) {
+        if constexpr (MM && SPLIT) {
+            // C fragments hold G^T: row = column of the tile (lane >> 2), columns = radial 2 ji + {0, 1}
+            if (kact && ji == 0) cz[k] = acc00;  // lm = 0: S_0^0 = 1
+            const int k0 = kb * kKBlock + 2 * ji;
+#pragma unroll
+            for (int l = 1; l <= LT; ++l)
+#pragma unroll
+                for (int t = 0; t < mma_tiles(l); ++t) {
+                    const int col = 8 * t + (lane >> 2);
+                    if (col < 2 * l + 1 && l <= pl.l_max) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            if (k0 + h < n)
+                                cz[(l * l + col) * n + k0 + h] = ct[2 * (mma_tile_base(l) + t) + h];
+                    }
+                }
+        } else if constexpr (MM) {
+            // ---- tensor-path epilogue: nothing leaves the registers ----
+            // mixing   D_l (n' x cols) = Bm_l (n' x k) * G_l (k x cols): A = the lane's two entries of
+            //          the padded Loewdin matrix, B = the C fragments of phase C as they are (K slot
+            //          ji <-> radial index 2 ji + h, one product per h)
+            // spectrum P_l (n x n') = sum over the columns of w^2 D[n][col] D[n'][col]: the lane's
+            //          D element is both its A entry (times w^2) and its B entry (K slot ji <-> column
+            //          2 ji + h), so the Gram matrix needs no data movement either
+            const int na = lane >> 2;
+            double pv[2 * (LT + 1)];
+            const double2* __restrict__ bm2 = reinterpret_cast<const double2*>(bmat_s) + na * 4 + ji;
+            const double2* __restrict__ wq2 = reinterpret_cast<const double2*>(swlm_s) + ji;
+            {
+                const double g0a = __shfl_sync(kFullS, acc00, 8 * ji);       // G_0[2 ji]
+                const double g0b = __shfl_sync(kFullS, acc00, 8 * ji + 4);   // G_0[2 ji + 1]
+                const double2 bm = bm2[0], w = wq2[0];
+                double d0 = 0.0, d1 = 0.0, p0 = 0.0, p1 = 0.0;
+                dmma_8x8x4(d0, d1, bm.x, na == 0 ? g0a : 0.0);
+                dmma_8x8x4(d0, d1, bm.y, na == 0 ? g0b : 0.0);
+                dmma_8x8x4(p0, p1, d0 * w.x, d0);
+                dmma_8x8x4(p0, p1, d1 * w.y, d1);
+                pv[0] = p0;
+                pv[1] = p1;
+            }
+#pragma unroll
+            for (int l = 1; l <= LT; ++l) {
+                double p0 = 0.0, p1 = 0.0;
+                if (l <= pl.l_max) {
+                    const double2 bm = bm2[l * 32];
+#pragma unroll
+                    for (int t = 0; t < mma_tiles(l); ++t) {
+                        const double2 w = wq2[(1 + mma_tile_base(l) + t) * 4];
+                        double d0 = 0.0, d1 = 0.0;
+                        dmma_8x8x4(d0, d1, bm.x, ct[2 * (mma_tile_base(l) + t)]);
+                        dmma_8x8x4(d0, d1, bm.y, ct[2 * (mma_tile_base(l) + t) + 1]);
+                        dmma_8x8x4(p0, p1, d0 * w.x, d0);
+                        dmma_8x8x4(p0, p1, d1 * w.y, d1);
+                    }
+                }
+                pv[2 * l] = p0;
+                pv[2 * l + 1] = p1;
+            }
+            // the lane holds P_l[na][2 ji + {0, 1}]; features of one l: rows na, columns nb >= na
+            const int nb0 = 2 * ji, blk = n * (n + 1) / 2;
+            const int c_first = na * n - (na * (na - 1)) / 2 + nb0 - na;
+            const bool ok0 = na <= nb0 && nb0 < n, ok1 = na <= nb0 + 1 && nb0 + 1 < n;
+            double* out_row =
+                a.out ? a.out + (long long)ci * a.stride_i + (long long)f * a.stride_f : nullptr;
+            if constexpr (SEQ) {
+                // ring slot f mod delay still holds frame f - delay (if the run got that far)
+                double* ring = a.ring + (((size_t)blockIdx.y * a.n_cent + ci) * a.delay +
+                                         (size_t)(f % a.delay)) * (size_t)(pl.n_feat + 1);
+                // runs overlap by `delay` frames: the spectrum row of a frame (if wanted) is
+                // written by the run its index falls into
+                if (min(f / a.seq_run, (int)gridDim.y - 1) != (int)blockIdx.y) out_row = nullptr;
+                double rv[2 * (LT + 1)];
+#pragma unroll
+                for (int l = 0; l <= LT; ++l) {   // all the ring loads before the ring stores
+                    const int c = l * blk + c_first;
+                    rv[2 * l] = (ok0 && l <= pl.l_max) ? ring[c] : 0.0;
+                    rv[2 * l + 1] = (ok1 && l <= pl.l_max) ? ring[c + 1] : 0.0;
+                }
+                double csq = 0.0, dot = 0.0;
+#pragma unroll
+                for (int l = 0; l <= LT; ++l) {
+                    const int c = l * blk + c_first;
+                    if (ok0 && l <= pl.l_max) {
+                        csq = fma(pv[2 * l], pv[2 * l], csq);
+                        dot = fma(pv[2 * l], rv[2 * l], dot);
+                        ring[c] = pv[2 * l];
+                    }
+                    if (ok1 && l <= pl.l_max) {
+                        csq = fma(pv[2 * l + 1], pv[2 * l + 1], csq);
+                        dot = fma(pv[2 * l + 1], rv[2 * l + 1], dot);
+                        ring[c + 1] = pv[2 * l + 1];
+                    }
+                }
+                csq = warp_sum(csq);
+                dot = warp_sum(dot);
+                if (lane == 0) {
+                    double* ring_sq = ring + pl.n_feat;
+                    if (fo >= a.delay)
+                        a.ts_out[(long long)ci * a.ts_ld + a.ts_col0 + (f - a.delay)] =
+                            soap_dist_from_sums(*ring_sq, csq, dot);
+                    *ring_sq = csq;
+                }
+            }
+            if (out_row) {
+#pragma unroll
+                for (int l = 0; l <= LT; ++l) {
+                    const int c = l * blk + c_first;
+                    if (ok0 && l <= pl.l_max) out_row[c] = pv[2 * l];
+                    if (ok1 && l <= pl.l_max) out_row[c + 1] = pv[2 * l + 1];
+                }
+            }
+            __syncwarp();
+        } else if (kact) {
             if (g == 0) cz[k] = acc00;  // lm = 0: S_0^0 = 1
             if constexpr (PK) store_packed(a0, g, k, n, cz);
             else store_item<S0>(a0, il[0], k, n, cz);
@@ -1124,7 +1387,7 @@ soap_kernel(const SoapArgs a) {
             store_item<S3>(a3, il[3], k, n, cz);
         }
         __syncwarp();
-        if (!SPLIT) {
+        if (!SPLIT && !MM) {
             // the harmonics buffer is free now: G sits at its start, the mixed coefficients follow
             SpectrumSink sink;
             sink.out = a.out ? a.out + (long long)ci * a.stride_i + (long long)f * a.stride_f
@@ -1505,7 +1768,7 @@ static int soap_layout(int n_frames, int n_atoms, int n_cent, int n_species, int
 
 // lt = compile-time l cap of the instantiation, s0 = its widest item
 static void make_plan(int n_species, int n_max, int l_max, int lt, int s0, SoapPlan* pl) {
-    const bool packed = lt == 8 && s0 == kPackSlots;
+    const bool packed = !DSG_SOAP_MMA && lt == 8 && s0 == kPackSlots;
     pl->n_max = n_max;
     pl->l_max = l_max;
     pl->n_species = n_species;
@@ -1516,6 +1779,7 @@ static void make_plan(int n_species, int n_max, int l_max, int lt, int s0, SoapP
     pl->kblocks = (n_max + kKBlock - 1) / kKBlock;
     int p = packed ? kGroups * kPackSlots : harm_len(lt);
     while (p % (lt == 8 ? 4 : 16) != 2) ++p;
+    if (DSG_SOAP_MMA) p = mma_row_stride(lt);   // dense rows, odd stride (see soap_kernel)
     pl->row_stride = p;
     int rb = kChunk * p + s0 + 2;  // tail: item rows are read S_t wide past the last row
     // fused epilogue: G and the mixed coefficients both live here (split mode: neither)
@@ -1535,7 +1799,7 @@ static void make_plan(int n_species, int n_max, int l_max, int lt, int s0, SoapP
         int best = 0;
         for (int g = 1; g < kGroups; ++g)
             if (load[g] < load[best]) best = g;
-        pl->item_off[best][cnt[best]] = packed ? hoff<8, true>(l) : harm_off(lt, l);
+        pl->item_off[best][cnt[best]] = packed ? hoff<8, kRowPacked>(l) : harm_off(lt, l);
         pl->item_l[best][cnt[best]++] = l;
         load[best] += 2 * l + 1;
     }
@@ -1721,6 +1985,10 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     // two warps per block keep several blocks resident per SM
     // swlm (n_lm doubles) + decode (n_feat u16) + lm_l (n_lm bytes), rounded to 16 bytes
     a.epi_smem_doubles = split ? 0 : (int)((n_lm + (2 * n_feat + n_lm + 7) / 8 + 1) & ~1);
+    if (DSG_SOAP_MMA && !split) {   // padded 8 x 8 matrices, squared weights per 8-column tile
+        a.bmat_smem_doubles = (lt + 1) * 64;
+        a.epi_smem_doubles = 8 * (mma_tile_base(lt + 1) + 1);
+    }
     const size_t shared_tables =
         8 * ((size_t)kExpTab +
              (split ? 0 : (size_t)a.bmat_smem_doubles + (size_t)a.epi_smem_doubles));
@@ -1787,18 +2055,25 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
             DSG_SOAP_LAUNCH_ONE((soap_kernel<LT, A, B, C, D, false, false>), grid, warps, smem); \
         }                                                                                        \
     } while (0)
+#ifdef DSG_SOAP_ONLY_L8   // development builds: only the l_max = 8 instantiations (compile time)
+    if (l_max != 8) return set_error(DSG_ERR_UNSUPPORTED, "development build: l_max = 8 only");
+#else
     if (l_max <= 4) DSG_SOAP_LAUNCH(4, 9, 0, 0, 0);
     else if (l_max <= 6) DSG_SOAP_LAUNCH(6, 13, 5, 0, 0);
     else if (l_max < 8 || (l_max == 8 && !DSG_SOAP_PACK)) DSG_SOAP_LAUNCH(8, 17, 9, 0, 0);
-    else if (l_max == 8) {
+    else
+#endif
+    if (l_max == 8) {
         // the packed kernel hard-codes the packing {8 - g, 1 + g} of lane group g
-        for (int g = 0; g < kGroups; ++g)
+        for (int g = 0; g < kGroups && !DSG_SOAP_MMA; ++g)
             if (a.plan.item_l[g][0] != 8 - g || a.plan.item_l[g][1] != 1 + g)
                 return set_error(DSG_ERR_UNSUPPORTED, "unexpected l packing for l_max = 8");
         DSG_SOAP_LAUNCH(8, kPackSlots, 0, 0, 0);
     }
+#ifndef DSG_SOAP_ONLY_L8
     else if (l_max <= 10) DSG_SOAP_LAUNCH(10, 21, 13, 5, 0);
     else DSG_SOAP_LAUNCH(12, 25, 17, 9, 0);
+#endif
 #undef DSG_SOAP_LAUNCH
 #undef DSG_SOAP_LAUNCH_ONE
     DSG_LAUNCH_CHECK("soap_kernel");

@@ -1,11 +1,14 @@
 #!/bin/bash
-# time one profile_target stage with every library variant under gpurun_variants/
+# usage: gpu_variants.sh TAG variant... ("default" = the in-tree library): fused cfg5 + soap + fused3 timings
 mkdir -p gpurun_out
-out=gpurun_out/variants_$1.log
-: > $out
-for lib in default gpurun_variants/lib_*.so; do
-  if [ $lib = default ]; then unset DSG_LIB_PATH; else export DSG_LIB_PATH=$PWD/$lib; fi
-  echo "== $lib" >> $out
-  timeout 300 python scripts/profile_target.py "$@" 2>&1 | tail -2 >> $out
+tag=$1; shift
+log=gpurun_out/${tag}_timing.log; : > $log
+for v in "$@"; do
+  if [ $v = default ]; then unset DSG_LIB_PATH; else export DSG_LIB_PATH=$PWD/gpurun_variants/lib_$v.so; fi
+  echo "== $v" >> $log
+  timeout 300 python scripts/profile_target.py fused 100000 33 2>&1 | tail -1 >> $log
+  timeout 300 python scripts/profile_target.py soap 20000 8 2>&1 | tail -1 >> $log
+  timeout 300 python scripts/profile_target.py fused3 50000 8 2>&1 | tail -1 >> $log
 done
-cat $out
+unset DSG_LIB_PATH
+cat $log
