@@ -20,6 +20,7 @@
 // sums need double precision to meet 1e-5 relative (SURVEY.md section 7 "hard parts").
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -131,7 +132,7 @@ struct SoapArgs {
     double r2max;
     const double* gamma;    // (L+1, n)
     const double* bmat;     // (L+1, n, n)  beta * prefactor
-    const double* exp_tab;  // (kExpTab) 2^(j/32)
+    const double* exp_tab;  // (kExpTab) bit patterns, see exp_scaled
     int bmat_smem_doubles;  // size of bmat if it is staged in shared memory, else 0
     int epi_smem_doubles;   // fused epilogue tables (swlm, lm_l, decode) in shared memory
     const double* swlm;     // (n_lm)  sqrt of the m-contraction weights
@@ -245,6 +246,20 @@ __device__ __forceinline__ void soap_locate(const SoapFrame* __restrict__ p, dou
     }
 }
 
+// the cell of a coordinate that soap_locate has already wrapped (same arithmetic minus the wrap,
+// which leaves such a value unchanged: no float64 division per centre)
+__device__ __forceinline__ void soap_cell_of_wrapped(const SoapFrame* __restrict__ p, double x,
+                                                     double y, double z, int* c) {
+    const double in[3] = {x, y, z};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double v = p->mode[k] == kOpen ? in[k] - p->origin[k] : in[k];
+        int ck = (int)(v * p->inv_edge[k]);
+        const int nc = p->nc[k];
+        c[k] = ck < 0 ? 0 : (ck >= nc ? nc - 1 : ck);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 soap_bin_kernel(const T* __restrict__ pos, const int* __restrict__ species, int n_atoms,
@@ -314,10 +329,7 @@ soap_list_kernel(const SoapArgs a) {
     const SoapFrame* __restrict__ fr = a.frames + f;
     const double xc = a.sx[slot], yc = a.sy[slot], zc = a.sz[slot];
     int cc[3];
-    {
-        double w[3];
-        soap_locate(fr, xc, yc, zc, w, cc);
-    }
+    soap_cell_of_wrapped(fr, xc, yc, zc, cc);
     const int nc0 = fr->nc[0], nc1 = fr->nc[1], nc2 = fr->nc[2];
     const double b0 = fr->box[0], b1 = fr->box[1], b2 = fr->box[2];
     const int frame_first = f * a.n_atoms;
@@ -370,53 +382,49 @@ struct Acc {
     double v[N > 0 ? N : 1];
 };
 
-// exp(x) for x in [-690, 0], argument given pre-scaled: t = x * 32 log2(e).  2^n * 2^(j/32) * e^u
-// with 32 n + j = rint(t); 2^(j/32) from a shared-memory table, e^u by a degree-5 Taylor
-// polynomial in v = t - rint(t) (coefficients (ln2/32)^i / i! folded in; |u| <= ln2/64,
-// truncation 2.2e-15).  Relative error < 5e-15.  Branch-free, 8 fp64 operations: the kernel is
-// issue-bound and an fp64 instruction holds the issue port for two cycles (DESIGN.md section
-// 3.4), so the exponential is built for the fewest instructions, not the shortest chain: Horner
-// with the coefficients read as constant-bank operands (no register or move is spent on them;
-// the literal constants of the former degree-6 Estrin form were re-materialised by 12 moves per
-// neighbour) and a 32-entry table instead of 16 (entries j and j + 16 share a bank: at worst a
-// two-way conflict on a load pipe that has slack).
+// exp(x) for x in [-690, 0], argument given pre-scaled: t = x * 128 log2(e).  2^n * 2^(j/128) * e^u
+// with 128 n + j = rint(t); 2^(j/128) from a shared-memory table, e^u by a degree-4 Taylor
+// polynomial in v = t - rint(t) (coefficients (ln2/128)^i / i! folded in; |u| <= ln2/256,
+// truncation 1.2e-15).  Relative error < 4e-15.  Branch-free, 8 fp64 operations (3 for the range
+// reduction, 4 Horner steps with constant-bank coefficients, 1 product): the kernel is bound by the
+// fp64 pipe, which the tensor-path products share, so the exponential is
+// built for the fewest fp64 instructions.  The table is replicated 16 times, entry j of copy r at
+// tab[16 j + r]: lane `lane` reads copy lane & 15, i.e. its own bank pair, so a lookup costs the
+// two wavefronts of any 64-bit warp load whatever the 32 indices are (the 32-entry table of round
+// 1 cost 2 to 4).  The table holds bit patterns, not values: the high word of entry j is that of
+// 2^(j/128) minus j << 13, so adding (128 n + j) << 13 = (n << 20) + (j << 13) puts n into the
+// exponent without masking j out first.
 // The caller guarantees t >= -690 * kExpScale (2^n stays normal): soap_layout rejects cutoffs
 // for which gamma * r^2 could exceed 690.
-constexpr int kExpTab = 32;
-constexpr int kExpTabLog2 = 5;
-constexpr double kExpScale = 46.166241308446828;  // 32 * log2(e)
-__constant__ double kExpPoly[5] = {
-    2.16608493924982901946e-02,   // (ln2/32)^1 / 1!
-    2.34596198202246771555e-04,   // (ln2/32)^2 / 2!
-    1.69385097243718189026e-06,   // (ln2/32)^3 / 3!
-    9.17256270182464301942e-09,   // (ln2/32)^4 / 4!
-    3.97370998454941544405e-11,   // (ln2/32)^5 / 5!
+constexpr int kExpTab = 128;
+constexpr int kExpRep = 16;
+constexpr int kExpTabDoubles = kExpTab * kExpRep;   // 16 KB per block
+constexpr int kExpHiShift = 13;                      // 20 - log2(kExpTab)
+constexpr double kExpScale = 184.6649652337873;      // 128 * log2(e)
+__constant__ double kExpPoly[4] = {
+    5.4152123481245725e-03,   // (ln2/128)^1 / 1!
+    1.4662262387640423e-05,   // (ln2/128)^2 / 2!
+    2.6466421444330967e-08,   // (ln2/128)^3 / 3!
+    3.583032305400251e-11,    // (ln2/128)^4 / 4!
 };
-// g = gamma * kExpScale (negative), s = r^2.  The product enters only through two FMAs: rint(g s)
-// by the magic-constant trick and the remainder v = g s - rint(g s) with a single rounding, so
-// the argument is never rounded to float64 (one operation fewer and v exact to 1e-17).
+// g = gamma * kExpScale (negative), s = r^2, tab = the lane's copy of the table.  The product
+// enters only through two FMAs: rint(g s) by the magic-constant trick and the remainder
+// v = g s - rint(g s) with a single rounding, so the argument is never rounded to float64 (one
+// operation fewer and v exact to 1e-17).
+__device__ __forceinline__ double exp_scale_factor(int kq, const double* __restrict__ tab) {
+    const double tv = tab[(kq & (kExpTab - 1)) * kExpRep];
+    return __hiloint2double(__double2hiint(tv) + (kq << kExpHiShift), __double2loint(tv));
+}
 __device__ __forceinline__ double exp_scaled(double g, double s, const double* __restrict__ tab) {
     const double magic = 6755399441055744.0;                     // 1.5 * 2^52
     const double tn = fma(g, s, magic);
-    const int kq = __double2loint(tn);                           // 32 n + j
+    const double sc = exp_scale_factor(__double2loint(tn), tab);  // 2^n 2^(j/128), 128 n + j = rint(g s)
     const double v = fma(g, s, magic - tn);                      // [-1/2, 1/2]
-#if DSG_SOAP_EXP_ESTRIN   // 7 operations at depth 3 instead of 5 at depth 5
-    const double v2 = v * v;
-    const double t0 = fma(kExpPoly[0], v, 1.0);
-    const double t1 = fma(kExpPoly[2], v, kExpPoly[1]);
-    const double t2 = fma(kExpPoly[4], v, kExpPoly[3]);
-    const double v4 = v2 * v2;
-    double p = fma(t1, v2, t0);
-    p = fma(t2, v4, p);
-#else
-    double p = fma(kExpPoly[4], v, kExpPoly[3]);
-    p = fma(p, v, kExpPoly[2]);
+    double p = fma(kExpPoly[3], v, kExpPoly[2]);
     p = fma(p, v, kExpPoly[1]);
     p = fma(p, v, kExpPoly[0]);
     p = fma(p, v, 1.0);
-#endif
-    const double r = tab[kq & (kExpTab - 1)] * p;
-    return __hiloint2double(__double2hiint(r) + ((kq >> kExpTabLog2) << 20), __double2loint(r));
+    return sc * p;
 }
 
 // NE exponentials of the same s, written stage by stage: ptxas keeps roughly the source order, so
@@ -426,17 +434,15 @@ template <int NE>
 __device__ __forceinline__ void exp_scaled_batch(const double (&g)[NE], double s,
                                                  const double* __restrict__ tab, double (&e)[NE]) {
     const double magic = 6755399441055744.0;
-    double tn[NE], v[NE], p[NE], tv[NE];
+    double tn[NE], v[NE], p[NE], sc[NE];
 #pragma unroll
     for (int i = 0; i < NE; ++i) tn[i] = fma(g[i], s, magic);
 #pragma unroll
     for (int i = 0; i < NE; ++i) v[i] = fma(g[i], s, magic - tn[i]);
 #pragma unroll
-    for (int i = 0; i < NE; ++i) tv[i] = tab[__double2loint(tn[i]) & (kExpTab - 1)];
+    for (int i = 0; i < NE; ++i) sc[i] = exp_scale_factor(__double2loint(tn[i]), tab);
 #pragma unroll
-    for (int i = 0; i < NE; ++i) p[i] = fma(kExpPoly[4], v[i], kExpPoly[3]);
-#pragma unroll
-    for (int i = 0; i < NE; ++i) p[i] = fma(p[i], v[i], kExpPoly[2]);
+    for (int i = 0; i < NE; ++i) p[i] = fma(kExpPoly[3], v[i], kExpPoly[2]);
 #pragma unroll
     for (int i = 0; i < NE; ++i) p[i] = fma(p[i], v[i], kExpPoly[1]);
 #pragma unroll
@@ -444,11 +450,7 @@ __device__ __forceinline__ void exp_scaled_batch(const double (&g)[NE], double s
 #pragma unroll
     for (int i = 0; i < NE; ++i) p[i] = fma(p[i], v[i], 1.0);
 #pragma unroll
-    for (int i = 0; i < NE; ++i) {
-        const double r = tv[i] * p[i];
-        const int kq = __double2loint(tn[i]);
-        e[i] = __hiloint2double(__double2hiint(r) + ((kq >> kExpTabLog2) << 20), __double2loint(r));
-    }
+    for (int i = 0; i < NE; ++i) e[i] = sc[i] * p[i];
 }
 
 // Layout of one neighbour's harmonics row: the block of angular momentum l (2l+1 values, padded
@@ -811,9 +813,12 @@ constexpr int kListWarps = DSG_SOAP_LIST_WARPS;
 // soap_spectrum_kernel is the frame-sequential one).
 template <int LT, int S0, int S1, int S2, int S3, bool SPLIT, bool LIST, bool SEQ = false>
 __global__ void __launch_bounds__(
-    (LIST && S0 <= 20) ? 32 * kListWarps : 64,
-    (S0 <= 20) ? (LIST ? DSG_SOAP_LIST_BLOCKS : DSG_SOAP_MIN_BLOCKS)
-               : (S0 <= 21 ? DSG_SOAP_MIN_BLOCKS_L10 : 4))
+    DSG_SOAP_MMA ? 128 : ((LIST && S0 <= 20) ? 32 * kListWarps : 64),
+    // tensor path: four warps share the 16 KB exponential table; 3 blocks per SM (168 registers)
+    // up to l_max = 8, 2 blocks (255 registers: 40 / 56 accumulator registers more) beyond
+    DSG_SOAP_MMA ? (LT <= 8 ? 3 : 2)
+                 : ((S0 <= 20) ? (LIST ? DSG_SOAP_LIST_BLOCKS : DSG_SOAP_MIN_BLOCKS)
+                               : (S0 <= 21 ? DSG_SOAP_MIN_BLOCKS_L10 : 4)))
 soap_kernel(const SoapArgs a) {
     static_assert(!(SEQ && SPLIT), "frame-sequential accumulation is only the fused kernel");
     // MM: phase C as tensor-core products G_l (8 radial x 2l+1) += E_l (8 x 4 neighbours) * Y_l
@@ -832,9 +837,10 @@ soap_kernel(const SoapArgs a) {
     extern __shared__ __align__(16) double smem_all[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warps = blockDim.x >> 5;
-    // block-wide tables: 2^(j/32) and (if small enough) the Loewdin matrices
-    double* exp_tab = smem_all;
-    double* bmat_s = smem_all + kExpTab;
+    // block-wide tables: 2^(j/128) (16 copies, the lane reads its own) and the Loewdin matrices
+    double* exp_tab_all = smem_all;
+    const double* exp_tab = exp_tab_all + (lane & (kExpRep - 1));
+    double* bmat_s = smem_all + kExpTabDoubles;
     const int bmat_stage = SPLIT ? 0 : a.bmat_smem_doubles;
     // fused epilogue: m-weights, lm -> l and the feature decode table also sit in shared memory
     // (their global loads were exposed latency in every centre's epilogue)
@@ -842,7 +848,8 @@ soap_kernel(const SoapArgs a) {
     double* swlm_s = bmat_s + bmat_stage;
     unsigned short* decode_s = reinterpret_cast<unsigned short*>(swlm_s + a.plan.n_lm);
     unsigned char* lm_l_s = reinterpret_cast<unsigned char*>(decode_s + a.plan.n_feat);
-    for (int i = threadIdx.x; i < kExpTab; i += blockDim.x) exp_tab[i] = a.exp_tab[i];
+    for (int i = threadIdx.x; i < kExpTabDoubles; i += blockDim.x)
+        exp_tab_all[i] = a.exp_tab[i / kExpRep];
     if (MM && !SPLIT) {
         // tensor-path epilogue: Loewdin matrices padded to 8 x 8 (zero rows / columns behind
         // n_max), and per 8-column tile the squared m-weights (zero in the pad columns)
@@ -880,7 +887,7 @@ soap_kernel(const SoapArgs a) {
     }
     __syncthreads();
     const double* __restrict__ bmat = bmat_stage > 0 ? bmat_s : a.bmat;
-    double* smem = smem_all + kExpTab + bmat_stage + epi_stage;
+    double* smem = smem_all + kExpTabDoubles + bmat_stage + epi_stage;
     // non-SEQ: each warp walks a run of consecutive slots of the frame's (species, cell)-sorted
     // order: consecutive centres share their candidate cells (L1 reuse, cached cell table) and
     // the block-wide tables are loaded once
@@ -972,10 +979,7 @@ soap_kernel(const SoapArgs a) {
         if (ci < 0) continue;
         const double xc = a.sx[slot], yc = a.sy[slot], zc = a.sz[slot];
         int cc[3];
-        {
-            double w[3];
-            soap_locate(fr, xc, yc, zc, w, cc);  // coordinates are already wrapped: the cell again
-        }
+        soap_cell_of_wrapped(fr, xc, yc, zc, cc);
         double gam[kMaxItems];
 #pragma unroll
         for (int t = 0; t < kMaxItems; ++t)
@@ -1889,7 +1893,13 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     DSG_CUDA_CHECK(cudaMemcpyAsync(d_frames, frames.data(), sizeof(SoapFrame) * n_frames,
                                    cudaMemcpyHostToDevice, st));
     double exp_tab[kExpTab];
-    for (int j = 0; j < kExpTab; ++j) exp_tab[j] = std::exp2((double)j / kExpTab);  // 2^(j/32)
+    for (int j = 0; j < kExpTab; ++j) {   // bit pattern of 2^(j/128) with j << 13 taken off the high word
+        const double v = std::exp2((double)j / kExpTab);
+        uint64_t bits;
+        std::memcpy(&bits, &v, 8);
+        bits -= (uint64_t)j << (32 + kExpHiShift);
+        std::memcpy(&exp_tab[j], &bits, 8);
+    }
     DSG_CUDA_CHECK(cudaMemcpyAsync(ws + L.off_exptab, exp_tab, sizeof(exp_tab),
                                    cudaMemcpyHostToDevice, st));
 
@@ -1990,15 +2000,15 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
         a.epi_smem_doubles = 8 * (mma_tile_base(lt + 1) + 1);
     }
     const size_t shared_tables =
-        8 * ((size_t)kExpTab +
+        8 * ((size_t)kExpTabDoubles +
              (split ? 0 : (size_t)a.bmat_smem_doubles + (size_t)a.epi_smem_doubles));
-    int warps = 2;
-    if (per_warp * warps + shared_tables > 227 * 1024) warps = 1;
+    int warps = DSG_SOAP_MMA ? 4 : 2;
+    while (warps > 1 && per_warp * warps + shared_tables > 227 * 1024) warps >>= 1;
     const size_t smem = per_warp * warps + shared_tables + DSG_SOAP_EXTRA_SMEM;  // (occupancy probe)
     // list-mode consumer: smaller per-warp part, four warps share the block tables
     const size_t per_warp_l =
         8 * ((((size_t)soap_warp_fixed(true) + (size_t)a.plan.rbuf_doubles) + 1) & ~(size_t)1);
-    int warps_l = s0 <= kPackSlots ? kListWarps : 2;
+    int warps_l = (DSG_SOAP_MMA || s0 <= kPackSlots) ? kListWarps : 2;
     while (warps_l > 1 && per_warp_l * warps_l + shared_tables > 227 * 1024) warps_l >>= 1;
     const size_t smem_l = per_warp_l * warps_l + shared_tables + DSG_SOAP_EXTRA_SMEM;
     // spectrum kernel: mixed coefficients of one l per warp
