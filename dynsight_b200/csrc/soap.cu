@@ -81,11 +81,7 @@ constexpr int kOpenCellsPerAxis = 32;
 #ifndef DSG_SOAP_EXTRA_SMEM
 #define DSG_SOAP_EXTRA_SMEM 0      // occupancy probe: dummy dynamic shared memory per block
 #endif
-#ifndef DSG_SOAP_SEQ_GROUP
-#define DSG_SOAP_SEQ_GROUP 1
-#endif
 
-constexpr int kSeqGroup = DSG_SOAP_SEQ_GROUP;  // centres a warp of the frame-sequential kernels walks per frame
 constexpr int kListCap = 32;     // displacement list entries per warp
 constexpr int kCellTab = 32;     // (cell range, shift) entries resolved per pass
 constexpr int kBatchCap = 64;    // 32-candidate batches listed per pass
@@ -955,19 +951,19 @@ soap_kernel(const SoapArgs a) {
     // the block-wide tables are loaded once
     int first = 0, last = 0, seq_t0 = 0, seq_frames = 1, seq_first = 0;
     if (SEQ) {
-        // warp w takes the kSeqGroup atoms that sit at the sorted slots [w * kSeqGroup, ...) of the
-        // run's FIRST frame (neighbours in space, so the warps of a block keep sharing lines).
+        // warp w takes the atom that sits at sorted slot w of the run's FIRST frame (neighbours in
+        // space, so the warps of a block keep sharing lines).
         // Measured on 100 000 atoms x 33 frames: groups of 1 / 2 / 4 / 8 / 16 / 32 centres per warp
         // give 69.3 / 72.1 / 73.6 / 76.1 / 77.6 / 80.2 ms -- more, shorter-lived warps balance the
         // SMs better than longer walks reuse L1, so a warp owns ONE centre (69.0 ms + 1.3 ms for
         // the two-kernel path).
-        seq_first = (blockIdx.x * warps + warp) * kSeqGroup;
+        seq_first = blockIdx.x * warps + warp;
         if (seq_first >= a.n_atoms) return;   // warps are independent from here: only __syncwarp below
         seq_t0 = blockIdx.y * a.seq_run;                       // first frame pair of the run
         const int t1 = min(a.n_frames - a.delay, seq_t0 + a.seq_run);
         seq_frames = t1 - seq_t0 + a.delay;                    // frames seq_t0 .. t1 + delay - 1
         first = 0;
-        last = min(kSeqGroup, a.n_atoms - seq_first);
+        last = 1;
     } else {
         first = (blockIdx.x * warps + warp) * a.slots_per_warp;
         last = min(a.n_atoms, first + a.slots_per_warp);
@@ -1009,8 +1005,23 @@ soap_kernel(const SoapArgs a) {
     }
 
     const int n_pass = SPLIT ? pl.n_species * pl.kblocks : 1;
+    // SEQ: the warp's atom and output row are fixed; its sorted slot in frame f + 1 is fetched while
+    // frame f is processed (one of the three dependent round trips at the start of a frame)
+    int seq_ci = 0, seq_atom = 0, seq_slot_next = 0;
+    if (SEQ) {
+        seq_atom = a.sid[(size_t)seq_t0 * a.n_atoms + seq_first];
+        seq_ci = a.centre_of_atom[seq_atom];
+        if (seq_ci < 0) return;
+        seq_slot_next = a.slot_of_atom[(size_t)seq_t0 * a.n_atoms + seq_atom];
+    }
+    double gm[LT + 1];   // tensor path: exponents of the lane (fixed per pass)
+    // (also requesting the centre's coordinates and first row codes of frame f + 1 before the
+    // epilogue of frame f made the fused kernel 5 % slower: 168 registers are all in use)
     for (int fo = 0; fo < seq_frames; ++fo) {   // one trip unless SEQ
     const int f = SEQ ? seq_t0 + fo : (int)blockIdx.y;
+    const int seq_slot = seq_slot_next;
+    if (SEQ && fo + 1 < seq_frames)
+        seq_slot_next = a.slot_of_atom[(size_t)(f + 1) * a.n_atoms + seq_atom];
     const SoapFrame* __restrict__ fr = a.frames + f;
     int ne[3], mode[3], nc[3], nimg[3];
     double box[3];
@@ -1030,14 +1041,16 @@ soap_kernel(const SoapArgs a) {
     const int k = kb * kKBlock + kk;
     const bool kact = k < n;
     int cached_cell = -1, n_batches = -1;
+    if (MM && (SPLIT || fo == 0)) {
+#pragma unroll
+        for (int l = 0; l <= LT; ++l)
+            gm[l] = (kact && l <= pl.l_max) ? -a.gamma[l * n + k] * kExpScale : 0.0;
+    }
 
     for (int walk = first; walk < last; ++walk) {
-        // SEQ: the walk-th atom of the warp's group, wherever this frame's order has put it
-        const size_t slot =
-            SEQ ? (size_t)a.slot_of_atom[(size_t)f * a.n_atoms +
-                                         a.sid[(size_t)seq_t0 * a.n_atoms + seq_first + walk]]
-                : (size_t)f * a.n_atoms + walk;
-        const int ci = a.centre_of_atom[a.sid[slot]];
+        // SEQ: the warp's atom, wherever this frame's order has put it
+        const size_t slot = SEQ ? (size_t)seq_slot : (size_t)f * a.n_atoms + walk;
+        const int ci = SEQ ? seq_ci : a.centre_of_atom[a.sid[slot]];
         if (ci < 0) continue;
         const double xc = a.sx[slot], yc = a.sy[slot], zc = a.sz[slot];
         int cc[3];
@@ -1046,10 +1059,7 @@ soap_kernel(const SoapArgs a) {
 #pragma unroll
         for (int t = 0; t < kMaxItems; ++t)
             gam[t] = (!MM && kact && il[t] >= 0) ? -a.gamma[il[t] * n + k] * kExpScale : 0.0;
-        double gm[LT + 1], ct[2 * kTiles];   // tensor path: exponents of the lane, C fragments
-#pragma unroll
-        for (int l = 0; l <= LT; ++l)
-            gm[l] = (MM && kact && l <= pl.l_max) ? -a.gamma[l * n + k] * kExpScale : 0.0;
+        double ct[2 * kTiles];   // tensor path: C fragments
 #pragma unroll
         for (int t = 0; t < 2 * kTiles; ++t) ct[t] = 0.0;
         // l = 0: lane (jq, k) sums exp(-gamma_0k r^2) over the neighbours jj = jq (mod 4)
@@ -1820,7 +1830,7 @@ static int soap_layout(int n_frames, int n_atoms, int n_cent, int n_species, int
         // frame pairs per warp: long runs (the `delay` frames a run shares with the next one are
         // computed twice) as long as the grid still has ~4 generations of resident warps
         const long long pairs = n_frames - delay;
-        long long run = pairs * n_cent / kSeqGroup / (148LL * 16 * 4);
+        long long run = pairs * n_cent / (148LL * 16 * 4);
         if (run > 64) run = 64;
         if (run < 8LL * delay) run = 8LL * delay;
         if (run > pairs) run = pairs;
@@ -2094,8 +2104,8 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     dim3 grid((warps_needed + warps - 1) / warps, n_frames);
     dim3 grid_l((warps_needed + warps_l - 1) / warps_l, n_frames);
     // frame-sequential grids (fused timeSOAP): one warp per (centre, run of frame pairs)
-    dim3 grid_q((n_atoms + warps * kSeqGroup - 1) / (warps * kSeqGroup), seq ? L.n_runs : 1);
-    dim3 grid_ql((n_atoms + warps_l * kSeqGroup - 1) / (warps_l * kSeqGroup), seq ? L.n_runs : 1);
+    dim3 grid_q((n_atoms + warps - 1) / warps, seq ? L.n_runs : 1);
+    dim3 grid_ql((n_atoms + warps_l - 1) / warps_l, seq ? L.n_runs : 1);
 #define DSG_SOAP_LAUNCH_ONE(KERNEL, GRID, WARPS, SMEM)                                           \
     do {                                                                                         \
         DSG_CUDA_CHECK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, \
