@@ -41,7 +41,12 @@ ATOMIC_NUMBERS = {sym: z for z, sym in enumerate(_SYMBOLS)}
 def _species_indices(types: np.ndarray) -> tuple[np.ndarray, int]:
     """Atom types are used as element symbols (saponify.py:108,111-116); DScribe orders species
     by atomic number.  Returns per-atom species index and the species count."""
-    symbols, inverse = np.unique(np.asarray(types).astype(str), return_inverse=True)
+    types = np.asarray(types)
+    if types.size and bool((types == types[0]).all()):
+        # one species (the common case): no sort of 1e5 strings on the critical path of a call
+        symbols, inverse = np.asarray([str(types[0])]), np.zeros(types.size, dtype=np.intp)
+    else:
+        symbols, inverse = np.unique(types.astype(str), return_inverse=True)
     try:
         z_of_symbol = np.asarray([ATOMIC_NUMBERS[str(sym)] for sym in symbols], dtype=np.int64)
     except KeyError as exc:
@@ -55,6 +60,8 @@ def _centre_positions(sel: Any, centers: str) -> np.ndarray:
     """Selection-local indices of the centre atoms, in selection order (saponify.py:92-95)."""
     sel_ix = np.asarray(sel.indices)
     cen_ix = np.asarray(sel.select_atoms(centers).indices)
+    if cen_ix.size == sel_ix.size:   # every selected atom is a centre (e.g. centers="all")
+        return np.arange(sel_ix.size, dtype=np.int32)
     return np.nonzero(np.isin(sel_ix, cen_ix))[0].astype(np.int32)
 
 
