@@ -1672,6 +1672,219 @@ soap_spectrum_kernel(const SoapArgs a, const SpecTask* __restrict__ tasks, int n
     }  // frame loop (SEQ)
 }
 
+// Split mode, second kernel on the fp64 tensor path (n_max <= 8, up to 4 species): the same
+// register-to-register products as the fused epilogue of soap_kernel, per angular momentum:
+//   mixing    D_z (n' x cols) = Bm_l (n' x k) * G_z,l (k x cols): lane (col = lane >> 2, ji) takes
+//             G[z][l^2 + col][2 ji, 2 ji + 1] as its B entries, two products per 8-column tile
+//   spectrum  P_zz' (n x n') = sum over the columns of w^2 D_z[n][col] D_z'[n'][col] for z <= z'
+// One block of four warps per centre, warp w takes l = w, w + 4, ....  The primitive sums of a
+// (centre, frame) -- 8 S (l_max+1)^2 n bytes, 23 KB at cfg4 -- are copied from the scratch to
+// shared memory with cp.async; SEQ: the block walks the frames of its run, the copy of frame f + 1
+// is in flight while frame f is processed (the version that loaded the fragments straight from
+// global memory spent its time waiting for them: 9 % of the HBM bandwidth, tensor pipe 29 % busy),
+// and every spectrum is folded into the timeSOAP sums (partial sums of the four warps meet in
+// shared memory).  RS (SEQ, delay = 1): the previous spectrum of the centre stays in shared memory,
+// one lane-private slot per (l, species pair, element) -- the global ring cost 2 x 8 C bytes of HBM
+// traffic per centre-frame (C = 3300 at cfg4: 21 of the 30 GB the kernel moved).
+constexpr int kSpecWarps = 4;
+__device__ __forceinline__ void cp_async_bytes(double* dst_smem, const double* src, int n_doubles,
+                                               int tid, int n_threads) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(dst_smem);
+    if ((n_doubles & 1) == 0 && (((size_t)src) & 15) == 0) {
+        for (int i = tid; i < n_doubles / 2; i += n_threads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i),
+                         "l"(src + 2 * i));
+    } else {
+        for (int i = tid; i < n_doubles; i += n_threads)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * i),
+                         "l"(src + i));
+    }
+    asm volatile("cp.async.commit_group;");
+}
+
+// one angular momentum with NT tiles (compile time: exact product counts, no predication)
+template <int S, int NT, bool SEQ, bool RS>
+__device__ __forceinline__ void spectrum_one_l(const SoapArgs& a, int l, const double* __restrict__ gs,
+                                               const double* __restrict__ bm8,
+                                               const double* __restrict__ wq, double* ring,
+                                               double* ring_s, double* out_row, int lane,
+                                               double& csq, double& dot) {
+    constexpr int kPairs = S * (S + 1) / 2;
+    const int n = a.plan.n_max, n_lm = a.plan.n_lm, l_max = a.plan.l_max;
+    const int na = lane >> 2, nb0 = 2 * (lane & 3);
+    const int blk_d = n * (n + 1) / 2, blk_o = n * n;
+    // offsets of the lane's two elements inside one l block of a diagonal / off-diagonal pair
+    const int off_d = na * n - (na * (na - 1)) / 2 + nb0 - na, off_o = na * n + nb0;
+    const bool okd0 = na <= nb0 && nb0 < n, okd1 = na <= nb0 + 1 && nb0 + 1 < n;
+    const bool oko0 = na < n && nb0 < n, oko1 = na < n && nb0 + 1 < n;
+    const double2 bm = *reinterpret_cast<const double2*>(bm8 + l * 64 + na * 8 + nb0);
+    // the ring values of this l first: none of their loads waits behind a ring store
+    [[maybe_unused]] double rv[kPairs][2];
+    if (SEQ) {
+        int base = 0, q = 0;
+#pragma unroll
+        for (int zi = 0; zi < S; ++zi)
+#pragma unroll
+            for (int zj = zi; zj < S; ++zj, ++q) {
+                const bool diag = zi == zj;
+                const int c = base + l * (diag ? blk_d : blk_o) + (diag ? off_d : off_o);
+                if (RS) {
+                    rv[q][0] = ring_s[((l * kPairs + q) * 2) * 32];
+                    rv[q][1] = ring_s[((l * kPairs + q) * 2 + 1) * 32];
+                } else {
+                    rv[q][0] = (diag ? okd0 : oko0) ? ring[c] : 0.0;
+                    rv[q][1] = (diag ? okd1 : oko1) ? ring[c + 1] : 0.0;
+                }
+                base += (diag ? blk_d : blk_o) * (l_max + 1);
+            }
+    }
+    double d[S][NT][2];
+#pragma unroll
+    for (int z = 0; z < S; ++z)
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const int col = 8 * t + na;
+            double g0 = 0.0, g1 = 0.0;
+            if (col < 2 * l + 1) {
+                const double* __restrict__ gp = gs + ((size_t)z * n_lm + l * l + col) * n + nb0;
+                if (n == 8) {
+                    const double2 g = *reinterpret_cast<const double2*>(gp);
+                    g0 = g.x;
+                    g1 = g.y;
+                } else {
+                    if (nb0 < n) g0 = gp[0];
+                    if (nb0 + 1 < n) g1 = gp[1];
+                }
+            }
+            d[z][t][0] = d[z][t][1] = 0.0;
+            dmma_8x8x4(d[z][t][0], d[z][t][1], bm.x, g0);
+            dmma_8x8x4(d[z][t][0], d[z][t][1], bm.y, g1);
+        }
+    int base = 0, q = 0;   // first feature of the species pair, its number
+#pragma unroll
+    for (int zi = 0; zi < S; ++zi)
+#pragma unroll
+        for (int zj = zi; zj < S; ++zj, ++q) {
+            double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const double2 w = *reinterpret_cast<const double2*>(wq + (l * 4 + t) * 8 + nb0);
+                dmma_8x8x4(p0, p1, d[zi][t][0] * w.x, d[zj][t][0]);
+                dmma_8x8x4(p0, p1, d[zi][t][1] * w.y, d[zj][t][1]);
+            }
+            const bool diag = zi == zj;
+            const int c = base + l * (diag ? blk_d : blk_o) + (diag ? off_d : off_o);
+            const bool ok0 = diag ? okd0 : oko0, ok1 = diag ? okd1 : oko1;
+            if (SEQ) {
+                if (ok0) {
+                    csq = fma(p0, p0, csq);
+                    dot = fma(p0, rv[q][0], dot);
+                    if (RS) ring_s[((l * kPairs + q) * 2) * 32] = p0;
+                    else ring[c] = p0;
+                }
+                if (ok1) {
+                    csq = fma(p1, p1, csq);
+                    dot = fma(p1, rv[q][1], dot);
+                    if (RS) ring_s[((l * kPairs + q) * 2 + 1) * 32] = p1;
+                    else ring[c + 1] = p1;
+                }
+            }
+            if (out_row) {
+                if (ok0) out_row[c] = p0;
+                if (ok1) out_row[c + 1] = p1;
+            }
+            base += (diag ? blk_d : blk_o) * (l_max + 1);
+        }
+}
+
+template <int S, bool SEQ, bool RS>
+__global__ void __launch_bounds__(32 * kSpecWarps)
+soap_spectrum_mma_kernel(const SoapArgs a) {
+    extern __shared__ __align__(16) double smem_all[];
+    const SoapPlan& pl = a.plan;
+    const int n = pl.n_max, n_lm = pl.n_lm, l_max = pl.l_max;
+    constexpr int kPairs = S * (S + 1) / 2;
+    const int g_doubles = S * n_lm * n, g_stride = (g_doubles + 1) & ~1;
+    double* bm8 = smem_all;                        // [l][n'][k] padded to 8 x 8
+    double* wq = bm8 + (l_max + 1) * 64;           // [l][4 tiles][8] squared m-weights, 0 in the pads
+    double* part = wq + (l_max + 1) * 32;          // [2][kSpecWarps][2] partial (csq, dot)
+    double* gbuf = part + 4 * kSpecWarps;          // [SEQ ? 2 : 1][g_stride] primitive sums
+    [[maybe_unused]] double* ring_s = gbuf + (SEQ ? 2 : 1) * g_stride + (threadIdx.x & 31);
+    const int ci = blockIdx.x;
+    const int t0 = SEQ ? blockIdx.y * a.seq_run : 0;
+    const int n_fr = SEQ ? min(a.n_frames - a.delay, t0 + a.seq_run) - t0 + a.delay : 1;
+    const int f_first = SEQ ? t0 : (int)blockIdx.y;
+    cp_async_bytes(gbuf, a.gscr + ((size_t)f_first * a.n_cent + ci) * g_doubles, g_doubles,
+                   threadIdx.x, blockDim.x);
+    for (int i = threadIdx.x; i < (l_max + 1) * 64; i += blockDim.x) {
+        const int l = i >> 6, np = (i >> 3) & 7, kq = i & 7;
+        bm8[i] = (np < n && kq < n) ? a.bmat[((size_t)l * n + np) * n + kq] : 0.0;
+    }
+    for (int i = threadIdx.x; i < (l_max + 1) * 32; i += blockDim.x) {
+        const int l = i >> 5, col = i & 31;
+        const double w = col < 2 * l + 1 ? a.swlm[l * l + col] : 0.0;
+        wq[i] = w * w;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    [[maybe_unused]] double prev_sq = 0.0;
+    for (int fo = 0; fo < n_fr; ++fo) {
+        const int f = f_first + fo;
+        const double* gs = gbuf + (fo & 1) * g_stride;
+        // frame f has landed (and the tables, first trip); every warp is done with frame f - 1,
+        // whose buffer the copy of frame f + 1 overwrites
+        asm volatile("cp.async.wait_group 0;");
+        __syncthreads();
+        if (SEQ && fo + 1 < n_fr)
+            cp_async_bytes(gbuf + ((fo + 1) & 1) * g_stride,
+                           a.gscr + ((size_t)(f + 1) * a.n_cent + ci) * g_doubles, g_doubles,
+                           threadIdx.x, blockDim.x);
+        double* out_row =
+            a.out ? a.out + (long long)ci * a.stride_i + (long long)f * a.stride_f : nullptr;
+        double* ring = nullptr;
+        if (SEQ) {
+            if (!RS)
+                ring = a.ring + (((size_t)blockIdx.y * a.n_cent + ci) * a.delay +
+                                 (size_t)(f % a.delay)) * (size_t)(pl.n_feat + 1);
+            if (min(f / a.seq_run, (int)gridDim.y - 1) != (int)blockIdx.y) out_row = nullptr;
+        }
+        double csq = 0.0, dot = 0.0;
+        for (int l = warp; l <= l_max; l += kSpecWarps) {
+            const int nt = (2 * l + 1 + 7) >> 3;
+            if (nt == 1)
+                spectrum_one_l<S, 1, SEQ, RS>(a, l, gs, bm8, wq, ring, ring_s, out_row, lane, csq, dot);
+            else if (nt == 2)
+                spectrum_one_l<S, 2, SEQ, RS>(a, l, gs, bm8, wq, ring, ring_s, out_row, lane, csq, dot);
+            else if (nt == 3)
+                spectrum_one_l<S, 3, SEQ, RS>(a, l, gs, bm8, wq, ring, ring_s, out_row, lane, csq, dot);
+            else
+                spectrum_one_l<S, 4, SEQ, RS>(a, l, gs, bm8, wq, ring, ring_s, out_row, lane, csq, dot);
+        }
+        if (SEQ) {
+            csq = warp_sum(csq);
+            dot = warp_sum(dot);
+            double* pp = part + (fo & 1) * 2 * kSpecWarps;   // double-buffered: the barrier at the top
+            if (lane == 0) {                                  // of the next trip separates the uses
+                pp[2 * warp] = csq;
+                pp[2 * warp + 1] = dot;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double cs = 0.0, dt = 0.0;
+#pragma unroll
+                for (int w = 0; w < kSpecWarps; ++w) {
+                    cs += pp[2 * w];
+                    dt += pp[2 * w + 1];
+                }
+                double* ring_sq = RS ? &prev_sq : ring + pl.n_feat;
+                if (fo >= a.delay)
+                    a.ts_out[(long long)ci * a.ts_ld + a.ts_col0 + (f - a.delay)] =
+                        soap_dist_from_sums(*ring_sq, cs, dt);
+                *ring_sq = cs;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -2160,7 +2373,37 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
 #undef DSG_SOAP_LAUNCH
 #undef DSG_SOAP_LAUNCH_ONE
     DSG_LAUNCH_CHECK("soap_kernel");
-    if (split) {
+    if (split && DSG_SOAP_MMA && n_max <= 8 && n_species <= 4) {
+        // tables + partial sums + (delay = 1) the ring: 64 doubles per (l, species pair)
+        // tables + partial sums + one (SEQ: two) buffers of primitive sums + (delay = 1) the ring:
+        // 64 doubles per (l, species pair)
+        const size_t g_stride = ((size_t)n_species * n_lm * n_max + 1) & ~(size_t)1;
+        const size_t tab_bytes =
+            8 * ((size_t)(l_max + 1) * 96 + 4 * kSpecWarps + (seq ? 2 : 1) * g_stride);
+        const size_t ring_bytes = 8 * (size_t)(l_max + 1) * (n_species * (n_species + 1) / 2) * 64;
+        const bool ring_smem = seq && delay == 1 && tab_bytes + ring_bytes <= 100 * 1024;
+        const size_t ssm = tab_bytes + (ring_smem ? ring_bytes : 0);
+        dim3 sgrid(n_cent, seq ? L.n_runs : n_frames);
+#define DSG_SPEC_LAUNCH_ONE(S, SEQ, RS)                                                           \
+    do {                                                                                          \
+        DSG_CUDA_CHECK(cudaFuncSetAttribute((soap_spectrum_mma_kernel<S, SEQ, RS>),               \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                            (int)ssm));                                           \
+        soap_spectrum_mma_kernel<S, SEQ, RS><<<sgrid, 32 * kSpecWarps, ssm, st>>>(a);             \
+    } while (0)
+#define DSG_SPEC_LAUNCH(S)                                                                        \
+    do {                                                                                          \
+        if (ring_smem) DSG_SPEC_LAUNCH_ONE(S, true, true);                                        \
+        else if (seq) DSG_SPEC_LAUNCH_ONE(S, true, false);                                        \
+        else DSG_SPEC_LAUNCH_ONE(S, false, false);                                                \
+    } while (0)
+        if (n_species == 2) DSG_SPEC_LAUNCH(2);
+        else if (n_species == 3) DSG_SPEC_LAUNCH(3);
+        else DSG_SPEC_LAUNCH(4);
+#undef DSG_SPEC_LAUNCH
+#undef DSG_SPEC_LAUNCH_ONE
+        DSG_LAUNCH_CHECK("soap_spectrum_mma_kernel");
+    } else if (split) {
         std::vector<SpecTask> tasks;
         int base = 0;
         const int tiles = (n_max + 1) / 2;
