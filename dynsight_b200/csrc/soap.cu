@@ -498,7 +498,12 @@ __host__ __device__ constexpr int hoff(int l) {
     return l >= 5 ? (8 - l) * kPackSlots : (l - 1) * kPackSlots + pack_size0(l - 1);
 }
 // tensor path: 8-column tiles of the (2l+1) values of one l
-__host__ __device__ constexpr int mma_tiles(int l) { return (2 * l + 1 + 7) / 8; }
+// l = 4, 8, 12 have 8 t + 1 columns: a tile for one column would be 7/8 padding, so their last
+// column (m = +l) is "peeled": accumulated like l = 0 by a scalar FMA per lane (k, j) and handed to
+// the epilogue as a one-column tile (two tiles out of 14 less per four neighbours at l_max = 8)
+__host__ __device__ constexpr bool mma_peeled(int l) { return l > 0 && l % 4 == 0; }
+__host__ __device__ constexpr int mma_cols(int l) { return mma_peeled(l) ? 2 * l : 2 * l + 1; }
+__host__ __device__ constexpr int mma_tiles(int l) { return (mma_cols(l) + 7) / 8; }
 __host__ __device__ constexpr int mma_tile_base(int l) {
     int b = 0;
     for (int i = 1; i < l; ++i) b += mma_tiles(i);
@@ -890,6 +895,7 @@ soap_kernel(const SoapArgs a) {
     constexpr bool MM = DSG_SOAP_MMA != 0;
     [[maybe_unused]] constexpr bool PK = !MM && LT == 8 && S0 == kPackSlots;  // packed rows (see hoff)
     constexpr int kTiles = mma_tile_base(LT + 1);
+    constexpr int kPeel = LT / 4;   // peeled columns (l = 4, 8, 12)
     // list mode: the consumer runs unless a row overflowed, the fallback only if one did
     if (a.list_role != 0 && ((*a.list_flag != 0) != (a.list_role == 2))) return;
     extern __shared__ __align__(16) double smem_all[];
@@ -917,16 +923,22 @@ soap_kernel(const SoapArgs a) {
             bmat_s[i] = (l <= a.plan.l_max && np < nm && kq < nm)
                             ? a.bmat[((size_t)l * nm + np) * nm + kq] : 0.0;
         }
-        for (int i = threadIdx.x; i < 8 * (kTiles + 1); i += blockDim.x) {
-            const int tt = i >> 3, c = i & 7;   // tile 0 = l = 0, then the tiles of l = 1, 2, ...
-            int l = 0, t = 0;
-            if (tt > 0) {
+        for (int i = threadIdx.x; i < 8 * (kTiles + 1 + kPeel); i += blockDim.x) {
+            // tile 0 = l = 0, then the tiles of l = 1, 2, ..., then one single-column tile per
+            // peeled l = 4, 8, ...
+            const int tt = i >> 3, c = i & 7;
+            int l = 0, col = c;
+            bool valid = c == 0;
+            if (tt > kTiles) {
+                l = 4 * (tt - kTiles);
+                col = 2 * l;
+            } else if (tt > 0) {
                 l = 1;
                 while (l < LT && mma_tile_base(l + 1) <= tt - 1) ++l;
-                t = tt - 1 - mma_tile_base(l);
+                col = 8 * (tt - 1 - mma_tile_base(l)) + c;
+                valid = col < mma_cols(l);
             }
-            const int col = 8 * t + c;
-            const double w = (l <= a.plan.l_max && col < 2 * l + 1) ? a.swlm[l * l + col] : 0.0;
+            const double w = (l <= a.plan.l_max && valid) ? a.swlm[l * l + col] : 0.0;
             swlm_s[i] = w * w;
         }
     } else {
@@ -1060,6 +1072,9 @@ soap_kernel(const SoapArgs a) {
         for (int t = 0; t < kMaxItems; ++t)
             gam[t] = (!MM && kact && il[t] >= 0) ? -a.gamma[il[t] * n + k] * kExpScale : 0.0;
         double ct[2 * kTiles];   // tensor path: C fragments
+        [[maybe_unused]] double accp[kPeel > 0 ? kPeel : 1];   // peeled columns of l = 4, 8, 12
+#pragma unroll
+        for (int i = 0; i < kPeel; ++i) accp[i] = 0.0;
 #pragma unroll
         for (int t = 0; t < 2 * kTiles; ++t) ct[t] = 0.0;
         // l = 0: lane (jq, k) sums exp(-gamma_0k r^2) over the neighbours jj = jq (mod 4)
@@ -1113,6 +1128,10 @@ soap_kernel(const SoapArgs a) {
                                 dmma_8x8x4(ct[2 * (mma_tile_base(l) + t)],
                                            ct[2 * (mma_tile_base(l) + t) + 1],
                                            rt[l * l - 1 + 8 * t], e[l]);
+                            // peeled column (m = +l) of the lane's own neighbour (zero row if absent)
+                            if (mma_peeled(l))
+                                accp[l / 4 - 1] = fma(rt[l * l - 1 + 2 * l - (lane >> 2)], e[l],
+                                                      accp[l / 4 - 1]);
                         }
                     }
                     __syncwarp();
@@ -1343,16 +1362,30 @@ soap_kernel(const SoapArgs a) {
         double* cz = SPLIT ? a.gscr + ((size_t)f * a.n_cent + ci) * c_doubles +
                                  (size_t)z_sp * n_lm * n
                            : rbuf;
+        if constexpr (MM) {
+#pragma unroll
+            for (int i = 0; i < kPeel; ++i) {
+                accp[i] += __shfl_xor_sync(kFullS, accp[i], 1);
+                accp[i] += __shfl_xor_sync(kFullS, accp[i], 2);
+            }
+        }
         if constexpr (MM && SPLIT) {
             // C fragments hold G^T: row = column of the tile (lane >> 2), columns = radial 2 ji + {0, 1}
-            if (kact && ji == 0) cz[k] = acc00;  // lm = 0: S_0^0 = 1
+            if (kact && ji == 0) {
+                cz[k] = acc00;  // lm = 0: S_0^0 = 1
+#pragma unroll
+                for (int i = 0; i < kPeel; ++i) {
+                    const int l = 4 * (i + 1);
+                    if (l <= pl.l_max) cz[(l * l + 2 * l) * n + k] = accp[i];
+                }
+            }
             const int k0 = kb * kKBlock + 2 * ji;
 #pragma unroll
             for (int l = 1; l <= LT; ++l)
 #pragma unroll
                 for (int t = 0; t < mma_tiles(l); ++t) {
                     const int col = 8 * t + (lane >> 2);
-                    if (col < 2 * l + 1 && l <= pl.l_max) {
+                    if (col < mma_cols(l) && l <= pl.l_max) {
 #pragma unroll
                         for (int h = 0; h < 2; ++h)
                             if (k0 + h < n)
@@ -1394,6 +1427,16 @@ soap_kernel(const SoapArgs a) {
                         double d0 = 0.0, d1 = 0.0;
                         dmma_8x8x4(d0, d1, bm.x, ct[2 * (mma_tile_base(l) + t)]);
                         dmma_8x8x4(d0, d1, bm.y, ct[2 * (mma_tile_base(l) + t) + 1]);
+                        dmma_8x8x4(p0, p1, d0 * w.x, d0);
+                        dmma_8x8x4(p0, p1, d1 * w.y, d1);
+                    }
+                    if (mma_peeled(l)) {   // the peeled column as a one-column tile, like l = 0
+                        const double ga = __shfl_sync(kFullS, accp[l / 4 - 1], 8 * ji);
+                        const double gb = __shfl_sync(kFullS, accp[l / 4 - 1], 8 * ji + 4);
+                        const double2 w = wq2[(kTiles + l / 4) * 4];
+                        double d0 = 0.0, d1 = 0.0;
+                        dmma_8x8x4(d0, d1, bm.x, na == 0 ? ga : 0.0);
+                        dmma_8x8x4(d0, d1, bm.y, na == 0 ? gb : 0.0);
                         dmma_8x8x4(p0, p1, d0 * w.x, d0);
                         dmma_8x8x4(p0, p1, d1 * w.y, d1);
                     }
@@ -2283,7 +2326,7 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     a.epi_smem_doubles = split ? 0 : (int)((n_lm + (2 * n_feat + n_lm + 7) / 8 + 1) & ~1);
     if (DSG_SOAP_MMA && !split) {   // padded 8 x 8 matrices, squared weights per 8-column tile
         a.bmat_smem_doubles = (lt + 1) * 64;
-        a.epi_smem_doubles = 8 * (mma_tile_base(lt + 1) + 1);
+        a.epi_smem_doubles = 8 * (mma_tile_base(lt + 1) + 1 + lt / 4);
     }
     const size_t shared_tables =
         8 * ((size_t)kExpTabDoubles +

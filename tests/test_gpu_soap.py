@@ -435,3 +435,81 @@ def test_fused_timesoap_vs_oracle_and_api():
         got = dsoap.timesoap_from_trajectory(uni, 5.0, 8, 8, delay=delay, batch_frames=batch,
                                              as_numpy=True)[cent]
         assert np.all(np.abs(got - want) <= 1e-5 * np.abs(want) + 1e-7)
+
+
+# ---------------------------------------------------------------------------------------------
+# the BASELINE configurations at their stated sizes (sampled centres vs the oracle)
+# ---------------------------------------------------------------------------------------------
+def _random_walk(n: int, n_frames: int, box_l: float, step: float, seed: int) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    top = np.nextafter(np.float32(box_l), np.float32(0))
+    cur = rng.random((n, 3)) * box_l
+    out = np.empty((n_frames, n, 3), dtype=np.float32)
+    for f in range(n_frames):
+        cur = np.mod(cur + rng.normal(0, step, cur.shape), box_l)
+        out[f] = np.minimum(cur.astype(np.float32), top)
+    return out
+
+
+def test_cfg5_size_soap_and_fused_timesoap_vs_oracle():
+    """BASELINE.json configs[4] shape (what bench.py times): 100,000 atoms at water-oxygen density,
+    SOAP(5 A, 8, 8) in list mode on the tensor path, three frames.  The spectra of 128 sampled centres
+    and the fused SOAP -> timeSOAP values of the same centres against the oracle chain."""
+    import os
+
+    from dynsight_b200 import engine
+
+    n, n_frames = 100_000, 3
+    box_l = (n / 0.0334) ** (1 / 3)
+    pos = _random_walk(n, n_frames, box_l, 0.1, 21)
+    box = np.full(3, np.float32(box_l), dtype=np.float32)
+    dpos = torch.as_tensor(pos).cuda()
+    sp = torch.zeros(n, dtype=torch.int32, device="cuda")
+    sample = np.linspace(0, n - 1, 128).astype(np.int32)
+    basis = so.gto_basis(5.0, 8, 8)
+    want = np.stack(
+        [so.soap_frame_c(pos[f], np.full(n, 8), sample, box.astype(np.float64), 5.0, 8, 8, basis,
+                         n_threads=os.cpu_count() or 1) for f in range(n_frames)], axis=1,
+    )  # fmt: skip
+    got = engine.soap_power_spectrum(dpos, sp, torch.as_tensor(sample).cuda(), box, 5.0, 8, 8)
+    assert _rel_err(got.cpu().numpy(), want) < REL
+    # the fused kernel on ALL centres (frame-sequential warps, one ring slot per centre)
+    ts = engine.soap_timesoap(dpos, sp, torch.arange(n, dtype=torch.int32, device="cuda"), box,
+                              5.0, 8, 8, delay=1).cpu().numpy()  # fmt: skip
+    want_t = to.timesoap(want, 1)
+    assert ts.shape == (n, n_frames - 1)
+    assert np.all(np.abs(ts[sample] - want_t) <= 1e-5 * np.abs(want_t) + 1e-7)
+    assert np.isfinite(ts).all() and float(ts.min()) >= 0.0
+
+
+def test_cfg4_size_three_species_l10_vs_oracle():
+    """BASELINE.json configs[3] at its stated size: 250,000 atoms, 3 species, l_max = 10, metal
+    density (K ~ 239), two frames through the split-mode kernels (accumulate on the tensor path +
+    soap_spectrum_mma_kernel): spectra of 36 sampled centres and their timeSOAP vs the oracle."""
+    import os
+
+    from dynsight_b200 import engine
+
+    n, n_frames, n_sp = 250_000, 2, 3
+    box_l = (n / 0.0857) ** (1 / 3)
+    pos = _random_walk(n, n_frames, box_l, 0.05, 22)
+    box = np.full(3, np.float32(box_l), dtype=np.float32)
+    sp_idx = (np.arange(n) * 7919) % n_sp
+    z = np.asarray([26, 28, 29])[sp_idx]   # Fe, Ni, Cu: ascending atomic numbers
+    dpos = torch.as_tensor(pos).cuda()
+    sp = torch.as_tensor(sp_idx.astype(np.int32)).cuda()
+    sample = np.linspace(0, n - 1, 36).astype(np.int32)
+    basis = so.gto_basis(5.0, 8, 10)
+    want = np.stack(
+        [so.soap_frame_c(pos[f], z, sample, box.astype(np.float64), 5.0, 8, 10, basis,
+                         n_threads=os.cpu_count() or 1) for f in range(n_frames)], axis=1,
+    )  # fmt: skip
+    got = engine.soap_power_spectrum(dpos, sp, torch.as_tensor(sample).cuda(), box, 5.0, 8, 10,
+                                     n_species=n_sp)  # fmt: skip
+    assert got.shape == (36, n_frames, 3300)
+    assert _rel_err(got.cpu().numpy(), want) < REL
+    ts = engine.soap_timesoap(dpos, sp, torch.arange(n, dtype=torch.int32, device="cuda"), box,
+                              5.0, 8, 10, delay=1, n_species=n_sp).cpu().numpy()  # fmt: skip
+    want_t = to.timesoap(want, 1)
+    assert np.all(np.abs(ts[sample] - want_t) <= 1e-5 * np.abs(want_t) + 1e-7)
+    assert np.isfinite(ts).all()
