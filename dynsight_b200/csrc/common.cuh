@@ -53,6 +53,8 @@ __host__ __device__ inline double py_floordiv(double a, double b) {
 __host__ __device__ inline int cell_of(double x, double box, int ncell) {
     double v = x / box * (double)ncell;
     long long t = (long long)v;  // truncation toward zero, like numba's int()
+    // an atom inside the box (almost every atom) needs no modulo: no 64-bit division on its path
+    if ((unsigned long long)t < (unsigned long long)ncell) return (int)t;
     long long r = t % ncell;
     if (r < 0) r += ncell;
     return (int)r;
