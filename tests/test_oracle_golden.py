@@ -244,3 +244,57 @@ def test_spatial_average_oracle_vs_reference_golden():
     got = spatial_oracle.spatial_average(pos, coex["dims"], values, 5.0)
     assert got.shape == coex["spavg"].shape
     assert np.abs(got - coex["spavg"]).max() <= 1e-12 * np.abs(coex["spavg"]).max()
+
+
+def test_soap_oracle_multi_species_blocks_sum_to_the_single_species_spectrum():
+    """Derived pin of the oracle's multi-species layout (no reference golden has S > 1, DScribe is
+    called with species = set(types) at saponify.py:96): relabelling a one-species system into three
+    species leaves c_nlm = sum_Z c^Z_nlm unchanged, hence p_lnn' = sum_Z p^ZZ_lnn' +
+    sum_{Z<Z'} (p^ZZ'_lnn' + p^ZZ'_ln'n) -- content and (l, n, n') layout of every block against the
+    single-species oracle, which the seven DScribe goldens pin.  Swapping two labels swaps the
+    diagonal blocks and transposes the cross block (species ordered by atomic number)."""
+    rng = np.random.default_rng(3)
+    n, n_max, l_max = 40, 4, 3
+    box = np.array([[21.0, 22.0, 20.5]])
+    pos = rng.random((1, n, 3)) * box
+    cent = np.arange(0, n, 3)
+    one = so.soap_trajectory(pos, np.full(n, 8), cent, box, 4.0, n_max, l_max)[:, 0]
+    z3 = np.asarray([1, 8, 29])[rng.integers(0, 3, n)]
+    three = so.soap_trajectory(pos, z3, cent, box, 4.0, n_max, l_max)[:, 0]
+
+    def blocks(spec, n_species):
+        out, at = {}, 0
+        iu = np.triu_indices(n_max)
+        for zi in range(n_species):
+            for zj in range(zi, n_species):
+                if zi == zj:
+                    size = (l_max + 1) * iu[0].size
+                    tri = spec[:, at : at + size].reshape(-1, l_max + 1, iu[0].size)
+                    full = np.zeros((spec.shape[0], l_max + 1, n_max, n_max))
+                    full[..., iu[0], iu[1]] = tri
+                    full[..., iu[1], iu[0]] = tri
+                else:
+                    size = (l_max + 1) * n_max * n_max
+                    full = spec[:, at : at + size].reshape(-1, l_max + 1, n_max, n_max)
+                out[(zi, zj)] = full
+                at += size
+        assert at == spec.shape[1]
+        return out
+
+    blk = blocks(three, 3)
+    total = sum(blk[(z, z)] for z in range(3))
+    for zi in range(3):
+        for zj in range(zi + 1, 3):
+            total = total + blk[(zi, zj)] + np.swapaxes(blk[(zi, zj)], -1, -2)
+    iu = np.triu_indices(n_max)
+    got = total[..., iu[0], iu[1]].reshape(len(cent), -1)
+    assert np.abs(got - one).max() < 1e-10 * np.abs(one).max()
+    # two species, labels swapped: H (Z = 1) is species 0 either way
+    z2 = np.where(np.arange(n) % 2 == 0, 1, 29)
+    a = blocks(so.soap_trajectory(pos, z2, cent, box, 4.0, n_max, l_max)[:, 0], 2)
+    b = blocks(so.soap_trajectory(pos, np.where(z2 == 1, 29, 1), cent, box, 4.0, n_max, l_max)[:, 0], 2)
+    scale = np.abs(a[(0, 1)]).max()
+    assert np.abs(a[(0, 0)] - b[(1, 1)]).max() < 1e-10 * scale
+    assert np.abs(a[(1, 1)] - b[(0, 0)]).max() < 1e-10 * scale
+    assert np.abs(a[(0, 1)] - np.swapaxes(b[(0, 1)], -1, -2)).max() < 1e-10 * scale
+    assert np.abs(a[(0, 1)] - np.swapaxes(a[(0, 1)], -1, -2)).max() > 1e-3 * scale  # not symmetric
