@@ -53,6 +53,20 @@ class Selection:
         return self._dev_index
 
 
+def to_device_async(arr: np.ndarray) -> torch.Tensor:
+    """Small host array -> device without blocking the host: a pageable ``torch.as_tensor(...,
+    device=...)`` is a synchronous copy on the current stream, i.e. it waits for every kernel
+    already enqueued there (the LENS kernels of the same call, for the SOAP job's index arrays).
+    The page-locked staging buffer comes from torch's caching host allocator, which keeps it alive
+    until the copy has run."""
+    host = torch.from_numpy(np.ascontiguousarray(arr))
+    try:
+        host = host.pin_memory()
+    except RuntimeError:
+        return host.to(device())
+    return host.to(device(), non_blocking=True)
+
+
 def device() -> torch.device:
     if not torch.cuda.is_available():
         msg = (

@@ -271,8 +271,8 @@ class TimesoapJob:
         self.n_feat = soap_basis.n_features(self.n_species, self.n_max, self.l_max)
         self.out = torch.empty((self.n_cent, len(self.fr_idx) - delay), dtype=torch.float64,
                                device=dev)  # fmt: skip
-        self.species_t = torch.as_tensor(sp_idx, device=dev)
-        self.centres_t = torch.as_tensor(centers_list, device=dev)
+        self.species_t = frames.to_device_async(sp_idx)
+        self.centres_t = frames.to_device_async(centers_list)
         self.n_all = len(universe.atoms)
         self.sel_all = frames.Selection(self.sel_ix, self.n_all)
 
