@@ -209,6 +209,16 @@ class ArrayUniverse:
     def from_gro_xtc(cls, topo_file: str | Path, traj_file: str | Path) -> ArrayUniverse:
         topo, _, _ = dsg_io.read_gro(topo_file)
         pos, dims = dsg_io.read_xtc(traj_file)  # native reader: compressed frames included
+        # MDAnalysis reports ``ts.dimensions = None`` for a frame whose box is all zero, which sends
+        # LENS to its bounding-box rule (lens.py:271-274) and SOAP / the spatial average to their
+        # box-less branches; an array-backed universe has one answer for the whole file
+        boxless = ~np.any(dims[:, :3] > 0.0, axis=1)
+        if boxless.all():
+            dims = None
+        elif boxless.any():
+            msg = (f"{traj_file}: {int(boxless.sum())} of {len(boxless)} frames have an all-zero "
+                   "box; mixed boxed / box-less trajectories are not supported")
+            raise ValueError(msg)
         return cls(pos, dims, topo.names, topo.types, topo.ids, topo.resnames)
 
     @classmethod

@@ -102,3 +102,38 @@ def test_reference_coex_trajectory_decodes_to_the_stored_fixture():
     assert hashlib.sha256(np.ascontiguousarray(pos).tobytes()).hexdigest() == str(fx["sha256_all"])
     assert np.array_equal(pos[:, fx["o_index"]], fx["o_positions"])
     assert np.array_equal(dims, fx["dims"])
+
+
+def test_all_zero_box_means_no_box_like_mdanalysis(tmp_path):
+    """MDAnalysis hands out ``ts.dimensions = None`` for a frame whose box is all zero (then LENS
+    uses the bounding-box rule of lens.py:271-274): ``from_gro_xtc`` turns such a file into a
+    box-less universe; a file that mixes boxed and box-less frames is refused."""
+    from dynsight_b200.universe import ArrayUniverse
+
+    rng = np.random.default_rng(2)
+    n, nf = 5, 3
+    xyz = rng.random((nf, n, 3)).astype(np.float32) * 3
+
+    def write(boxes, name):
+        raw = b""
+        for f in range(nf):
+            raw += struct.pack(">iiif", 1995, n, f, 0.1 * f)
+            b = boxes[f]
+            raw += struct.pack(">9f", b, 0, 0, 0, b, 0, 0, 0, b)
+            raw += struct.pack(">i", n) + xyz[f].astype(">f4").tobytes()
+        path = tmp_path / name
+        path.write_bytes(raw)
+        return path
+
+    gro = tmp_path / "t.gro"
+    lines = ["t", f"{n:5d}"]
+    for i in range(n):
+        lines.append(f"{1:5d}{'RES':<5s}{'O':>5s}{i + 1:5d}{xyz[0, i, 0]:8.3f}{xyz[0, i, 1]:8.3f}{xyz[0, i, 2]:8.3f}")
+    lines.append("   3.00000   3.00000   3.00000")
+    gro.write_text("\n".join(lines) + "\n")
+    uni = ArrayUniverse.from_gro_xtc(gro, write([0.0, 0.0, 0.0], "nobox.xtc"))
+    assert uni.trajectory[0].dimensions is None
+    boxed = ArrayUniverse.from_gro_xtc(gro, write([3.0, 3.0, 3.0], "box.xtc"))
+    assert np.allclose(boxed.trajectory[1].dimensions, [30.0, 30.0, 30.0, 90, 90, 90])
+    with pytest.raises(ValueError, match="all-zero"):
+        ArrayUniverse.from_gro_xtc(gro, write([3.0, 0.0, 3.0], "mixed.xtc"))
