@@ -513,7 +513,10 @@ def run_b200(args: argparse.Namespace) -> None:
         )
         return sum(v.nbytes for v in res.values())
 
-    for _ in range(2):  # warm-up: page-locked result buffers enter the host allocator's cache
+    # warm-up (the same W as the device-timed loop, at least 3): the page-locked result buffers
+    # enter the host allocator's cache -- a cudaHostAlloc of 77 MB inside the timed region costs
+    # 10 ms alone and 40-60 ms when the eight processes of a box allocate at the same time
+    for _ in range(max(3, args.warmup)):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
