@@ -50,6 +50,9 @@ constexpr int kOpenCellsPerAxis = 32;
 #define DSG_SOAP_MIN_BLOCKS_L10 4
 #endif
 // Build-time switches of the measured variants (defaults = what ships)
+#ifndef DSG_SOAP_MMA_BLOCKS_L10
+#define DSG_SOAP_MMA_BLOCKS_L10 2  // resident blocks per SM of the l_max = 9..12 tensor-path kernels
+#endif
 #ifndef DSG_SOAP_MMA
 #define DSG_SOAP_MMA 1             // phase C on the fp64 tensor path (DMMA.8x8x4), see soap_kernel
 #endif
@@ -879,7 +882,7 @@ __global__ void __launch_bounds__(
     DSG_SOAP_MMA ? 128 : ((LIST && S0 <= 20) ? 32 * kListWarps : 64),
     // tensor path: four warps share the 16 KB exponential table; 3 blocks per SM (168 registers)
     // up to l_max = 8, 2 blocks (255 registers: 40 / 56 accumulator registers more) beyond
-    DSG_SOAP_MMA ? (LT <= 8 ? 3 : 2)
+    DSG_SOAP_MMA ? (LT <= 8 ? 3 : DSG_SOAP_MMA_BLOCKS_L10)
                  : ((S0 <= 20) ? (LIST ? DSG_SOAP_LIST_BLOCKS : DSG_SOAP_MIN_BLOCKS)
                                : (S0 <= 21 ? DSG_SOAP_MIN_BLOCKS_L10 : 4)))
 soap_kernel(const SoapArgs a) {
