@@ -247,8 +247,8 @@ def workload_config(args: argparse.Namespace) -> dict:
         "frames_per_step": args.frames_per_step,
         "frame_sharding": "contiguous frame blocks per rank, 1-frame NCCL halo per step",
         "l2_policy": (
-            "each step reads a different resident frame block; SOAP spectra of a block "
-            "(>8 GB) exceed L2 (126 MB)"
+            "each step reads a different resident frame block; the working set of a step "
+            "(neighbour rows 3 GB, sorted coordinates, rings) exceeds L2 (126 MB)"
         ),
     }
 
@@ -463,8 +463,12 @@ def run_b200(args: argparse.Namespace) -> None:
     soap_traffic, soap_traffic_src = traffic_for("soap_kernel", n_atoms, bsz + 1)
     lens_traffic, lens_traffic_src = traffic_for("lens_pair_pipeline", n_atoms, bsz + 1)
     roofline = {
-        "kernel": "soap_kernel<8,20,0,0,0,false,LIST=true,SEQ=true> (SOAP with the timeSOAP distance "
-                  "folded into the spectrum epilogue; + soap_list_kernel, binning)",
+        "kernel": "soap_kernel<8,20,0,0,0,SPLIT=false,LIST=true,SEQ=true> (tensor path: phase C, "
+                  "Loewdin mixing and the power spectrum as DMMA.8x8x4 products, timeSOAP folded into "
+                  "the epilogue; + soap_list_kernel, binning)",
+        "pipe_note": "DMMA.8x8x4 (mma.sync.m8n8k4.f64) and DFMA share the fp64 pipe at 32 flop/clk/SMSP "
+                     "(scripts/probes/dmma_issue_probe.cu), so the DFMA probe is the peak of both; tile "
+                     "padding, harmonics and exponentials are not counted as flops",
         "bound": "fp64",
         "achieved": soap_tflops,
         "peak": fp64_peak_tflops,
