@@ -50,6 +50,9 @@ constexpr int kOpenCellsPerAxis = 32;
 #define DSG_SOAP_MIN_BLOCKS_L10 4
 #endif
 // Build-time switches of the measured variants (defaults = what ships)
+#ifndef DSG_SOAP_MMA_BLOCKS_L8
+#define DSG_SOAP_MMA_BLOCKS_L8 3   // resident blocks per SM of the l_max <= 8 tensor-path kernels (168 registers)
+#endif
 #ifndef DSG_SOAP_MMA_BLOCKS_L10
 #define DSG_SOAP_MMA_BLOCKS_L10 2  // resident blocks per SM of the l_max = 9..12 tensor-path kernels
 #endif
@@ -395,9 +398,20 @@ struct Acc {
 // exponent without masking j out first.
 // The caller guarantees t >= -690 * kExpScale (2^n stays normal): soap_layout rejects cutoffs
 // for which gamma * r^2 could exceed 690.
+#ifndef DSG_SOAP_EXP_DEG3
+#define DSG_SOAP_EXP_DEG3 0   // measured variant: 256-entry table in 8 copies, economised cubic (1.8e-14)
+#endif
+#if DSG_SOAP_EXP_DEG3
+constexpr int kExpTab = 256;
+constexpr int kExpRep = 8;
+constexpr int kExpHiShift = 12;
+constexpr double kExpScale = 369.3299304675746;      // 256 * log2(e)
+__constant__ double kExpPoly[4] = {   // Chebyshev-economised cubic of e^u on |u| <= ln2/512, in v
+    2.7076061740622624e-03, 3.6655661567589036e-06, 3.308303059503886e-09, 0.9999999999999825,
+};
+#else
 constexpr int kExpTab = 128;
 constexpr int kExpRep = 16;
-constexpr int kExpTabDoubles = kExpTab * kExpRep;   // 16 KB per block
 constexpr int kExpHiShift = 13;                      // 20 - log2(kExpTab)
 constexpr double kExpScale = 184.6649652337873;      // 128 * log2(e)
 __constant__ double kExpPoly[4] = {
@@ -406,6 +420,8 @@ __constant__ double kExpPoly[4] = {
     2.6466421444330967e-08,   // (ln2/128)^3 / 3!
     3.583032305400251e-11,    // (ln2/128)^4 / 4!
 };
+#endif
+constexpr int kExpTabDoubles = kExpTab * kExpRep;   // 16 KB per block
 // g = gamma * kExpScale (negative), s = r^2, tab = the lane's copy of the table.  The product
 // enters only through two FMAs: rint(g s) by the magic-constant trick and the remainder
 // v = g s - rint(g s) with a single rounding, so the argument is never rounded to float64 (one
@@ -419,10 +435,16 @@ __device__ __forceinline__ double exp_scaled(double g, double s, const double* _
     const double tn = fma(g, s, magic);
     const double sc = exp_scale_factor(__double2loint(tn), tab);  // 2^n 2^(j/128), 128 n + j = rint(g s)
     const double v = fma(g, s, magic - tn);                      // [-1/2, 1/2]
+#if DSG_SOAP_EXP_DEG3
+    double p = fma(kExpPoly[2], v, kExpPoly[1]);
+    p = fma(p, v, kExpPoly[0]);
+    p = fma(p, v, kExpPoly[3]);
+#else
     double p = fma(kExpPoly[3], v, kExpPoly[2]);
     p = fma(p, v, kExpPoly[1]);
     p = fma(p, v, kExpPoly[0]);
     p = fma(p, v, 1.0);
+#endif
     return sc * p;
 }
 
@@ -440,6 +462,14 @@ __device__ __forceinline__ void exp_scaled_batch(const double (&g)[NE], double s
     for (int i = 0; i < NE; ++i) v[i] = fma(g[i], s, magic - tn[i]);
 #pragma unroll
     for (int i = 0; i < NE; ++i) sc[i] = exp_scale_factor(__double2loint(tn[i]), tab);
+#if DSG_SOAP_EXP_DEG3
+#pragma unroll
+    for (int i = 0; i < NE; ++i) p[i] = fma(kExpPoly[2], v[i], kExpPoly[1]);
+#pragma unroll
+    for (int i = 0; i < NE; ++i) p[i] = fma(p[i], v[i], kExpPoly[0]);
+#pragma unroll
+    for (int i = 0; i < NE; ++i) p[i] = fma(p[i], v[i], kExpPoly[3]);
+#else
 #pragma unroll
     for (int i = 0; i < NE; ++i) p[i] = fma(kExpPoly[3], v[i], kExpPoly[2]);
 #pragma unroll
@@ -448,6 +478,7 @@ __device__ __forceinline__ void exp_scaled_batch(const double (&g)[NE], double s
     for (int i = 0; i < NE; ++i) p[i] = fma(p[i], v[i], kExpPoly[0]);
 #pragma unroll
     for (int i = 0; i < NE; ++i) p[i] = fma(p[i], v[i], 1.0);
+#endif
 #pragma unroll
     for (int i = 0; i < NE; ++i) e[i] = sc[i] * p[i];
 }
@@ -882,7 +913,7 @@ __global__ void __launch_bounds__(
     DSG_SOAP_MMA ? 128 : ((LIST && S0 <= 20) ? 32 * kListWarps : 64),
     // tensor path: four warps share the 16 KB exponential table; 3 blocks per SM (168 registers)
     // up to l_max = 8, 2 blocks (255 registers: 40 / 56 accumulator registers more) beyond
-    DSG_SOAP_MMA ? (LT <= 8 ? 3 : DSG_SOAP_MMA_BLOCKS_L10)
+    DSG_SOAP_MMA ? (LT <= 8 ? DSG_SOAP_MMA_BLOCKS_L8 : DSG_SOAP_MMA_BLOCKS_L10)
                  : ((S0 <= 20) ? (LIST ? DSG_SOAP_LIST_BLOCKS : DSG_SOAP_MIN_BLOCKS)
                                : (S0 <= 21 ? DSG_SOAP_MIN_BLOCKS_L10 : 4)))
 soap_kernel(const SoapArgs a) {
