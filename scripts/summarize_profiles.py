@@ -102,8 +102,10 @@ def launch_shares(csv_name: str, out_csv: str, out_txt: str):
         tot[k] += v
         cnt[k] += 1
     all_ms = sum(tot.values())
-    lines = [f"launch shares of `python bench.py --no-extra` under ncu (first {sum(cnt.values())} launches, "
-             f"{all_ms:.1f} ms of kernel time; cold-cache, serialised: compare shares, not absolutes)", ""]
+    lines = [f"launch shares of `python bench.py --no-extra` under ncu (the library's own kernels, first "
+             f"{sum(cnt.values())} launches = warm-up + timed device steps + end-to-end steps + parity "
+             f"block, {all_ms:.1f} ms of kernel time; cold-cache, serialised: compare shares, not "
+             f"absolutes)", ""]
     for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
         lines.append(f"{100 * v / all_ms:6.2f} %  {v:10.3f} ms  {cnt[k]:5d} launches  {k}")
     (OUT / out_txt).write_text("\n".join(lines) + "\n")
