@@ -1,20 +1,32 @@
 // soap.cu -- SOAP power spectrum (GTO radial basis, sigma = 1) batched over frames (sm_100a).
 //
-// Replaces the DScribe call of soapify/saponify.py:98-122.  One warp owns one centre; centres are
-// visited in cell order so that the warps resident on an SM read the same candidate cells:
+// Replaces the DScribe call of soapify/saponify.py:98-122 and, fused with the timeSOAP distance,
+// the chain trajectory.py:267-320 -> insight.py:136-155 -> timesoap.py:130-179.  One warp owns one
+// centre:
 //
 //   gather   every periodic image within R = r_cut + sqrt(-2 ln 1e-3) is found through a cell list
 //            (cell edge >= R; axes shorter than 3R fall back to an explicit image loop; a
-//            non-periodic frame uses an open bounding-box grid); hits are ballot-compacted into a
+//            non-periodic frame uses an open bounding-box grid).  List mode (periodic, >= 3 cells
+//            per axis): soap_list_kernel searches with one thread per centre and the warp fetches
+//            32 listed neighbours per round trip; otherwise hits are ballot-compacted into a
 //            32-entry displacement list in shared memory (next batch prefetched)
-//   phase B  one lane per neighbour evaluates the un-normalised regular solid harmonics r^l Y_lm
-//            with fully unrolled polynomial recursions (no sqrt, no division, exact at r = 0)
-//   phase C  lane (g, k) owns radial index k and a load-balanced group g of angular momenta; it
-//            evaluates its Gaussians exp(-gamma_lk r^2) (each needed exponential exactly once per
-//            neighbour, branch-free float64 exp) and accumulates G_lkm in registers, reading the
-//            harmonics as 128-bit shared-memory broadcasts
-//   epilogue Loewdin mixing c = (beta * prefactor) G (scaled by sqrt of the m-weights) in shared
-//            memory, then one lane per output contracts over m and writes the spectrum coalesced.
+//   phase B  two lanes per neighbour (even / odd orders m) evaluate the un-normalised regular solid
+//            harmonics r^l Y_lm of 16 neighbours with fully unrolled polynomial recursions (no sqrt,
+//            no division, exact at r = 0) into dense shared-memory rows
+//   phase C  tensor path: per l, G_l^T (cols x 8 radial) += Y_l^T (cols x 4 neighbours) E_l (4 x 8)
+//            as DMMA.8x8x4 (mma.sync.m8n8k4.f64); lane (k = lane >> 2, j = lane & 3) evaluates the
+//            Gaussians exp(-gamma_lk r_j^2) -- each needed exponential exactly once, branch-free
+//            float64 exp, 8 operations -- straight into its B fragment
+//   epilogue Loewdin mixing D = Bm G and the power spectrum P = sum_m w^2 D D^T as DMMA products on
+//            the C fragments of phase C (nothing leaves the registers); the lane writes its two
+//            elements of every P_l and / or folds them into the timeSOAP sums against the spectrum
+//            the same warp computed `delay` frames earlier (ring in L2).
+//   Several species / n_max > 8 (split mode): the primitive sums G go to a scratch and
+//   soap_spectrum_mma_kernel (tensor path, cp.async staging) or soap_spectrum_kernel finishes.
+//
+// The scalar-FMA form of phase C and the shared-memory epilogue of round 1 (lane (g, k) = radial
+// index k x a group g of angular momenta, 20 FMAs + ten 128-bit shared loads per neighbour) stay
+// selectable with -DDSG_SOAP_MMA=0 for A/B measurements.
 //
 // float64 throughout: the Loewdin matrices have entries of order 1e3..1e6 and cancel, so primitive
 // sums need double precision to meet 1e-5 relative (SURVEY.md section 7 "hard parts").
@@ -77,12 +89,6 @@ constexpr int kOpenCellsPerAxis = 32;
 #endif
 #ifndef DSG_SOAP_TILE_SPECTRUM
 #define DSG_SOAP_TILE_SPECTRUM 1   // fused epilogue: 2x2 register tiles for n_max = 8
-#endif
-#ifndef DSG_SOAP_EXP_ESTRIN
-#define DSG_SOAP_EXP_ESTRIN 0      // Estrin instead of Horner in exp_scaled (two more operations)
-#endif
-#ifndef DSG_SOAP_KO_HALFLOADS
-#define DSG_SOAP_KO_HALFLOADS 0    // timing probe: half of the harmonics loads of phase C (wrong results)
 #endif
 #ifndef DSG_SOAP_EXTRA_SMEM
 #define DSG_SOAP_EXTRA_SMEM 0      // occupancy probe: dummy dynamic shared memory per block
@@ -677,23 +683,6 @@ __device__ __forceinline__ void accumulate_packed(Acc<kPackSlots>& a, double e0,
         a.v[2 * s] = fma(e0, v.x, a.v[2 * s]);
         a.v[2 * s + 1] = fma(e0, v.y, a.v[2 * s + 1]);
     }
-#if DSG_SOAP_KO_HALFLOADS   // timing probe only (wrong results): how much do the shared loads cost?
-    double2 v = r2p[0];
-    a.v[10] = fma(e0, v.x, a.v[10]);
-    a.v[11] = fma(ea, v.y, a.v[11]);
-    v = r2p[1];
-    a.v[12] = fma(ea, v.x, a.v[12]);
-    a.v[13] = fma(eb, v.y, a.v[13]);
-    v = r2p[2];
-    a.v[14] = fma(eb, v.x, a.v[14]);
-    a.v[15] = fma(ec, v.y, a.v[15]);
-    v = r2p[3];
-    a.v[16] = fma(ec, v.x, a.v[16]);
-    a.v[17] = fma(e1, v.y, a.v[17]);
-    v = r2p[4];
-    a.v[18] = fma(e1, v.x, a.v[18]);
-    a.v[19] = fma(e1, v.y, a.v[19]);
-#else
     double2 v = r2p[5];
     a.v[10] = fma(e0, v.x, a.v[10]);
     a.v[11] = fma(ea, v.y, a.v[11]);
@@ -709,7 +698,6 @@ __device__ __forceinline__ void accumulate_packed(Acc<kPackSlots>& a, double e0,
     v = r2p[9];
     a.v[18] = fma(e1, v.x, a.v[18]);
     a.v[19] = fma(e1, v.y, a.v[19]);
-#endif
 }
 
 // C (8x8) += A (8x4) * B (4x8) on the fp64 tensor path.  Fragments (PTX m8n8k4): A[row = lane >> 2]

@@ -379,7 +379,7 @@ def test_multi_species_block_order_and_orientation_derived():
 @pytest.mark.parametrize(
     ("n_species", "n_max", "l_max", "periodic"),
     [(1, 8, 8, True), (1, 4, 4, True), (1, 6, 6, False), (3, 8, 10, True), (2, 4, 3, True),
-     (1, 12, 5, True)],
+     (1, 12, 5, True), (4, 5, 4, True), (2, 8, 12, False)],
 )
 def test_fused_timesoap_equals_two_kernel_path(n_species, n_max, l_max, periodic):
     """engine.soap_timesoap == soap_power_spectrum + timesoap_device (to rounding) for the fused
