@@ -186,7 +186,8 @@ __device__ __forceinline__ bool in_grid(double x, double box, int ncell) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 cell_assign_kernel(const T* __restrict__ pos, int n_atoms, FrameParams* __restrict__ fp,
-                   unsigned* __restrict__ cell_id, int* __restrict__ cell_cnt) {
+                   unsigned* __restrict__ cell_id, int* __restrict__ cell_cnt,
+                   unsigned long long* __restrict__ rank_out = nullptr) {
     const int f = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const FrameParams* p = fp + f;
@@ -205,7 +206,13 @@ cell_assign_kernel(const T* __restrict__ pos, int n_atoms, FrameParams* __restri
               in_grid(y, p->box[1], ny) && in_grid(z, p->box[2], nz)))
             atomicAnd(&fp[f].regular, 0);
         cell_id[(size_t)f * n_atoms + i] = (unsigned)c;
-        atomicAdd(&cell_cnt[p->cell_base + c], 1);
+        // rank_out (pair path): the atom's rank inside its cell, so that the scatter needs no second
+        // atomic per atom (it was bound by their latency); else a plain RED, no value comes back
+        if (rank_out)
+            rank_out[(size_t)f * n_atoms + i] =
+                (unsigned long long)atomicAdd(&cell_cnt[p->cell_base + c], 1);
+        else
+            atomicAdd(&cell_cnt[p->cell_base + c], 1);
         ax = __double2float_ru(fabs(x));
         ay = __double2float_ru(fabs(y));
         az = __double2float_ru(fabs(z));
@@ -848,7 +855,8 @@ __global__ void __launch_bounds__(256)
 cell_scatter_local_kernel(const T* __restrict__ pos, int n_atoms,
                           const FrameParams* __restrict__ fp, const unsigned* __restrict__ cell_id,
                           int* __restrict__ cell_cnt, const int* __restrict__ cell_start,
-                          float4* __restrict__ sorted, unsigned* __restrict__ slot_cell) {
+                          float4* __restrict__ sorted, unsigned* __restrict__ slot_cell,
+                          unsigned long long* __restrict__ rank_io = nullptr) {
     const int f = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_atoms) return;
@@ -856,7 +864,13 @@ cell_scatter_local_kernel(const T* __restrict__ pos, int n_atoms,
     const size_t a = (size_t)f * n_atoms + i;
     const int c = (int)cell_id[a];
     const int gc = p->cell_base + c;
-    const int slot = cell_start[gc] + atomicSub(&cell_cnt[gc], 1) - 1;
+    int slot;
+    if (rank_io) {   // rank from cell_assign_kernel; the word becomes the pair accumulator (zero)
+        slot = cell_start[gc] + (int)rank_io[a];
+        rank_io[a] = 0ull;
+    } else {
+        slot = cell_start[gc] + atomicSub(&cell_cnt[gc], 1) - 1;
+    }
     const int ny = p->ncell[1], nz = p->ncell[2];
     const int ck[3] = {c / (ny * nz), (c / nz) % ny, c % nz};
     float out[3];
@@ -1732,14 +1746,15 @@ static int lens_direct_impl(const void* d_pos, int n_frames, int n_atoms, const 
     DSG_CUDA_CHECK(cudaMemcpyAsync(d_fp, fps.data(), sizeof(FrameParams) * n_frames,
                                    cudaMemcpyHostToDevice, st));
     DSG_CUDA_CHECK(cudaMemsetAsync(cnt, 0, 4 * (size_t)L.total_cells, st));
-    DSG_CUDA_CHECK(cudaMemsetAsync(acc, 0, 8 * (size_t)n_frames * n_atoms, st));
+    // the accumulator words first carry the rank of every atom inside its cell (assign -> scatter),
+    // the scatter leaves them zero for the pair kernel: no memset, no second atomic per atom
     dim3 agrid((n_atoms + 255) / 256, n_frames);
-    cell_assign_kernel<T><<<agrid, 256, 0, st>>>((const T*)d_pos, n_atoms, d_fp, cid, cnt);
+    cell_assign_kernel<T><<<agrid, 256, 0, st>>>((const T*)d_pos, n_atoms, d_fp, cid, cnt, acc);
     DSG_LAUNCH_CHECK("cell_assign_kernel");
     rc = run_scan(cnt, L.total_cells, 1, start, tile_tmp, nullptr, st);
     if (rc) return rc;
     cell_scatter_local_kernel<T><<<agrid, 256, 0, st>>>((const T*)d_pos, n_atoms, d_fp, cid, cnt,
-                                                        start, sorted, slot_cell);
+                                                        start, sorted, slot_cell, acc);
     DSG_LAUNCH_CHECK("cell_scatter_local_kernel");
     frame_finalize_kernel<<<(n_frames + 127) / 128, 128, 0, st>>>(d_fp, n_frames, r_cut, r2);
     DSG_LAUNCH_CHECK("frame_finalize_kernel");
