@@ -898,7 +898,7 @@ constexpr int kListWarps = DSG_SOAP_LIST_WARPS;
 // soap_spectrum_kernel is the frame-sequential one).
 template <int LT, int S0, int S1, int S2, int S3, bool SPLIT, bool LIST, bool SEQ = false>
 __global__ void __launch_bounds__(
-    DSG_SOAP_MMA ? 128 : ((LIST && S0 <= 20) ? 32 * kListWarps : 64),
+    DSG_SOAP_MMA ? 32 * kListWarps : ((LIST && S0 <= 20) ? 32 * kListWarps : 64),
     // tensor path: four warps share the 16 KB exponential table; 3 blocks per SM (168 registers)
     // up to l_max = 8, 2 blocks (255 registers: 40 / 56 accumulator registers more) beyond
     DSG_SOAP_MMA ? (LT <= 8 ? DSG_SOAP_MMA_BLOCKS_L8 : DSG_SOAP_MMA_BLOCKS_L10)
@@ -2353,7 +2353,7 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
     const size_t shared_tables =
         8 * ((size_t)kExpTabDoubles +
              (split ? 0 : (size_t)a.bmat_smem_doubles + (size_t)a.epi_smem_doubles));
-    int warps = DSG_SOAP_MMA ? 4 : 2;
+    int warps = DSG_SOAP_MMA ? kListWarps : 2;
     while (warps > 1 && per_warp * warps + shared_tables > 227 * 1024) warps >>= 1;
     const size_t smem = per_warp * warps + shared_tables + DSG_SOAP_EXTRA_SMEM;  // (occupancy probe)
     // list-mode consumer: smaller per-warp part, four warps share the block tables
