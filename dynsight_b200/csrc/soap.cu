@@ -417,7 +417,10 @@ __constant__ double kExpPoly[4] = {   // Chebyshev-economised cubic of e^u on |u
 };
 #else
 constexpr int kExpTab = 128;
-constexpr int kExpRep = 16;
+#ifndef DSG_SOAP_EXP_REP
+#define DSG_SOAP_EXP_REP 16
+#endif
+constexpr int kExpRep = DSG_SOAP_EXP_REP;
 constexpr int kExpHiShift = 13;                      // 20 - log2(kExpTab)
 constexpr double kExpScale = 184.6649652337873;      // 128 * log2(e)
 __constant__ double kExpPoly[4] = {
