@@ -393,5 +393,26 @@ def test_pipeline_one_pass_equals_the_separate_calls(balls7):
             # SOAP sums run in cell order, and the order of atoms inside a cell (atomic scatter)
             # differs from launch to launch: equal to rounding, not bit for bit
             assert np.abs(res["timesoap"] - want_ts).max() < 1e-12
+    # default batch size: a short trajectory is uploaded before the jobs are set up and the LENS
+    # kernels are enqueued before the SOAP job exists (the early path of the pipeline); also with a
+    # sub-selection, a frame slice, LENS only and timeSOAP only
+    for kw in (dict(), dict(selection="name O"), dict(trajslice=slice(1, 8)),
+               dict(centers="name C", trajslice=slice(0, 9, 2))):
+        res = pipeline.descriptors_from_trajectory(uni, lens_r_cut=4.0, soap_r_cut=4.5, soapnmax=4,
+                                                   soaplmax=4, coord_number=True, **kw)  # fmt: skip
+        assert np.array_equal(res["lens"], dlens.compute_lens(uni, 4.0, **kw))
+        trj_kw = {k: v for k, v in kw.items() if k != "trajslice"}
+        _, nc = Trj(uni).with_slice(kw.get("trajslice")).get_coord_number(r_cut=4.0, **trj_kw)
+        assert np.array_equal(res["coord_number"], nc.dataset)
+        want_ts = dsoap.timesoap_from_trajectory(uni, 4.5, 4, 4, as_numpy=True, **kw)
+        assert np.abs(res["timesoap"] - want_ts).max() < 1e-12
+    only_lens = pipeline.descriptors_from_trajectory(uni, lens_r_cut=4.0)
+    assert set(only_lens) == {"lens"}
+    assert np.array_equal(only_lens["lens"], dlens.compute_lens(uni, 4.0))
+    only_ts = pipeline.descriptors_from_trajectory(uni, soap_r_cut=4.5, soapnmax=4, soaplmax=4)
+    assert set(only_ts) == {"timesoap"}
+    assert np.abs(only_ts["timesoap"] - dsoap.timesoap_from_trajectory(uni, 4.5, 4, 4, as_numpy=True)).max() < 1e-12
     with pytest.raises(ValueError, match="nothing to compute"):
         pipeline.descriptors_from_trajectory(uni)
+    with pytest.raises(ValueError, match="delay value outside bounds"):
+        pipeline.descriptors_from_trajectory(uni, soap_r_cut=4.5, delay=9)
