@@ -1980,6 +1980,25 @@ static bool soap_split(int n_species, int n_max) {
 
 static double soap_radius(double r_cut) { return r_cut + std::sqrt(-2.0 * std::log(1e-3)); }
 
+// Shared memory of soap_spectrum_mma_kernel: tables + partial sums + one (fused: two) buffers of
+// primitive sums, and -- fused with delay = 1, if a block then still fits twice per SM -- the ring
+// of previous spectra: 64 doubles per (l, species pair).  ring_in_smem: no global ring is needed.
+constexpr int kSpecWarpsHost = 4;
+static bool soap_spectrum_mma_applies(int n_species, int n_max) {
+    return DSG_SOAP_MMA && soap_split(n_species, n_max) && n_max <= 8 && n_species <= 4;
+}
+static size_t soap_spectrum_mma_smem(int n_species, int n_max, int l_max, bool seq, int delay,
+                                     bool* ring_in_smem) {
+    const size_t n_lm = (size_t)(l_max + 1) * (l_max + 1);
+    const size_t g_stride = ((size_t)n_species * n_lm * n_max + 1) & ~(size_t)1;
+    const size_t tab_bytes =
+        8 * ((size_t)(l_max + 1) * 96 + 4 * kSpecWarpsHost + (seq ? 2 : 1) * g_stride);
+    const size_t ring_bytes = 8 * (size_t)(l_max + 1) * (n_species * (n_species + 1) / 2) * 64;
+    const bool rs = seq && delay == 1 && tab_bytes + ring_bytes <= 100 * 1024;
+    if (ring_in_smem) *ring_in_smem = rs;
+    return tab_bytes + (rs ? ring_bytes : 0);
+}
+
 // delay > 0: layout of the fused SOAP -> timeSOAP call (dsg_soap_timesoap)
 static int soap_layout(int n_frames, int n_atoms, int n_cent, int n_species, int n_max, int l_max,
                        const double* h_box, double r_cut, SoapLayout* L,
@@ -2118,7 +2137,13 @@ static int soap_layout(int n_frames, int n_atoms, int n_cent, int n_species, int
         L->seq_run = (int)run;
         L->n_runs = (int)((pairs + run - 1) / run);
         L->off_slot_of = take(4 * fa);
-        L->off_ring = take(8 * (size_t)L->n_runs * n_cent * delay * ((size_t)n_feat + 1));
+        // (the split-mode tensor-path spectrum kernel keeps a delay-1 ring in shared memory: 6.6 GB of
+        // workspace less at cfg4)
+        bool ring_in_smem = false;
+        if (soap_spectrum_mma_applies(n_species, n_max))
+            soap_spectrum_mma_smem(n_species, n_max, l_max, true, delay, &ring_in_smem);
+        if (!ring_in_smem)
+            L->off_ring = take(8 * (size_t)L->n_runs * n_cent * delay * ((size_t)n_feat + 1));
     }
     L->bytes = o;
     return DSG_OK;
@@ -2441,16 +2466,10 @@ static int soap_impl(const T* d_pos, const int32_t* d_species, const int32_t* d_
 #undef DSG_SOAP_LAUNCH
 #undef DSG_SOAP_LAUNCH_ONE
     DSG_LAUNCH_CHECK("soap_kernel");
-    if (split && DSG_SOAP_MMA && n_max <= 8 && n_species <= 4) {
-        // tables + partial sums + (delay = 1) the ring: 64 doubles per (l, species pair)
-        // tables + partial sums + one (SEQ: two) buffers of primitive sums + (delay = 1) the ring:
-        // 64 doubles per (l, species pair)
-        const size_t g_stride = ((size_t)n_species * n_lm * n_max + 1) & ~(size_t)1;
-        const size_t tab_bytes =
-            8 * ((size_t)(l_max + 1) * 96 + 4 * kSpecWarps + (seq ? 2 : 1) * g_stride);
-        const size_t ring_bytes = 8 * (size_t)(l_max + 1) * (n_species * (n_species + 1) / 2) * 64;
-        const bool ring_smem = seq && delay == 1 && tab_bytes + ring_bytes <= 100 * 1024;
-        const size_t ssm = tab_bytes + (ring_smem ? ring_bytes : 0);
+    if (soap_spectrum_mma_applies(n_species, n_max)) {
+        static_assert(kSpecWarps == kSpecWarpsHost, "spectrum kernel block width");
+        bool ring_smem = false;
+        const size_t ssm = soap_spectrum_mma_smem(n_species, n_max, l_max, seq, delay, &ring_smem);
         dim3 sgrid(n_cent, seq ? L.n_runs : n_frames);
 #define DSG_SPEC_LAUNCH_ONE(S, SEQ, RS)                                                           \
     do {                                                                                          \
