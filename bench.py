@@ -795,7 +795,7 @@ def soap_cfg4_section(engine, dev, hbm_peak: float, fp64_peak_tflops: float, no_
     ts_out = torch.empty((n, n_frames - DELAY), dtype=torch.float64, device=dev)
     # primitive sums between the accumulate and the spectrum kernel: 23 KB per centre-frame; the
     # spectra (26.4 KB per centre-frame) only ever exist in the warps' rings
-    batch = 12
+    batch = 17   # 2 batches of 17 frames (one shared): 5.8 GB of primitive sums per frame
 
     def run() -> int:
         done = 0
