@@ -304,3 +304,60 @@ def test_trj_get_slice_keeps_coordinates_only(balls7):
     assert np.array_equal(sub.get_coordinates("all"), balls7["positions"][3:40:7])
     assert sub.universe.trajectory.ts.dimensions is None
     assert sub.universe.select_atoms("name C3").n_atoms == 1
+
+
+def test_c_abi_limits_are_refused_before_any_cuda_call():
+    """The limits the header states are checked on the host: n_frames * n_atoms
+    below 2^31 per batch, at most 65 535 frames per batch, SOAP search radius below 37 A, basis
+    sizes, species count, positive boxes, delay inside the batch -- each with its error code and a
+    message, and the fused call's workspace has no global ring where the spectrum kernel keeps it
+    in shared memory."""
+    from dynsight_b200 import _lib
+
+    lib = _lib.load()
+    n = ctypes.c_size_t(0)
+    box1 = np.array([60.0, 60.0, 60.0])
+    ok = lib.dsg_soap_workspace_bytes(1, 1000, 1000, 1, 8, 8, box1.ctypes.data, 5.0, ctypes.byref(n))
+    assert ok == 0 and n.value > 0
+    err_invalid, err_unsupported, err_overflow = -1, -4, -5
+    # n_frames * n_atoms >= 2^31
+    box_many = np.tile(box1, (4, 1))
+    assert lib.dsg_soap_workspace_bytes(4, 600_000_000, 10, 1, 8, 8, box_many.ctypes.data, 5.0,
+                                        ctypes.byref(n)) == err_overflow
+    assert b"2^31" in lib.dsg_last_error()
+    # more than 65 535 frames in one batch
+    assert lib.dsg_soap_workspace_bytes(70_000, 10, 10, 1, 8, 8, None, 5.0,
+                                        ctypes.byref(n)) == err_invalid
+    # search radius above 37 A (gamma r^2 would leave the range of the branch-free exponential)
+    assert lib.dsg_soap_workspace_bytes(1, 10, 10, 1, 8, 8, None, 40.0,
+                                        ctypes.byref(n)) == err_unsupported
+    assert b"37" in lib.dsg_last_error()
+    # basis and species limits, DScribe's r_cut > 1
+    for args in ((1, 33, 8), (1, 8, 13), (17, 8, 8)):
+        assert lib.dsg_soap_workspace_bytes(1, 10, 10, args[0], args[1], args[2], None, 5.0,
+                                            ctypes.byref(n)) == err_unsupported
+    assert lib.dsg_soap_workspace_bytes(1, 10, 10, 1, 8, 8, None, 0.9,
+                                        ctypes.byref(n)) == err_invalid
+    # a periodic frame needs a positive box
+    bad_box = np.array([60.0, 0.0, 60.0])
+    assert lib.dsg_soap_workspace_bytes(1, 10, 10, 1, 8, 8, bad_box.ctypes.data, 5.0,
+                                        ctypes.byref(n)) == err_invalid
+    # fused call: delay inside the batch
+    box3 = np.tile(box1, (3, 1))
+    assert lib.dsg_soap_timesoap_workspace_bytes(3, 100, 100, 1, 8, 8, box3.ctypes.data, 5.0, 3,
+                                                 ctypes.byref(n)) == err_invalid
+    assert lib.dsg_soap_timesoap_workspace_bytes(3, 100, 100, 1, 8, 8, box3.ctypes.data, 5.0, 0,
+                                                 ctypes.byref(n)) == err_invalid
+    # three species, delay 1: the previous spectra live in shared memory (no ring in the workspace);
+    # delay 2: a global ring of 2 x (n_feat + 1) doubles per centre
+    m1, m2 = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    box9 = np.tile(box1, (9, 1))
+    assert lib.dsg_soap_timesoap_workspace_bytes(9, 2000, 2000, 3, 8, 10, box9.ctypes.data, 5.0, 1,
+                                                 ctypes.byref(m1)) == 0
+    assert lib.dsg_soap_timesoap_workspace_bytes(9, 2000, 2000, 3, 8, 10, box9.ctypes.data, 5.0, 2,
+                                                 ctypes.byref(m2)) == 0
+    ring2 = 8 * 2000 * 2 * (3300 + 1)
+    assert m2.value - m1.value >= ring2 - 4096
+    # LENS pair path: same overflow rule
+    assert lib.dsg_lens_direct_workspace_bytes(4, 600_000_000, box_many.ctypes.data, 5.0,
+                                               ctypes.byref(n)) < 0
