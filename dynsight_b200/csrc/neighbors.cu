@@ -1414,7 +1414,10 @@ struct PairArgs {
     unsigned long long* acc;       // (F, N): count | intersection << 32
 };
 
-constexpr int kPairThreads = 128;
+#ifndef DSG_PAIR_THREADS
+#define DSG_PAIR_THREADS 128
+#endif
+constexpr int kPairThreads = DSG_PAIR_THREADS;
 constexpr int kPairCap = 32;   // staged hits per thread; a longer half row is settled inline
 #ifndef DSG_PAIR_MIN_BLOCKS
 #define DSG_PAIR_MIN_BLOCKS 6
